@@ -1,0 +1,174 @@
+/* surfh_b200 -- C ABI of the B200-native LMM instrument operator and CG primitives.
+ *
+ * This is the drop-in boundary for ONE hot path of sidiso/surfh: the linear-mixing-model
+ * MIRI-MRS operator `spectroSigRLSCT` (forward / adjoint / fwadj) and the vector work of the
+ * conjugate-gradient loop that drives it.  The reference has no FFI for this path (it is pure
+ * Python + Cython + JAX); each entry point below names the reference interface it replaces
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SURFH_E* code otherwise; the message is
+ *     available from surfh_last_error(); no exception crosses the boundary;
+ *   - one handle per GPU (the device current at surfh_create); a handle is not thread-safe;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it, nothing synchronises unless stated;
+ *   - "real" means the handle's dtype: SURFH_F64 -> double, SURFH_F32 -> float; complex means
+ *     interleaved (re, im) pairs of that type;
+ *   - pointers documented as [device] must be device memory of the handle's GPU and are
+ *     caller-owned; pointers documented as [any] may be host or device (cudaMemcpyDefault);
+ *     descriptor tables are copied at the call, the caller may free them afterwards;
+ *   - there is no CPU fallback: without a CUDA device surfh_create fails.
+ */
+#ifndef SURFH_B200_H
+#define SURFH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SURFH_ABI_VERSION 1
+
+enum { SURFH_F32 = 0, SURFH_F64 = 1 };
+
+/* Adjoint flavour.  The reference's `gridding_t` (spectroModelChannel.py:180-199) is a second
+ * bilinear interpolation, not the transpose of `gridding`; SURFH_ADJ_REFERENCE reproduces it,
+ * SURFH_ADJ_EXACT applies the true transpose (dot-test to rounding). */
+enum { SURFH_ADJ_EXACT = 0, SURFH_ADJ_REFERENCE = 1 };
+
+enum {
+    SURFH_OK = 0,
+    SURFH_EINVAL = -1,   /* bad argument / inconsistent descriptor          */
+    SURFH_ECUDA = -2,    /* CUDA runtime error                              */
+    SURFH_ECUFFT = -3,   /* cuFFT error                                     */
+    SURFH_ESTATE = -4,   /* call sequence violated (e.g. not finalised)     */
+    SURFH_ENOMEM = -5
+};
+
+typedef struct surfh_model surfh_model;
+typedef surfh_model* surfh_handle;
+
+/* Whole-model description: what spectroSigRLSCT.__init__ receives
+ * (surfh/Models/spectroModel.py:40-135) minus the per-band part. */
+typedef struct {
+    int32_t dtype;        /* SURFH_F32 / SURFH_F64: arithmetic type of every kernel           */
+    int32_t n_templates;  /* K; 0 = no LMM (templates=None, input is the [n_lambda,N,N] cube) */
+    int32_t n_alpha;      /* cube pixels along alpha (axis 0)                                 */
+    int32_t n_beta;       /* cube pixels along beta  (axis 1, contiguous)                     */
+    int32_t n_lambda;     /* cube wavelengths                                                 */
+    int32_t chunk;        /* wavelengths per pipeline chunk (0 = library default)             */
+    const double* templates; /* [any] [K, n_lambda] row-major, NULL when K == 0               */
+} surfh_model_desc;
+
+/* Sparse table of one adjoint flavour for one band, pointings merged: cube pixel -> weighted
+ * entries of the slit-space vector G[(p, s, a, b)].  Rows are the cube pixels that receive
+ * anything (compact list), in increasing pixel order. */
+typedef struct {
+    int32_t n_rows;
+    int64_t nnz;
+    const int32_t* row_pixel; /* [n_rows]   flat cube pixel i*n_beta + j                      */
+    const int64_t* row_ptr;   /* [n_rows+1]                                                   */
+    const int32_t* col;       /* [nnz]      ((p*S + s)*na + a)*nb + b                         */
+    const double* val;        /* [nnz]                                                        */
+} surfh_csr;
+
+/* One IFU band: everything `Channel.__init__` derives
+ * (surfh/Models/spectroModelChannel.py:27-108) flattened into tables. */
+typedef struct {
+    int32_t n_pointing;  /* P                                                                  */
+    int32_t n_slit;      /* S                                                                  */
+    int32_t na;          /* detector pixels along a slit = ceil(npix_alpha / srf)              */
+    int32_t nb;          /* cube pixels across a slit                                          */
+    int32_t srf;         /* super-resolution factor along alpha                                */
+    int32_t local_a;     /* A: local grid rows                                                 */
+    int32_t local_b;     /* B: local grid columns                                              */
+    int32_t wave_start;  /* first cube wavelength of the band (wslice.start)                   */
+    int32_t n_wave;      /* Lambda  = wslice.stop - wslice.start                               */
+    int32_t n_det;       /* Lambda' = detector wavelength samples                              */
+    int64_t out_offset;  /* element offset of this band in the caller's y vector (_idx[band])  */
+    const int32_t* slit_a0;   /* [S]      first local row of the slit                          */
+    const int32_t* slit_b0;   /* [S]      first local column of the slit                       */
+    const double* slit_w;     /* [S, nb]  beta edge weights (Slicer.get_slit_weights)          */
+    const double* lsf;        /* [n_det, n_wave, nb] spectral response (SpectralBlur.psfs)     */
+    const int32_t* grid_base; /* [P, A*B] flat cube index of the upper-left bilinear tap       */
+    const double* grid_frac;  /* [P, A*B, 2] normalised distances (t_alpha, t_beta)            */
+    surfh_csr adj_exact;      /* transpose of gather                                           */
+    surfh_csr adj_reference;  /* the reference's gridding_t chain                              */
+} surfh_band_desc;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int surfh_abi_version(void);
+/* replaces spectroSigRLSCT.__init__ (spectroModel.py:40-135) */
+int surfh_create(const surfh_model_desc* desc, surfh_handle* out);
+/* upload OTF planes [l_start, l_start+l_count) : complex128 [l_count, n_alpha, n_beta/2+1]
+ * ([any]; converted to the handle dtype).  Replaces `self.sotf = sotf` (spectroModel.py:51). */
+int surfh_set_otf(surfh_handle h, int32_t l_start, int32_t l_count, const void* otf_c128);
+/* replaces Channel.__init__ (spectroModelChannel.py:27-108); bands keep the order of calls */
+int surfh_add_band(surfh_handle h, const surfh_band_desc* band);
+/* build FFT plans and workspaces; must precede any compute call */
+int surfh_finalize(surfh_handle h);
+void surfh_destroy(surfh_handle h);
+const char* surfh_last_error(surfh_handle h); /* h may be NULL: error of the last failed create */
+
+/* ---- shapes ------------------------------------------------------------------------------ */
+int64_t surfh_input_size(surfh_handle h);  /* K*N*N, or n_lambda*N*N without LMM               */
+int64_t surfh_output_size(surfh_handle h); /* highest out_offset + band size over added bands  */
+int64_t surfh_workspace_bytes(surfh_handle h);
+
+/* ---- operator, device buffers ------------------------------------------------------------ */
+/* y[out_offset_b ...] = H_b x for every added band.  x: [device] real [K,N,N]; y: [device] real.
+ * Replaces spectroSigRLSCT.forward (spectroModel.py:158-170). */
+int surfh_forward(surfh_handle h, const void* x, void* y, void* stream);
+/* x = sum_b H_b^T y_b (mode: SURFH_ADJ_*).  Replaces spectroSigRLSCT.adjoint (:173-185). */
+int surfh_adjoint(surfh_handle h, const void* y, void* x, int32_t mode, void* stream);
+/* out = H^T H x without leaving the device; y_scratch: [device] real [output_size] or NULL to use
+ * an internal buffer.  Replaces aljabr.LinOp.fwadj as inherited by spectroSigRLSCT. */
+int surfh_fwadj(surfh_handle h, const void* x, void* out, int32_t mode, void* y_scratch, void* stream);
+/* cube = T x in float32, result export.  Replaces spectroSigRLSCT.mapsToCube
+ * (spectroModel.py:190-192 -> cythons_files.pyx:424-440).  maps: [device] real; cube: [device] float */
+int surfh_maps_to_cube(surfh_handle h, const void* maps, float* cube, void* stream);
+
+/* ---- operator, host buffers (the reference-facing call: numpy in, numpy out) --------------- */
+/* double host arrays whatever the handle dtype; copies through pinned staging, synchronises. */
+int surfh_forward_host(surfh_handle h, const double* x, double* y);
+int surfh_adjoint_host(surfh_handle h, const double* y, double* x, int32_t mode);
+
+/* ---- conjugate-gradient vector work (qmm.lcg as called from fusion_CT.py:194-232) ---------- */
+/* Scalars live in a caller-owned [device] double array `s` of at least SURFH_CG_NSCALARS + max_iter
+ * + 2 entries: s[0]=rho=<r,r>  s[1]=<d,q>  s[2]=alpha  s[3]=beta  s[4]=iteration counter,
+ * s[SURFH_CG_NSCALARS + i] = grad_norm history.  No call below synchronises with the host. */
+#define SURFH_CG_NSCALARS 8
+/* q = mu_s*q + mu_r*(D_r^T D_r + D_c^T D_c) d ; s[1] = <d,q>.  n_maps*[n_alpha,n_beta] vectors.
+ * Replaces the NpDiff_r / NpDiff_c hessp terms (fusion_CT.py:16-43) and the <d,Qd> dot. */
+int surfh_cg_regularise_dot(surfh_handle h, const void* d, void* q, double mu_s, double mu_r, double* s,
+                            void* stream);
+/* r = b - q ; d = r ; s[0] = <r,r> ; history[0] = s[0] ; counter = 0 (lcg initialisation) */
+int surfh_cg_start(surfh_handle h, const void* b, const void* q, void* r, void* d, double* s, void* stream);
+/* alpha = s[0]/s[1]; x += alpha d; r -= alpha q; rho' = <r,r>; beta = rho'/rho; d = r + beta d;
+ * s[0] = rho'; history appended.  One lcg iteration after q = Q d. */
+int surfh_cg_update(surfh_handle h, void* x, void* r, void* d, const void* q, double* s, void* stream);
+/* same but the residual is recomputed exactly: r = b - q_x where q_x = Q x_new is supplied by the
+ * caller in a second phase (lcg's periodic refresh): phase 0: x += alpha d.  phase 1: r = b - qx;
+ * rho' ; beta ; d = r + beta d. */
+int surfh_cg_refresh(surfh_handle h, int32_t phase, void* x, void* r, void* d, const void* b, const void* qx,
+                     double* s, void* stream);
+/* s_out[0] = sum (y - hx)^2 over n elements, s_out[1] = sum (D_r x)^2 + (D_c x)^2  (criterion pieces,
+ * fusion_CT.py:242-265).  hx/y may be NULL to skip the data term, x may be NULL to skip the prior. */
+int surfh_criterion_terms(surfh_handle h, const void* y, const void* hx, int64_t n, const void* x, double* s_out,
+                          void* stream);
+
+/* ---- instrumentation --------------------------------------------------------------------- */
+/* number of kernels (own + cuFFT exec calls) this handle has launched since creation */
+int64_t surfh_launch_count(surfh_handle h);
+int64_t surfh_own_launch_count(surfh_handle h);
+/* per-stage CUDA-event timing of the NEXT forward/adjoint call pair: enable, run, then read.
+ * names/ms arrays of capacity `cap`; returns number of stages filled (synchronises). */
+int surfh_profile_enable(surfh_handle h, int32_t on);
+int surfh_profile_read(surfh_handle h, int32_t cap, const char** names, float* ms, double* bytes, double* flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURFH_B200_H */

@@ -1,0 +1,943 @@
+// C ABI of surfh_b200 (see include/surfh_b200.h): handle, tables, cuFFT plans, the forward /
+// adjoint pipelines and the CG vector primitives.  sm_100a only, no CPU fallback.
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/surfh_b200.h"
+#include "common.cuh"
+#include "kernels_cg.cuh"
+#include "kernels_gemm.cuh"
+#include "kernels_lmm.cuh"
+#include "kernels_slit.cuh"
+
+namespace surfh {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define SURFH_CUDA(expr)                                                                                 \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            throw Error(SURFH_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                \
+    } while (0)
+#define SURFH_FFT(expr)                                                                                  \
+    do {                                                                                                 \
+        cufftResult r_ = (expr);                                                                         \
+        if (r_ != CUFFT_SUCCESS) throw Error(SURFH_ECUFFT, std::string(#expr) + ": cufft error " + std::to_string((int)r_)); \
+    } while (0)
+#define SURFH_REQUIRE(cond, msg)                                                                         \
+    do {                                                                                                 \
+        if (!(cond)) throw Error(SURFH_EINVAL, std::string(msg));                                        \
+    } while (0)
+
+static thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    void alloc(size_t n) {
+        release();
+        if (n == 0) return;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) throw Error(SURFH_ENOMEM, "cudaMalloc(" + std::to_string(n) + " bytes): " + cudaGetErrorString(e));
+        bytes = n;
+    }
+    void ensure(size_t n) {
+        if (bytes < n) alloc(n);
+    }
+    template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+template <typename U, typename V> static void upload_converted(DevBuf& dst, const V* src, size_t n) {
+    std::vector<U> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = (U)src[i];
+    dst.alloc(n * sizeof(U));
+    SURFH_CUDA(cudaMemcpy(dst.p, tmp.data(), n * sizeof(U), cudaMemcpyHostToDevice));
+}
+
+enum Stage {
+    ST_RFFT_MAPS = 0, ST_LMM_OTF_FWD, ST_IRFFT_CUBE, ST_SLIT_GATHER, ST_GEMM_FWD,
+    ST_GEMM_ADJ, ST_SLIT_SCATTER, ST_RFFT_CUBE, ST_LMM_OTF_ADJ, ST_IRFFT_MAPS, ST_MEMSET, ST_CG, ST_COUNT
+};
+static const char* kStageNames[ST_COUNT] = {
+    "cufft_rfft_maps", "lmm_otf_fwd", "cufft_irfft_cube", "slit_gather", "spectral_gemm_fwd",
+    "spectral_gemm_adj", "slit_scatter", "cufft_rfft_cube", "lmm_otf_adj", "cufft_irfft_maps", "memset", "cg_fused"};
+
+}  // namespace surfh
+
+using namespace surfh;
+
+// ------------------------------------------------------------------------------------------------
+struct surfh_model {
+    int dtype = SURFH_F64;
+    int K = 0, Na = 0, Nb = 0, Nl = 0, Nh = 0, chunk = 0;
+    size_t plane = 0, nf = 0, nfp = 0;
+    bool finalized = false;
+    std::string last_error;
+    int64_t launches = 0, own_launches = 0;
+    int device = 0;
+
+    // profiling
+    bool profiling = false;
+    struct Rec { int stage; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    double stage_bytes[ST_COUNT] = {0}, stage_flops[ST_COUNT] = {0};
+    int stage_launches[ST_COUNT] = {0};
+
+    virtual ~surfh_model() {
+        for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    }
+    virtual void set_otf(int l_start, int l_count, const void* src) = 0;
+    virtual void add_band(const surfh_band_desc* b) = 0;
+    virtual void finalize() = 0;
+    virtual int64_t input_size() const = 0;
+    virtual int64_t output_size() const = 0;
+    virtual int64_t workspace_bytes() const = 0;
+    virtual void forward(const void* x, void* y, cudaStream_t st) = 0;
+    virtual void adjoint(const void* y, void* x, int mode, cudaStream_t st) = 0;
+    virtual void fwadj(const void* x, void* out, int mode, void* yscratch, cudaStream_t st) = 0;
+    virtual void maps_to_cube(const void* maps, float* cube, cudaStream_t st) = 0;
+    virtual void forward_host(const double* x, double* y) = 0;
+    virtual void adjoint_host(const double* y, double* x, int mode) = 0;
+    virtual void cg_regularise_dot(const void* d, void* q, double mu_s, double mu_r, double* s, cudaStream_t st) = 0;
+    virtual void cg_start(const void* b, const void* q, void* r, void* d, double* s, cudaStream_t st) = 0;
+    virtual void cg_update(void* x, void* r, void* d, const void* q, double* s, cudaStream_t st) = 0;
+    virtual void cg_refresh(int phase, void* x, void* r, void* d, const void* b, const void* qx, double* s,
+                            cudaStream_t st) = 0;
+    virtual void criterion_terms(const void* y, const void* hx, int64_t n, const void* x, double* out,
+                                 cudaStream_t st) = 0;
+
+    struct Scope {
+        surfh_model* m; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+        Scope(surfh_model* m_, int stage_, cudaStream_t st_, double bytes, double flops, int n_launch, bool own)
+            : m(m_), stage(stage_), st(st_) {
+            m->launches += n_launch;
+            if (own) m->own_launches += n_launch;
+            if (m->profiling) {
+                cudaEventCreate(&a);
+                cudaEventCreate(&b);
+                cudaEventRecord(a, st);
+                m->stage_bytes[stage] += bytes;
+                m->stage_flops[stage] += flops;
+                m->stage_launches[stage] += n_launch;
+            }
+        }
+        ~Scope() {
+            if (m->profiling) {
+                cudaEventRecord(b, st);
+                m->recs.push_back({stage, a, b});
+            }
+        }
+    };
+};
+
+namespace surfh {
+
+template <typename T> struct BandT {
+    int P, S, na, nb, srf, A, B, l0, nl, nd, ncol, Nn, KB;
+    int64_t out_offset, out_size;
+    DevBuf slit_a0, slit_b0, slit_w, lsf, grid_base, grid_frac;
+    DevBuf csr_pix[2], csr_ptr[2], csr_col[2], csr_val[2];
+    int csr_rows[2] = {0, 0};
+    int64_t csr_nnz[2] = {0, 0};
+    DevBuf t_ident, t_wrow, t_gK, t_gN, t_yM, t_yN;
+    DevBuf G;  // [nl][ncol] slit-space vector (forward G / adjoint Gt)
+
+    SlitTables<T> slit_tables() const {
+        SlitTables<T> t;
+        t.slit_a0 = slit_a0.as<int32_t>();
+        t.slit_b0 = slit_b0.as<int32_t>();
+        t.slit_w = slit_w.as<T>();
+        t.grid_base = grid_base.as<int32_t>();
+        t.grid_frac = grid_frac.as<T>();
+        t.P = P; t.S = S; t.na = na; t.nb = nb; t.srf = srf; t.A = A; t.B = B; t.ncol = ncol;
+        return t;
+    }
+    CsrTable<T> csr(int mode) const {
+        CsrTable<T> c;
+        c.row_pixel = csr_pix[mode].as<int32_t>();
+        c.row_ptr = csr_ptr[mode].as<int64_t>();
+        c.col = csr_col[mode].as<int32_t>();
+        c.val = csr_val[mode].as<T>();
+        c.n_rows = csr_rows[mode];
+        return c;
+    }
+};
+
+template <typename T> struct FftTraits;
+template <> struct FftTraits<float> {
+    static constexpr cufftType R2C = CUFFT_R2C, C2R = CUFFT_C2R;
+    static cufftResult fwd(cufftHandle p, float* in, float2* out) { return cufftExecR2C(p, in, out); }
+    static cufftResult inv(cufftHandle p, float2* in, float* out) { return cufftExecC2R(p, in, out); }
+};
+template <> struct FftTraits<double> {
+    static constexpr cufftType R2C = CUFFT_D2Z, C2R = CUFFT_Z2D;
+    static cufftResult fwd(cufftHandle p, double* in, double2* out) { return cufftExecD2Z(p, in, out); }
+    static cufftResult inv(cufftHandle p, double2* in, double* out) { return cufftExecZ2D(p, in, out); }
+};
+
+// GEMM tile configuration per dtype
+template <typename T> struct GemmCfg;
+template <> struct GemmCfg<double> { static constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4; };
+template <> struct GemmCfg<float> { static constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8; };
+
+template <typename T> struct ModelImpl : surfh_model {
+    using C = cplx_t<T>;
+    DevBuf otf;       // [Nl][nfp] complex
+    DevBuf tpl;       // [K][Nl] real, pre-scaled by 1/(Na*Nb)
+    DevBuf tpl_raw;   // [K][Nl] real, unscaled (maps_to_cube)
+    DevBuf xhat;      // [K][nfp] complex
+    DevBuf spec;      // [chunk][nfp] complex
+    DevBuf cubebuf;   // [chunk][plane] real
+    DevBuf fft_work;
+    DevBuf y_internal, x_stage, y_stage, dbl_stage;
+    DevBuf cg_partial, cg_ticket;
+    std::vector<std::unique_ptr<BandT<T>>> bands;
+    std::vector<std::pair<int, int>> ranges;  // union of band wavelength windows
+    std::map<std::pair<int, int>, cufftHandle> plans;  // (kind, batch) -> plan
+    size_t fft_work_bytes = 0;
+    std::vector<uint8_t> otf_set;
+
+    ~ModelImpl() override {
+        for (auto& kv : plans) cufftDestroy(kv.second);
+    }
+
+    void init(const surfh_model_desc* d) {
+        SURFH_REQUIRE(d->n_alpha > 1 && d->n_beta > 1 && d->n_lambda > 0, "bad cube shape");
+        SURFH_REQUIRE(d->n_templates >= 0 && d->n_templates <= kMaxTemplates, "n_templates must be in [0, 8]");
+        SURFH_CUDA(cudaGetDevice(&device));
+        K = d->n_templates; Na = d->n_alpha; Nb = d->n_beta; Nl = d->n_lambda; Nh = Nb / 2 + 1;
+        plane = (size_t)Na * Nb;
+        nf = (size_t)Na * Nh;
+        nfp = (nf + 15) / 16 * 16;
+        chunk = d->chunk > 0 ? d->chunk : 0;
+        otf.alloc((size_t)Nl * nfp * sizeof(C));
+        SURFH_CUDA(cudaMemset(otf.p, 0, otf.bytes));
+        otf_set.assign(Nl, 0);
+        if (K > 0) {
+            SURFH_REQUIRE(d->templates != nullptr, "templates missing");
+            std::vector<double> host((size_t)K * Nl);
+            SURFH_CUDA(cudaMemcpy(host.data(), d->templates, host.size() * sizeof(double), cudaMemcpyDefault));
+            upload_converted<T>(tpl_raw, host.data(), host.size());
+            const double scale = 1.0 / ((double)Na * (double)Nb);
+            for (auto& v : host) v *= scale;
+            upload_converted<T>(tpl, host.data(), host.size());
+        }
+        cg_partial.alloc(sizeof(double) * 2 * kCgMaxBlocks);
+        cg_ticket.alloc(sizeof(unsigned int));
+        SURFH_CUDA(cudaMemset(cg_ticket.p, 0, sizeof(unsigned int)));
+    }
+
+    void set_otf(int l_start, int l_count, const void* src) override {
+        SURFH_REQUIRE(l_start >= 0 && l_count > 0 && l_start + l_count <= Nl, "otf plane range out of bounds");
+        SURFH_REQUIRE(src != nullptr, "otf pointer is NULL");
+        cudaPointerAttributes attr;
+        const double2* dsrc = nullptr;
+        DevBuf tmp;
+        cudaError_t e = cudaPointerGetAttributes(&attr, src);
+        if (e == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+            dsrc = reinterpret_cast<const double2*>(src);
+        } else {
+            cudaGetLastError();
+            tmp.alloc((size_t)l_count * nf * sizeof(double2));
+            SURFH_CUDA(cudaMemcpy(tmp.p, src, tmp.bytes, cudaMemcpyHostToDevice));
+            dsrc = tmp.as<double2>();
+        }
+        dim3 grid(ceil_div(nfp, 256), l_count);
+        otf_convert_kernel<T><<<grid, 256>>>(dsrc, otf.as<C>() + (size_t)l_start * nfp, nf, nfp, l_count);
+        SURFH_CUDA(cudaGetLastError());
+        SURFH_CUDA(cudaDeviceSynchronize());
+        for (int l = l_start; l < l_start + l_count; ++l) otf_set[l] = 1;
+    }
+
+    static void check_csr(const surfh_csr& c, int64_t npix, int ncol, const char* what) {
+        SURFH_REQUIRE(c.n_rows >= 0 && c.nnz >= 0, std::string(what) + ": negative size");
+        if (c.n_rows == 0) return;
+        SURFH_REQUIRE(c.row_pixel && c.row_ptr && c.col && c.val, std::string(what) + ": NULL table");
+        SURFH_REQUIRE(c.row_ptr[0] == 0 && c.row_ptr[c.n_rows] == c.nnz, std::string(what) + ": row_ptr inconsistent");
+        for (int r = 0; r < c.n_rows; ++r) {
+            SURFH_REQUIRE(c.row_pixel[r] >= 0 && c.row_pixel[r] < npix, std::string(what) + ": pixel out of range");
+            SURFH_REQUIRE(c.row_ptr[r + 1] >= c.row_ptr[r], std::string(what) + ": row_ptr not monotone");
+            SURFH_REQUIRE(r == 0 || c.row_pixel[r] > c.row_pixel[r - 1], std::string(what) + ": rows not strictly increasing");
+        }
+        for (int64_t e = 0; e < c.nnz; ++e)
+            SURFH_REQUIRE(c.col[e] >= 0 && c.col[e] < ncol, std::string(what) + ": column out of range");
+    }
+
+    void add_band(const surfh_band_desc* d) override {
+        SURFH_REQUIRE(!finalized, "add_band after finalize");
+        SURFH_REQUIRE(d->n_pointing > 0 && d->n_slit > 0 && d->na > 0 && d->nb > 0 && d->srf > 0, "bad band sizes");
+        SURFH_REQUIRE(d->local_a > 1 && d->local_b > 1 && d->n_det > 0 && d->n_wave > 0, "bad band sizes");
+        SURFH_REQUIRE(d->wave_start >= 0 && d->wave_start + d->n_wave <= Nl, "band wavelength window outside the cube");
+        SURFH_REQUIRE(d->slit_a0 && d->slit_b0 && d->slit_w && d->lsf && d->grid_base && d->grid_frac, "NULL band table");
+        auto b = std::make_unique<BandT<T>>();
+        b->P = d->n_pointing; b->S = d->n_slit; b->na = d->na; b->nb = d->nb; b->srf = d->srf;
+        b->A = d->local_a; b->B = d->local_b; b->l0 = d->wave_start; b->nl = d->n_wave; b->nd = d->n_det;
+        b->Nn = b->P * b->S * b->na;
+        b->ncol = b->Nn * b->nb;
+        b->KB = b->nl * b->nb;
+        b->out_offset = d->out_offset;
+        b->out_size = (int64_t)b->Nn * b->nd;
+        SURFH_REQUIRE(d->out_offset >= 0, "negative out_offset");
+        SURFH_REQUIRE((int64_t)b->nd * b->KB < (1ll << 31) && (int64_t)b->nl * b->ncol < (1ll << 31) &&
+                          b->out_size < (1ll << 31), "band too large for 32-bit operand offsets");
+        const int AB = b->A * b->B;
+        for (int s = 0; s < b->S; ++s) {
+            SURFH_REQUIRE(d->slit_a0[s] >= 0 && d->slit_a0[s] < b->A, "slit_a0 out of the local grid");
+            SURFH_REQUIRE(d->slit_b0[s] >= 0 && d->slit_b0[s] + b->nb <= b->B, "slit columns out of the local grid");
+        }
+        for (int64_t q = 0; q < (int64_t)b->P * AB; ++q) {
+            const int32_t off = d->grid_base[q];
+            // the reference raises ValueError when a pointing's FoV leaves the cube
+            SURFH_REQUIRE(off >= 0 && off / Nb < Na - 1 && off % Nb < Nb - 1,
+                          "One of the requested xi is out of bounds (a pointing's field of view leaves the cube)");
+        }
+        check_csr(d->adj_exact, (int64_t)plane, b->ncol, "adj_exact");
+        check_csr(d->adj_reference, (int64_t)plane, b->ncol, "adj_reference");
+
+        upload_converted<int32_t>(b->slit_a0, d->slit_a0, b->S);
+        upload_converted<int32_t>(b->slit_b0, d->slit_b0, b->S);
+        upload_converted<T>(b->slit_w, d->slit_w, (size_t)b->S * b->nb);
+        upload_converted<T>(b->lsf, d->lsf, (size_t)b->nd * b->KB);
+        upload_converted<int32_t>(b->grid_base, d->grid_base, (size_t)b->P * AB);
+        upload_converted<T>(b->grid_frac, d->grid_frac, (size_t)b->P * AB * 2);
+        const surfh_csr* cs[2] = {&d->adj_exact, &d->adj_reference};
+        for (int m = 0; m < 2; ++m) {
+            b->csr_rows[m] = cs[m]->n_rows;
+            b->csr_nnz[m] = cs[m]->nnz;
+            if (cs[m]->n_rows == 0) continue;
+            upload_converted<int32_t>(b->csr_pix[m], cs[m]->row_pixel, cs[m]->n_rows);
+            upload_converted<int64_t>(b->csr_ptr[m], cs[m]->row_ptr, (size_t)cs[m]->n_rows + 1);
+            upload_converted<int32_t>(b->csr_col[m], cs[m]->col, cs[m]->nnz);
+            upload_converted<T>(b->csr_val[m], cs[m]->val, cs[m]->nnz);
+        }
+        // GEMM offset tables
+        {
+            const int nmax = std::max(b->KB, b->nd);
+            std::vector<int32_t> v(nmax);
+            for (int i = 0; i < nmax; ++i) v[i] = i;
+            upload_converted<int32_t>(b->t_ident, v.data(), nmax);
+            v.assign(b->nd, 0);
+            for (int i = 0; i < b->nd; ++i) v[i] = i * b->KB;
+            upload_converted<int32_t>(b->t_wrow, v.data(), b->nd);
+            v.assign(b->KB, 0);
+            for (int k = 0; k < b->KB; ++k) v[k] = (k / b->nb) * b->ncol + k % b->nb;
+            upload_converted<int32_t>(b->t_gK, v.data(), b->KB);
+            v.assign(b->Nn, 0);
+            for (int n = 0; n < b->Nn; ++n) v[n] = n * b->nb;
+            upload_converted<int32_t>(b->t_gN, v.data(), b->Nn);
+            v.assign(b->nd, 0);
+            for (int m = 0; m < b->nd; ++m) v[m] = m * b->na;
+            upload_converted<int32_t>(b->t_yM, v.data(), b->nd);
+            v.assign(b->Nn, 0);
+            for (int n = 0; n < b->Nn; ++n) v[n] = (n / b->na) * (b->nd * b->na) + n % b->na;
+            upload_converted<int32_t>(b->t_yN, v.data(), b->Nn);
+        }
+        b->G.alloc((size_t)b->nl * b->ncol * sizeof(T));
+        bands.push_back(std::move(b));
+    }
+
+    cufftHandle plan(int kind, int batch) {
+        auto key = std::make_pair(kind, batch);
+        auto it = plans.find(key);
+        if (it != plans.end()) return it->second;
+        throw Error(SURFH_ESTATE, "internal: FFT plan missing");
+    }
+
+    // kind 0: real planes (dist plane) -> complex planes (dist nfp); kind 1: the inverse
+    void make_plan(int kind, int batch) {
+        auto key = std::make_pair(kind, batch);
+        if (plans.count(key) || batch <= 0) return;
+        cufftHandle p;
+        SURFH_FFT(cufftCreate(&p));
+        SURFH_FFT(cufftSetAutoAllocation(p, 0));
+        int n[2] = {Na, Nb};
+        int rembed[2] = {Na, Nb};
+        int cembed[2] = {Na, Nh};
+        size_t ws = 0;
+        if (kind == 0)
+            SURFH_FFT(cufftMakePlanMany(p, 2, n, rembed, 1, (int)plane, cembed, 1, (int)nfp, FftTraits<T>::R2C, batch, &ws));
+        else
+            SURFH_FFT(cufftMakePlanMany(p, 2, n, cembed, 1, (int)nfp, rembed, 1, (int)plane, FftTraits<T>::C2R, batch, &ws));
+        fft_work_bytes = std::max(fft_work_bytes, ws);
+        plans[key] = p;
+    }
+
+    void finalize() override {
+        SURFH_REQUIRE(!bands.empty(), "no band added");
+        // union of wavelength windows
+        std::vector<std::pair<int, int>> w;
+        for (auto& b : bands) w.emplace_back(b->l0, b->l0 + b->nl);
+        std::sort(w.begin(), w.end());
+        ranges.clear();
+        for (auto& r : w) {
+            if (!ranges.empty() && r.first <= ranges.back().second)
+                ranges.back().second = std::max(ranges.back().second, r.second);
+            else
+                ranges.push_back(r);
+        }
+        for (auto& r : ranges)
+            for (int l = r.first; l < r.second; ++l)
+                SURFH_REQUIRE(otf_set[l], "OTF plane " + std::to_string(l) + " needed by a band was never uploaded");
+        int longest = 0;
+        for (auto& r : ranges) longest = std::max(longest, r.second - r.first);
+        if (chunk <= 0) {
+            // default: bound the two chunk buffers to ~2 GiB
+            const size_t per_l = nfp * sizeof(C) + plane * sizeof(T);
+            chunk = (int)std::max<size_t>(1, std::min<size_t>(512, ((size_t)2 << 30) / per_l));
+        }
+        chunk = std::min(chunk, longest);
+        spec.alloc((size_t)chunk * nfp * sizeof(C));
+        SURFH_CUDA(cudaMemset(spec.p, 0, spec.bytes));
+        cubebuf.alloc((size_t)chunk * plane * sizeof(T));
+        if (K > 0) {
+            xhat.alloc((size_t)K * nfp * sizeof(C));
+            SURFH_CUDA(cudaMemset(xhat.p, 0, xhat.bytes));
+            make_plan(0, K);
+            make_plan(1, K);
+        }
+        for (auto& r : ranges) {
+            const int len = r.second - r.first;
+            if (len >= chunk) { make_plan(0, chunk); make_plan(1, chunk); }
+            if (len % chunk) { make_plan(0, len % chunk); make_plan(1, len % chunk); }
+        }
+        fft_work.alloc(fft_work_bytes);
+        for (auto& kv : plans) SURFH_FFT(cufftSetWorkArea(kv.second, fft_work.p));
+        // opt in to > 48 KB dynamic shared memory for the GEMM kernels
+        using G = GemmCfg<T>;
+        const int smem = (int)otgemm_smem_bytes<T, G::BM, G::BN, G::BK>();
+        SURFH_CUDA(cudaFuncSetAttribute(otgemm_kernel<T, G::BM, G::BN, G::BK, G::TM, G::TN, true, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SURFH_CUDA(cudaFuncSetAttribute(otgemm_kernel<T, G::BM, G::BN, G::BK, G::TM, G::TN, false, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SURFH_CUDA(cudaDeviceSynchronize());
+        finalized = true;
+    }
+
+    int64_t input_size() const override { return (int64_t)(K > 0 ? K : Nl) * (int64_t)plane; }
+    int64_t output_size() const override {
+        int64_t m = 0;
+        for (auto& b : bands) m = std::max(m, b->out_offset + b->out_size);
+        return m;
+    }
+    int64_t workspace_bytes() const override {
+        int64_t t = otf.bytes + tpl.bytes + tpl_raw.bytes + xhat.bytes + spec.bytes + cubebuf.bytes + fft_work.bytes +
+                    y_internal.bytes + x_stage.bytes + y_stage.bytes + dbl_stage.bytes;
+        for (auto& b : bands)
+            t += b->lsf.bytes + b->G.bytes + b->grid_base.bytes + b->grid_frac.bytes + b->csr_col[0].bytes +
+                 b->csr_val[0].bytes + b->csr_col[1].bytes + b->csr_val[1].bytes;
+        return t;
+    }
+
+    // ---- launch helpers ---------------------------------------------------------------------
+    template <int KK> void launch_lmm_fwd(int c0, int nl, cudaStream_t st) {
+        dim3 grid(ceil_div(nfp, 256), ceil_div(nl, kLmmLsub));
+        lmm_otf_fwd_kernel<T, KK><<<grid, 256, 0, st>>>(xhat.as<C>(), otf.as<C>() + (size_t)c0 * nfp, tpl.as<T>(), Nl,
+                                                        c0, nl, nfp, spec.as<C>());
+    }
+    template <int KK> void launch_lmm_adj(int c0, int nl, bool accumulate, cudaStream_t st) {
+        dim3 grid(ceil_div(nfp, 32)), block(32, kAdjLanes);
+        lmm_otf_adj_kernel<T, KK><<<grid, block, 0, st>>>(spec.as<C>(), otf.as<C>() + (size_t)c0 * nfp, tpl.as<T>(),
+                                                          Nl, c0, nl, nfp, xhat.as<C>(), accumulate ? 1 : 0);
+    }
+    template <int KK> void launch_maps_to_cube(const T* maps, float* cube, cudaStream_t st) {
+        dim3 grid(ceil_div(plane, 256), ceil_div(Nl, 32));
+        maps_to_cube_kernel<T, KK><<<grid, 256, 0, st>>>(maps, tpl_raw.as<T>(), Nl, Nl, plane, cube);
+    }
+#define SURFH_DISPATCH_K(fn, ...)                                                          \
+    switch (K) {                                                                           \
+        case 1: fn<1>(__VA_ARGS__); break;                                                 \
+        case 2: fn<2>(__VA_ARGS__); break;                                                 \
+        case 3: fn<3>(__VA_ARGS__); break;                                                 \
+        case 4: fn<4>(__VA_ARGS__); break;                                                 \
+        case 5: fn<5>(__VA_ARGS__); break;                                                 \
+        case 6: fn<6>(__VA_ARGS__); break;                                                 \
+        case 7: fn<7>(__VA_ARGS__); break;                                                 \
+        case 8: fn<8>(__VA_ARGS__); break;                                                 \
+        default: throw Error(SURFH_EINVAL, "unsupported template count");                  \
+    }
+
+    void fft_exec(int kind, int batch, void* in, void* out, cudaStream_t st) {
+        cufftHandle p = plan(kind, batch);
+        SURFH_FFT(cufftSetStream(p, st));
+        if (kind == 0)
+            SURFH_FFT(FftTraits<T>::fwd(p, reinterpret_cast<T*>(in), reinterpret_cast<C*>(out)));
+        else
+            SURFH_FFT(FftTraits<T>::inv(p, reinterpret_cast<C*>(in), reinterpret_cast<T*>(out)));
+    }
+
+    void gemm_forward(BandT<T>& b, T* y, cudaStream_t st) {
+        using G = GemmCfg<T>;
+        GemmArgs<T> g;
+        g.M = b.nd; g.N = b.Nn; g.K = b.KB;
+        g.A = b.lsf.template as<T>(); g.aM = b.t_wrow.template as<int32_t>(); g.aK = b.t_ident.template as<int32_t>();
+        g.B = b.G.template as<T>(); g.bK = b.t_gK.template as<int32_t>(); g.bN = b.t_gN.template as<int32_t>();
+        g.C = y + b.out_offset; g.cM = b.t_yM.template as<int32_t>(); g.cN = b.t_yN.template as<int32_t>();
+        dim3 grid(ceil_div(g.N, G::BN), ceil_div(g.M, G::BM));
+        const double bytes = sizeof(T) * ((double)b.nd * b.KB + (double)b.nl * b.ncol + (double)b.out_size);
+        Scope sc(this, ST_GEMM_FWD, st, bytes, 2.0 * g.M * g.N * g.K, 1, true);
+        otgemm_kernel<T, G::BM, G::BN, G::BK, G::TM, G::TN, true, true>
+            <<<grid, (G::BM / G::TM) * (G::BN / G::TN), otgemm_smem_bytes<T, G::BM, G::BN, G::BK>(), st>>>(g);
+        SURFH_CUDA(cudaGetLastError());
+    }
+
+    void gemm_adjoint(BandT<T>& b, const T* y, cudaStream_t st) {
+        using G = GemmCfg<T>;
+        GemmArgs<T> g;
+        g.M = b.KB; g.N = b.Nn; g.K = b.nd;
+        g.A = b.lsf.template as<T>(); g.aM = b.t_ident.template as<int32_t>(); g.aK = b.t_wrow.template as<int32_t>();
+        g.B = y + b.out_offset; g.bK = b.t_yM.template as<int32_t>(); g.bN = b.t_yN.template as<int32_t>();
+        g.C = b.G.template as<T>(); g.cM = b.t_gK.template as<int32_t>(); g.cN = b.t_gN.template as<int32_t>();
+        dim3 grid(ceil_div(g.N, G::BN), ceil_div(g.M, G::BM));
+        const double bytes = sizeof(T) * ((double)b.nd * b.KB + (double)b.nl * b.ncol + (double)b.out_size);
+        Scope sc(this, ST_GEMM_ADJ, st, bytes, 2.0 * g.M * g.N * g.K, 1, true);
+        otgemm_kernel<T, G::BM, G::BN, G::BK, G::TM, G::TN, false, false>
+            <<<grid, (G::BM / G::TM) * (G::BN / G::TN), otgemm_smem_bytes<T, G::BM, G::BN, G::BK>(), st>>>(g);
+        SURFH_CUDA(cudaGetLastError());
+    }
+
+    static constexpr int kLB = 4;  // wavelengths per thread in the slit kernels
+
+    void gather_chunk(int c0, int c1, cudaStream_t st) {
+        for (auto& bp : bands) {
+            BandT<T>& b = *bp;
+            const int lo = std::max(c0, b.l0), hi = std::min(c1, b.l0 + b.nl);
+            if (lo >= hi) continue;
+            const int nl = hi - lo;
+            dim3 grid(ceil_div(b.ncol, 128), ceil_div(nl, kLB));
+            const double bytes = sizeof(T) * ((double)nl * b.A * b.B * b.P + (double)nl * b.ncol);
+            Scope sc(this, ST_SLIT_GATHER, st, bytes, 8.0 * nl * b.ncol * b.srf, 1, true);
+            slit_gather_kernel<T, kLB><<<grid, 128, 0, st>>>(cubebuf.as<T>() + (size_t)(lo - c0) * plane, plane, Nb, nl,
+                                                             b.slit_tables(),
+                                                             b.G.template as<T>() + (size_t)(lo - b.l0) * b.ncol);
+            SURFH_CUDA(cudaGetLastError());
+        }
+    }
+
+    void scatter_chunk(int c0, int c1, int mode, cudaStream_t st) {
+        {
+            Scope sc(this, ST_MEMSET, st, (double)(c1 - c0) * plane * sizeof(T), 0, 1, false);
+            SURFH_CUDA(cudaMemsetAsync(cubebuf.p, 0, (size_t)(c1 - c0) * plane * sizeof(T), st));
+        }
+        for (auto& bp : bands) {
+            BandT<T>& b = *bp;
+            const int lo = std::max(c0, b.l0), hi = std::min(c1, b.l0 + b.nl);
+            if (lo >= hi || b.csr_rows[mode] == 0) continue;
+            const int nl = hi - lo;
+            dim3 grid(ceil_div(b.csr_rows[mode], 128), ceil_div(nl, kLB));
+            const double bytes = sizeof(T) * ((double)nl * b.ncol + 2.0 * nl * b.csr_rows[mode]);
+            Scope sc(this, ST_SLIT_SCATTER, st, bytes, 2.0 * nl * (double)b.csr_nnz[mode], 1, true);
+            slit_scatter_kernel<T, kLB><<<grid, 128, 0, st>>>(b.G.template as<T>() + (size_t)(lo - b.l0) * b.ncol, b.ncol,
+                                                              nl, b.csr(mode),
+                                                              cubebuf.as<T>() + (size_t)(lo - c0) * plane, plane);
+            SURFH_CUDA(cudaGetLastError());
+        }
+    }
+
+    void require_ready() const {
+        if (!finalized) throw Error(SURFH_ESTATE, "surfh_finalize has not been called");
+    }
+
+    void forward(const void* xv, void* yv, cudaStream_t st) override {
+        require_ready();
+        SURFH_REQUIRE(xv && yv, "NULL buffer");
+        const T* x = reinterpret_cast<const T*>(xv);
+        T* y = reinterpret_cast<T*>(yv);
+        if (K > 0) {
+            Scope sc(this, ST_RFFT_MAPS, st, (double)K * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+            fft_exec(0, K, const_cast<T*>(x), xhat.p, st);
+        }
+        for (auto& r : ranges) {
+            for (int c0 = r.first; c0 < r.second; c0 += chunk) {
+                const int c1 = std::min(r.second, c0 + chunk), nl = c1 - c0;
+                if (K > 0) {
+                    Scope sc(this, ST_LMM_OTF_FWD, st, (double)nl * nf * sizeof(C) * 2 + (double)K * nf * sizeof(C),
+                             (4.0 * K + 6.0) * nl * nf, 1, true);
+                    SURFH_DISPATCH_K(launch_lmm_fwd, c0, nl, st);
+                    SURFH_CUDA(cudaGetLastError());
+                } else {
+                    {
+                        Scope sc(this, ST_RFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+                        fft_exec(0, nl, const_cast<T*>(x) + (size_t)c0 * plane, spec.p, st);
+                    }
+                    Scope sc(this, ST_LMM_OTF_FWD, st, (double)nl * nf * sizeof(C) * 3, 6.0 * nl * nf, 1, true);
+                    const size_t n = (size_t)nl * nfp;
+                    otf_mul_kernel<T, false><<<ceil_div(n, 256), 256, 0, st>>>(
+                        spec.as<C>(), otf.as<C>() + (size_t)c0 * nfp, n, (T)(1.0 / ((double)Na * Nb)));
+                    SURFH_CUDA(cudaGetLastError());
+                }
+                {
+                    Scope sc(this, ST_IRFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+                    fft_exec(1, nl, spec.p, cubebuf.p, st);
+                }
+                gather_chunk(c0, c1, st);
+            }
+        }
+        for (auto& bp : bands) gemm_forward(*bp, y, st);
+    }
+
+    void adjoint(const void* yv, void* xv, int mode, cudaStream_t st) override {
+        require_ready();
+        SURFH_REQUIRE(xv && yv, "NULL buffer");
+        SURFH_REQUIRE(mode == SURFH_ADJ_EXACT || mode == SURFH_ADJ_REFERENCE, "unknown adjoint mode");
+        const T* y = reinterpret_cast<const T*>(yv);
+        T* x = reinterpret_cast<T*>(xv);
+        for (auto& bp : bands) gemm_adjoint(*bp, y, st);
+        if (K == 0) {
+            Scope sc(this, ST_MEMSET, st, (double)Nl * plane * sizeof(T), 0, 1, false);
+            SURFH_CUDA(cudaMemsetAsync(x, 0, (size_t)Nl * plane * sizeof(T), st));
+        }
+        bool first = true;
+        for (auto& r : ranges) {
+            for (int c0 = r.first; c0 < r.second; c0 += chunk) {
+                const int c1 = std::min(r.second, c0 + chunk), nl = c1 - c0;
+                scatter_chunk(c0, c1, mode, st);
+                {
+                    Scope sc(this, ST_RFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+                    fft_exec(0, nl, cubebuf.p, spec.p, st);
+                }
+                if (K > 0) {
+                    Scope sc(this, ST_LMM_OTF_ADJ, st, (double)nl * nf * sizeof(C) * 2 + (double)K * nf * sizeof(C),
+                             (4.0 * K + 6.0) * nl * nf, 1, true);
+                    SURFH_DISPATCH_K(launch_lmm_adj, c0, nl, !first, st);
+                    SURFH_CUDA(cudaGetLastError());
+                } else {
+                    {
+                        Scope sc(this, ST_LMM_OTF_ADJ, st, (double)nl * nf * sizeof(C) * 3, 6.0 * nl * nf, 1, true);
+                        const size_t n = (size_t)nl * nfp;
+                        otf_mul_kernel<T, true><<<ceil_div(n, 256), 256, 0, st>>>(
+                            spec.as<C>(), otf.as<C>() + (size_t)c0 * nfp, n, (T)(1.0 / ((double)Na * Nb)));
+                        SURFH_CUDA(cudaGetLastError());
+                    }
+                    Scope sc(this, ST_IRFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+                    fft_exec(1, nl, spec.p, x + (size_t)c0 * plane, st);
+                }
+                first = false;
+            }
+        }
+        if (K > 0) {
+            Scope sc(this, ST_IRFFT_MAPS, st, (double)K * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+            fft_exec(1, K, xhat.p, x, st);
+        }
+    }
+
+    void fwadj(const void* x, void* out, int mode, void* yscratch, cudaStream_t st) override {
+        require_ready();
+        if (!yscratch) {
+            y_internal.ensure((size_t)output_size() * sizeof(T));
+            yscratch = y_internal.p;
+        }
+        forward(x, yscratch, st);
+        adjoint(yscratch, out, mode, st);
+    }
+
+    void maps_to_cube(const void* maps, float* cube, cudaStream_t st) override {
+        SURFH_REQUIRE(K > 0, "maps_to_cube needs templates");
+        SURFH_REQUIRE(maps && cube, "NULL buffer");
+        Scope sc(this, ST_LMM_OTF_FWD, st, 0, 0, 1, true);
+        SURFH_DISPATCH_K(launch_maps_to_cube, reinterpret_cast<const T*>(maps), cube, st);
+        SURFH_CUDA(cudaGetLastError());
+    }
+
+    // ---- host-buffer entry points -------------------------------------------------------------
+    void to_device(const double* host, DevBuf& dev, size_t n, cudaStream_t st) {
+        dev.ensure(n * sizeof(T));
+        if (std::is_same<T, double>::value) {
+            SURFH_CUDA(cudaMemcpyAsync(dev.p, host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        } else {
+            dbl_stage.ensure(n * sizeof(double));
+            SURFH_CUDA(cudaMemcpyAsync(dbl_stage.p, host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+            convert_kernel<double, T><<<ceil_div(n, 256), 256, 0, st>>>(dbl_stage.as<double>(), dev.as<T>(), n);
+            SURFH_CUDA(cudaGetLastError());
+            own_launches++; launches++;
+        }
+    }
+    void to_host(DevBuf& dev, double* host, size_t n, cudaStream_t st) {
+        if (std::is_same<T, double>::value) {
+            SURFH_CUDA(cudaMemcpyAsync(host, dev.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        } else {
+            dbl_stage.ensure(n * sizeof(double));
+            convert_kernel<T, double><<<ceil_div(n, 256), 256, 0, st>>>(dev.as<T>(), dbl_stage.as<double>(), n);
+            SURFH_CUDA(cudaGetLastError());
+            own_launches++; launches++;
+            SURFH_CUDA(cudaMemcpyAsync(host, dbl_stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+        SURFH_CUDA(cudaStreamSynchronize(st));
+    }
+    void forward_host(const double* x, double* y) override {
+        require_ready();
+        SURFH_REQUIRE(x && y, "NULL buffer");
+        cudaStream_t st = 0;
+        const size_t ni = (size_t)input_size(), no = (size_t)output_size();
+        to_device(x, x_stage, ni, st);
+        y_stage.ensure(no * sizeof(T));
+        forward(x_stage.p, y_stage.p, st);
+        to_host(y_stage, y, no, st);
+    }
+    void adjoint_host(const double* y, double* x, int mode) override {
+        require_ready();
+        SURFH_REQUIRE(x && y, "NULL buffer");
+        cudaStream_t st = 0;
+        const size_t ni = (size_t)input_size(), no = (size_t)output_size();
+        to_device(y, y_stage, no, st);
+        x_stage.ensure(ni * sizeof(T));
+        adjoint(y_stage.p, x_stage.p, mode, st);
+        to_host(x_stage, x, ni, st);
+    }
+
+    // ---- CG -----------------------------------------------------------------------------------
+    CgScratch scratch() { return CgScratch{cg_partial.as<double>(), cg_ticket.as<unsigned int>()}; }
+    int cg_grid(size_t n) const { return (int)std::min<size_t>(kCgMaxBlocks, (n + kCgThreads - 1) / kCgThreads); }
+    int n_maps() const { return K > 0 ? K : Nl; }
+
+    void cg_regularise_dot(const void* d, void* q, double mu_s, double mu_r, double* s, cudaStream_t st) override {
+        SURFH_REQUIRE(d && q && s, "NULL buffer");
+        const size_t n = (size_t)input_size();
+        Scope sc(this, ST_CG, st, 3.0 * n * sizeof(T), 10.0 * n, 1, true);
+        cg_regularise_dot_kernel<T><<<cg_grid(n), kCgThreads, 0, st>>>(reinterpret_cast<const T*>(d),
+                                                                       reinterpret_cast<T*>(q), n_maps(), Na, Nb, mu_s,
+                                                                       mu_r, s, scratch());
+        SURFH_CUDA(cudaGetLastError());
+    }
+    void cg_start(const void* b, const void* q, void* r, void* d, double* s, cudaStream_t st) override {
+        SURFH_REQUIRE(b && q && r && d && s, "NULL buffer");
+        const size_t n = (size_t)input_size();
+        Scope sc(this, ST_CG, st, 4.0 * n * sizeof(T), 3.0 * n, 1, true);
+        cg_start_kernel<T><<<cg_grid(n), kCgThreads, 0, st>>>(reinterpret_cast<const T*>(b), reinterpret_cast<const T*>(q),
+                                                              reinterpret_cast<T*>(r), reinterpret_cast<T*>(d), n, s,
+                                                              SURFH_CG_NSCALARS, scratch());
+        SURFH_CUDA(cudaGetLastError());
+    }
+    void cg_update(void* x, void* r, void* d, const void* q, double* s, cudaStream_t st) override {
+        SURFH_REQUIRE(x && r && d && q && s, "NULL buffer");
+        const size_t n = (size_t)input_size();
+        Scope sc(this, ST_CG, st, 9.0 * n * sizeof(T), 8.0 * n, 2, true);
+        cg_step_kernel<T, false><<<cg_grid(n), kCgThreads, 0, st>>>(
+            reinterpret_cast<T*>(x), reinterpret_cast<T*>(r), reinterpret_cast<const T*>(d),
+            reinterpret_cast<const T*>(q), nullptr, n, s, SURFH_CG_NSCALARS, scratch());
+        cg_direction_kernel<T><<<cg_grid(n), kCgThreads, 0, st>>>(reinterpret_cast<const T*>(r), reinterpret_cast<T*>(d),
+                                                                  n, s);
+        SURFH_CUDA(cudaGetLastError());
+    }
+    void cg_refresh(int phase, void* x, void* r, void* d, const void* b, const void* qx, double* s,
+                    cudaStream_t st) override {
+        const size_t n = (size_t)input_size();
+        if (phase == 0) {
+            SURFH_REQUIRE(x && d && s, "NULL buffer");
+            Scope sc(this, ST_CG, st, 3.0 * n * sizeof(T), 2.0 * n, 1, true);
+            cg_axpy_alpha_kernel<T><<<cg_grid(n), kCgThreads, 0, st>>>(reinterpret_cast<T*>(x),
+                                                                       reinterpret_cast<const T*>(d), n, s);
+        } else {
+            SURFH_REQUIRE(r && d && b && qx && s, "NULL buffer");
+            Scope sc(this, ST_CG, st, 6.0 * n * sizeof(T), 6.0 * n, 2, true);
+            cg_step_kernel<T, true><<<cg_grid(n), kCgThreads, 0, st>>>(
+                nullptr, reinterpret_cast<T*>(r), nullptr, reinterpret_cast<const T*>(qx),
+                reinterpret_cast<const T*>(b), n, s, SURFH_CG_NSCALARS, scratch());
+            cg_direction_kernel<T><<<cg_grid(n), kCgThreads, 0, st>>>(reinterpret_cast<const T*>(r),
+                                                                      reinterpret_cast<T*>(d), n, s);
+        }
+        SURFH_CUDA(cudaGetLastError());
+    }
+    void criterion_terms(const void* y, const void* hx, int64_t n, const void* x, double* out, cudaStream_t st) override {
+        SURFH_REQUIRE(out, "NULL buffer");
+        const size_t nmax = std::max<size_t>((size_t)std::max<int64_t>(n, 0), x ? (size_t)input_size() : 0);
+        Scope sc(this, ST_CG, st, 2.0 * n * sizeof(T), 3.0 * n, 1, true);
+        criterion_kernel<T><<<cg_grid(std::max<size_t>(nmax, 1)), kCgThreads, 0, st>>>(
+            reinterpret_cast<const T*>(y), reinterpret_cast<const T*>(hx), (size_t)std::max<int64_t>(n, 0),
+            reinterpret_cast<const T*>(x), n_maps(), Na, Nb, out, scratch());
+        SURFH_CUDA(cudaGetLastError());
+    }
+};
+
+}  // namespace surfh
+
+// ------------------------------------------------------------------------------------------------
+#define SURFH_API_BEGIN(h)                                   \
+    if (!(h)) return SURFH_EINVAL;                           \
+    try {
+#define SURFH_API_END(h)                                     \
+    }                                                        \
+    catch (const surfh::Error& e) {                          \
+        (h)->last_error = e.what();                          \
+        return e.code;                                       \
+    }                                                        \
+    catch (const std::bad_alloc&) {                          \
+        (h)->last_error = "host allocation failed";          \
+        return SURFH_ENOMEM;                                 \
+    }                                                        \
+    catch (const std::exception& e) {                        \
+        (h)->last_error = e.what();                          \
+        return SURFH_EINVAL;                                 \
+    }                                                        \
+    return SURFH_OK;
+
+extern "C" {
+
+int surfh_abi_version(void) { return SURFH_ABI_VERSION; }
+
+int surfh_create(const surfh_model_desc* desc, surfh_handle* out) {
+    if (!desc || !out) {
+        g_create_error = "NULL argument";
+        return SURFH_EINVAL;
+    }
+    *out = nullptr;
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Error(SURFH_ECUDA, std::string("no CUDA device available (surfh_b200 has no CPU fallback): ") +
+                                         cudaGetErrorString(e));
+        if (desc->dtype == SURFH_F64) {
+            auto m = std::make_unique<ModelImpl<double>>();
+            m->dtype = SURFH_F64;
+            m->init(desc);
+            *out = m.release();
+        } else if (desc->dtype == SURFH_F32) {
+            auto m = std::make_unique<ModelImpl<float>>();
+            m->dtype = SURFH_F32;
+            m->init(desc);
+            *out = m.release();
+        } else {
+            throw Error(SURFH_EINVAL, "dtype must be SURFH_F32 or SURFH_F64");
+        }
+    } catch (const surfh::Error& e) {
+        g_create_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return SURFH_EINVAL;
+    }
+    return SURFH_OK;
+}
+
+int surfh_set_otf(surfh_handle h, int32_t l_start, int32_t l_count, const void* otf) {
+    SURFH_API_BEGIN(h) h->set_otf(l_start, l_count, otf);
+    SURFH_API_END(h)
+}
+int surfh_add_band(surfh_handle h, const surfh_band_desc* band) {
+    SURFH_API_BEGIN(h)
+    if (!band) throw Error(SURFH_EINVAL, "NULL band descriptor");
+    h->add_band(band);
+    SURFH_API_END(h)
+}
+int surfh_finalize(surfh_handle h) {
+    SURFH_API_BEGIN(h) h->finalize();
+    SURFH_API_END(h)
+}
+void surfh_destroy(surfh_handle h) { delete h; }
+const char* surfh_last_error(surfh_handle h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+int64_t surfh_input_size(surfh_handle h) { return h ? h->input_size() : -1; }
+int64_t surfh_output_size(surfh_handle h) { return h ? h->output_size() : -1; }
+int64_t surfh_workspace_bytes(surfh_handle h) { return h ? h->workspace_bytes() : -1; }
+
+int surfh_forward(surfh_handle h, const void* x, void* y, void* stream) {
+    SURFH_API_BEGIN(h) h->forward(x, y, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+int surfh_adjoint(surfh_handle h, const void* y, void* x, int32_t mode, void* stream) {
+    SURFH_API_BEGIN(h) h->adjoint(y, x, mode, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+int surfh_fwadj(surfh_handle h, const void* x, void* out, int32_t mode, void* y_scratch, void* stream) {
+    SURFH_API_BEGIN(h) h->fwadj(x, out, mode, y_scratch, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+int surfh_maps_to_cube(surfh_handle h, const void* maps, float* cube, void* stream) {
+    SURFH_API_BEGIN(h) h->maps_to_cube(maps, cube, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+int surfh_forward_host(surfh_handle h, const double* x, double* y) {
+    SURFH_API_BEGIN(h) h->forward_host(x, y);
+    SURFH_API_END(h)
+}
+int surfh_adjoint_host(surfh_handle h, const double* y, double* x, int32_t mode) {
+    SURFH_API_BEGIN(h) h->adjoint_host(y, x, mode);
+    SURFH_API_END(h)
+}
+
+int surfh_cg_regularise_dot(surfh_handle h, const void* d, void* q, double mu_s, double mu_r, double* s, void* stream) {
+    SURFH_API_BEGIN(h) h->cg_regularise_dot(d, q, mu_s, mu_r, s, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+int surfh_cg_start(surfh_handle h, const void* b, const void* q, void* r, void* d, double* s, void* stream) {
+    SURFH_API_BEGIN(h) h->cg_start(b, q, r, d, s, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+int surfh_cg_update(surfh_handle h, void* x, void* r, void* d, const void* q, double* s, void* stream) {
+    SURFH_API_BEGIN(h) h->cg_update(x, r, d, q, s, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+int surfh_cg_refresh(surfh_handle h, int32_t phase, void* x, void* r, void* d, const void* b, const void* qx, double* s,
+                     void* stream) {
+    SURFH_API_BEGIN(h) h->cg_refresh(phase, x, r, d, b, qx, s, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+int surfh_criterion_terms(surfh_handle h, const void* y, const void* hx, int64_t n, const void* x, double* s_out,
+                          void* stream) {
+    SURFH_API_BEGIN(h) h->criterion_terms(y, hx, n, x, s_out, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+
+int64_t surfh_launch_count(surfh_handle h) { return h ? h->launches : -1; }
+int64_t surfh_own_launch_count(surfh_handle h) { return h ? h->own_launches : -1; }
+
+int surfh_profile_enable(surfh_handle h, int32_t on) {
+    if (!h) return SURFH_EINVAL;
+    for (auto& r : h->recs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    h->recs.clear();
+    for (int i = 0; i < ST_COUNT; ++i) {
+        h->stage_bytes[i] = 0;
+        h->stage_flops[i] = 0;
+        h->stage_launches[i] = 0;
+    }
+    h->profiling = on != 0;
+    return SURFH_OK;
+}
+
+int surfh_profile_read(surfh_handle h, int32_t cap, const char** names, float* ms, double* bytes, double* flops) {
+    if (!h || cap < 0) return SURFH_EINVAL;
+    cudaDeviceSynchronize();
+    float acc[ST_COUNT] = {0};
+    for (auto& r : h->recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) acc[r.stage] += t;
+    }
+    int n = 0;
+    for (int i = 0; i < ST_COUNT && n < cap; ++i) {
+        if (h->stage_launches[i] == 0) continue;
+        if (names) names[n] = kStageNames[i];
+        if (ms) ms[n] = acc[i];
+        if (bytes) bytes[n] = h->stage_bytes[i];
+        if (flops) flops[n] = h->stage_flops[i];
+        ++n;
+    }
+    return n;
+}
+
+}  // extern "C"

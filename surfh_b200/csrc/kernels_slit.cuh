@@ -1,0 +1,118 @@
+// k3 / k3^T: IFU slit sampling and its two "adjoints".
+//
+// Forward (gather), fused S . Sum . L . alpha-decimation for all pointings of a band:
+//   G[l, (p,s,a,b)] = w[s,b] * sum_{m<srf} bilinear(cube[l]; grid[p][(a0[s] + a*srf + m) mod A, b0[s] + b])
+// Replaces (paths relative to the reference tree)
+//   Channel.gridding            surfh/Models/spectroModelChannel.py:158-177
+//     -> cythons_files.find_indices / solve_2D_hypercube   surfh/ToolsDir/cythons_files.pyx:109-193
+//   the FFT "Sum" stage          spectroModelChannel.py:220-223  (== circular box-sum of srf rows)
+//   Slicer.slicing               surfh/Models/slicer.py:64-68
+//   the `[:, : na*srf : srf]` decimation                  spectroModelChannel.py:229
+// Only the rows the detector keeps are ever computed (the reference computes and discards
+// (srf-1)/srf of them), and the two FFTs per pointing of the Sum stage disappear.
+//
+// Adjoint (scatter as gather): the composition of the slit placement, Sum^T and either the true
+// transpose of the bilinear gridding (exact) or the reference's `gridding_t` interpolation
+// (spectroModelChannel.py:180-199, 234-264) is precomputed on the host as ONE sparse table
+// cube pixel -> (slit-space column, weight), shared by every wavelength.  Each cube pixel is owned
+// by one thread, so the reduction is a fixed-order segmented sum: deterministic, no atomics.
+//
+// Both kernels are HBM/L2-bound index streams; a thread carries `LB` wavelengths so that one
+// table lookup serves LB planes.
+#pragma once
+#include "common.cuh"
+
+namespace surfh {
+
+template <typename T> struct SlitTables {
+    const int32_t* slit_a0;    // [S]
+    const int32_t* slit_b0;    // [S]
+    const T* slit_w;           // [S, nb]
+    const int32_t* grid_base;  // [P, A*B]
+    const T* grid_frac;        // [P, A*B, 2]
+    int32_t P, S, na, nb, srf, A, B;
+    int32_t ncol;  // P*S*na*nb
+};
+
+template <typename T, int LB>
+__global__ void __launch_bounds__(128)
+slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube plane */, int n_beta,
+                   int n_l, SlitTables<T> t, T* __restrict__ G) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= t.ncol) return;
+    const int l0 = blockIdx.y * LB;
+    int b = c % t.nb;
+    int r = c / t.nb;
+    const int a = r % t.na;
+    r /= t.na;
+    const int s = r % t.S;
+    const int p = r / t.S;
+    const int j = t.slit_b0[s] + b;
+    const int i_first = t.slit_a0[s] + a * t.srf;
+    const int32_t* gb = t.grid_base + (size_t)p * t.A * t.B;
+    const T* gf = t.grid_frac + (size_t)p * t.A * t.B * 2;
+    T acc[LB];
+#pragma unroll
+    for (int u = 0; u < LB; ++u) acc[u] = T(0);
+    const T* base_l = cube + (size_t)l0 * plane;
+    for (int m = 0; m < t.srf; ++m) {
+        int i = i_first + m;
+        i = i >= t.A ? i - t.A : i;  // circular wrap of the FFT box-sum
+        const int q = i * t.B + j;
+        const int32_t off = __ldg(gb + q);
+        const T y0 = __ldg(gf + 2 * q), y1 = __ldg(gf + 2 * q + 1);
+        const T w00 = (T(1) - y0) * (T(1) - y1), w01 = (T(1) - y0) * y1;
+        const T w10 = y0 * (T(1) - y1), w11 = y0 * y1;
+#pragma unroll
+        for (int u = 0; u < LB; ++u) {
+            if (l0 + u < n_l) {
+                const T* pl = base_l + (size_t)u * plane + off;
+                T v = __ldg(pl) * w00;
+                v = fma(__ldg(pl + 1), w01, v);
+                v = fma(__ldg(pl + n_beta), w10, v);
+                v = fma(__ldg(pl + n_beta + 1), w11, v);
+                acc[u] += v;
+            }
+        }
+    }
+    const T w = t.slit_w[s * t.nb + b];
+#pragma unroll
+    for (int u = 0; u < LB; ++u)
+        if (l0 + u < n_l) G[(size_t)(l0 + u) * t.ncol + c] = w * acc[u];
+}
+
+template <typename T> struct CsrTable {
+    const int32_t* row_pixel;  // [n_rows]
+    const int64_t* row_ptr;    // [n_rows + 1]
+    const int32_t* col;        // [nnz]
+    const T* val;              // [nnz]
+    int32_t n_rows;
+};
+
+// cube[l, pixel] += sum_e val[e] * Gt[l, col[e]]     (cube is zeroed by the caller)
+template <typename T, int LB>
+__global__ void __launch_bounds__(128)
+slit_scatter_kernel(const T* __restrict__ Gt, int ncol, int n_l, CsrTable<T> t, T* __restrict__ cube,
+                    size_t plane) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= t.n_rows) return;
+    const int l0 = blockIdx.y * LB;
+    const int64_t e0 = t.row_ptr[r], e1 = t.row_ptr[r + 1];
+    T acc[LB];
+#pragma unroll
+    for (int u = 0; u < LB; ++u) acc[u] = T(0);
+    const T* g = Gt + (size_t)l0 * ncol;
+    for (int64_t e = e0; e < e1; ++e) {
+        const int c = __ldg(t.col + e);
+        const T v = __ldg(t.val + e);
+#pragma unroll
+        for (int u = 0; u < LB; ++u)
+            if (l0 + u < n_l) acc[u] = fma(v, __ldg(g + (size_t)u * ncol + c), acc[u]);
+    }
+    T* dst = cube + (size_t)l0 * plane + t.row_pixel[r];
+#pragma unroll
+    for (int u = 0; u < LB; ++u)
+        if (l0 + u < n_l) dst[(size_t)u * plane] += acc[u];
+}
+
+}  // namespace surfh

@@ -1,0 +1,351 @@
+"""`spectroSigRLSCT`: the reference's multi-band, multi-pointing LMM instrument operator, with
+the same constructor, shapes, ordering and LinOp surface, computed by the CUDA library.
+
+    y = sum_bands  Sig R . L . Sum . S . C . T  x
+
+Reference interface mirrored (paths relative to /root/reference):
+    class spectroSigRLSCT      surfh/Models/spectroModel.py:39-198
+    class Channel              surfh/Models/spectroModelChannel.py:26-264 (as `.channels[i]` views)
+Call sites kept working: scripts/main_fusion.py:136-156, 160-204, 257-265;
+surfh/Simulation/fusion_CT.py:130-136, 242-265.
+
+numpy in -> numpy out (host buffers; H2D/D2H inside the call, like the reference's LinOp);
+torch CUDA tensor in -> torch CUDA tensor out on the current stream (no synchronisation).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from math import ceil
+from typing import Callable, List, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _capi, geometry, instru
+from .linop import LinOp
+
+_DTYPES = {"float64": _capi.F64, "fp64": _capi.F64, "f64": _capi.F64, np.float64: _capi.F64,
+           "float32": _capi.F32, "fp32": _capi.F32, "f32": _capi.F32, np.float32: _capi.F32}
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+class SlicerView:
+    """What callers read from `Channel.slicer` (surfh/Models/slicer.py): slit slices/weights."""
+
+    def __init__(self, tables: geometry.BandTables):
+        self._t = tables
+        self.srf = tables.srf
+        self.npix_slit_beta_width = tables.nb
+        self.npix_slit_alpha_width = tables.npix_slit_alpha_width
+        self.slices_shape = (tables.n_slit, tables.na)
+
+    def get_slit_slices(self, slit_idx: int):
+        return self._t.slices[slit_idx]
+
+    def get_slit_weights(self, slit_idx: int, slices=None):
+        n_alpha = self._t.slices[slit_idx][0].stop - self._t.slices[slit_idx][0].start
+        return np.broadcast_to(self._t.weights[slit_idx][None, None, :], (1, n_alpha, self._t.nb)).copy()
+
+    def get_slit_shape_t(self):
+        sl = self._t.slices[0]
+        return (self._t.n_wave, sl[0].stop - sl[0].start, sl[1].stop - sl[1].start)
+
+    get_slit_shape = get_slit_shape_t
+
+
+class ChannelView:
+    """Read-only view of one band with the attribute names of the reference's `Channel`."""
+
+    def __init__(self, tables: geometry.BandTables, n_pointing: int):
+        self.tables = tables
+        self.instr = tables.instr
+        self.pointings = tables.pointings
+        self.srf = tables.srf
+        self.wslice = tables.wslice
+        self.local_alpha_axis = tables.local_alpha_axis
+        self.local_beta_axis = tables.local_beta_axis
+        self.local_im_shape = tables.local_shape
+        self.oshape = (n_pointing,) + tables.oshape[1:]
+        self.slices_shape = (n_pointing, tables.n_slit, tables.na)
+        self.slicer = SlicerView(tables)
+        self.wpsf = tables.lsf
+
+    @property
+    def name(self):
+        return self.instr.name
+
+
+class spectroSigRLSCT(LinOp):
+    """Drop-in for `surfh.Models.spectroModel.spectroSigRLSCT`.
+
+    Extra keyword arguments (all optional, defaults reproduce the reference's behaviour):
+      dtype          "float64" (default; parity <= 1e-10 vs the reference numpy path) or "float32"
+      adjoint_mode   "reference" (default: bug-for-bug `gridding_t` interpolation) or "exact"
+                     (true transpose; <Hx,y> = <x,H^T y> to rounding)
+      local_bands    indices of the bands this process computes (band sharding across GPUs);
+                     other bands' slices of y are left at zero / ignored
+      chunk          wavelengths per pipeline chunk (0 = library default)
+      device         CUDA device index (default: current device)
+      sotf           may also be a torch CUDA complex tensor, or a callable (l0, l1) -> complex
+                     array/tensor of planes [l0, l1), so a multi-GB OTF never sits on the host
+    """
+
+    def __init__(self, sotf, templates, alpha_axis, beta_axis, wavelength_axis,
+                 instrs: List[instru.IFU], step_degree: float, pointings: Sequence[instru.CoordList],
+                 dtype="float64", adjoint_mode: str = "reference", local_bands: Optional[Sequence[int]] = None,
+                 chunk: int = 0, device: Optional[int] = None):
+        self._h = None
+        self._lib = _capi.load()
+        if adjoint_mode not in _capi.ADJOINT_MODES:
+            raise ValueError("adjoint_mode must be 'reference' or 'exact'")
+        self.adjoint_mode = adjoint_mode
+        self._dtype_code = _DTYPES[dtype]
+        self.np_dtype = np.float64 if self._dtype_code == _capi.F64 else np.float32
+        self.alpha_axis = np.asarray(alpha_axis, dtype=np.float64)
+        self.beta_axis = np.asarray(beta_axis, dtype=np.float64)
+        self.wavelength_axis = np.asarray(wavelength_axis, dtype=np.float64)
+        self.step_degree = step_degree
+        self.instrs = [i.pix(step_degree) for i in instrs]
+        self.templates = None if templates is None else np.ascontiguousarray(templates, dtype=np.float64)
+        self.lmm = self.templates is not None
+        self.pointings = pointings
+        self.sotf = sotf if isinstance(sotf, np.ndarray) else None
+        self.srfs = instru.get_srf([i.det_pix_size for i in instrs], step_degree * 3600)
+        n_bands = len(instrs)
+        self.local_bands = list(range(n_bands)) if local_bands is None else sorted(int(b) for b in local_bands)
+        if device is not None:
+            import torch
+            torch.cuda.set_device(device)
+
+        self.band_tables: List[geometry.BandTables] = [
+            geometry.build_band(instr, self.alpha_axis, self.beta_axis, self.wavelength_axis, srf, pointings[it],
+                                step_degree, with_adjoint=(it in self.local_bands))
+            for it, (srf, instr) in enumerate(zip(self.srfs, instrs))]
+        n_point = len(pointings[0])
+        self.instrs_oshape = [(n_point, t.n_slit, t.n_det, t.na) for t in self.band_tables]
+        self._idx = np.cumsum([0] + [int(np.prod(s)) for s in self.instrs_oshape])
+        for t, off in zip(self.band_tables, self._idx[:-1]):
+            t.out_offset = int(off)
+            if t.n_pointing != n_point:
+                raise ValueError("every band must have the same number of pointings")
+        self.channels = [ChannelView(t, n_point) for t in self.band_tables]
+        self.list_wslice = [t.wslice for t in self.band_tables]
+        self.list_local_alpha_axis = [t.local_alpha_axis for t in self.band_tables]
+        self.list_local_beta_axis = [t.local_beta_axis for t in self.band_tables]
+        self.list_local_im_shape = [t.local_shape for t in self.band_tables]
+        self.cube_shape = (len(self.wavelength_axis), len(self.alpha_axis), len(self.beta_axis))
+        self.imshape = self.cube_shape[1:]
+        ishape = ((self.templates.shape[0],) + self.imshape) if self.lmm else self.cube_shape
+        super().__init__(ishape=ishape, oshape=(int(self._idx[-1]),))
+        if self.lmm and self.templates.shape[1] != len(self.wavelength_axis):
+            raise ValueError("templates must be [K, n_lambda]")
+
+        desc = _capi.ModelDesc(self._dtype_code, self.templates.shape[0] if self.lmm else 0,
+                               len(self.alpha_axis), len(self.beta_axis), len(self.wavelength_axis), int(chunk),
+                               _capi.ptr(self.templates) if self.lmm else None)
+        handle = C.c_void_p()
+        code = self._lib.surfh_create(C.byref(desc), C.byref(handle))
+        _capi.check(None, code)
+        self._h = handle
+        self._upload_otf(sotf)
+        for it in self.local_bands:
+            self._add_band(self.band_tables[it])
+        _capi.check(self._h, self._lib.surfh_finalize(self._h))
+        # the big host tables are on the device now
+        for it in self.local_bands:
+            self.band_tables[it].adj_exact = None
+            self.band_tables[it].adj_reference = None
+
+    # ------------------------------------------------------------------ construction helpers
+    def _needed_planes(self):
+        need = np.zeros(len(self.wavelength_axis), dtype=bool)
+        for it in self.local_bands:
+            need[self.band_tables[it].wslice] = True
+        return need
+
+    def _upload_otf(self, sotf, planes_per_call: int = 128):
+        n_l, n_a, n_b = self.cube_shape
+        shape = (n_a, n_b // 2 + 1)
+        need = self._needed_planes()
+        idx = np.flatnonzero(need)
+        if len(idx) == 0:
+            return
+        # contiguous runs of needed planes, cut into pieces
+        runs = np.split(idx, np.flatnonzero(np.diff(idx) > 1) + 1)
+        for run in runs:
+            for lo in range(int(run[0]), int(run[-1]) + 1, planes_per_call):
+                hi = min(int(run[-1]) + 1, lo + planes_per_call)
+                block = sotf(lo, hi) if callable(sotf) else sotf[lo:hi]
+                if tuple(block.shape) != (hi - lo,) + shape:
+                    raise ValueError(f"sotf planes must have shape {shape}, got {tuple(block.shape[1:])}")
+                if _is_torch(block):
+                    import torch
+                    block = block.to(torch.complex128).contiguous()
+                    if block.is_cuda:
+                        torch.cuda.current_stream().synchronize()
+                    p = block.data_ptr()
+                else:
+                    block = np.ascontiguousarray(block, dtype=np.complex128)
+                    p = _capi.ptr(block)
+                _capi.check(self._h, self._lib.surfh_set_otf(self._h, lo, hi - lo, p))
+
+    def _add_band(self, t: geometry.BandTables):
+        keep: list = []
+
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return _capi.ptr(a)
+
+        d = _capi.BandDesc(
+            t.n_pointing, t.n_slit, t.na, t.nb, t.srf, t.local_shape[0], t.local_shape[1], t.wslice.start,
+            t.n_wave, t.n_det, t.out_offset,
+            arr(t.slit_a0, np.int32), arr(t.slit_b0, np.int32), arr(t.weights, np.float64),
+            arr(t.lsf, np.float64), arr(t.grid_base, np.int32), arr(t.grid_frac, np.float64),
+            _capi.csr_desc(t.adj_exact, keep), _capi.csr_desc(t.adj_reference, keep))
+        _capi.check(self._h, self._lib.surfh_add_band(self._h, C.byref(d)))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and getattr(self, "_lib", None) is not None:
+            self._lib.surfh_destroy(h)
+
+    # ------------------------------------------------------------------------------ helpers
+    @property
+    def alpha_step(self) -> float:
+        return self.alpha_axis[1] - self.alpha_axis[0]
+
+    @property
+    def beta_step(self) -> float:
+        return self.beta_axis[1] - self.beta_axis[0]
+
+    @property
+    def mode_code(self) -> int:
+        return _capi.ADJOINT_MODES[self.adjoint_mode]
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _torch_dtype(self):
+        import torch
+        return torch.float64 if self._dtype_code == _capi.F64 else torch.float32
+
+    def _stream(self) -> int:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+
+    def _dev_in(self, t, size: int):
+        t = t.to(self._torch_dtype()).contiguous().reshape(-1)
+        if not t.is_cuda:
+            raise ValueError("torch inputs must be CUDA tensors (pass numpy arrays for host data)")
+        if t.numel() != size:
+            raise ValueError(f"expected {size} elements, got {t.numel()}")
+        return t
+
+    # ------------------------------------------------------------------------------ LinOp
+    def forward(self, maps):
+        """y = H maps.  maps: [K, N, N] (or the [n_lambda, N, N] cube when templates is None)."""
+        if _is_torch(maps):
+            import torch
+            x = self._dev_in(maps, self.isize)
+            alloc = torch.empty if len(self.local_bands) == len(self.band_tables) else torch.zeros
+            y = alloc(self.osize, dtype=x.dtype, device=x.device)
+            _capi.check(self._h, self._lib.surfh_forward(self._h, x.data_ptr(), y.data_ptr(), self._stream()))
+            return y
+        x = np.ascontiguousarray(np.asarray(maps, dtype=np.float64).reshape(self.ishape))
+        y = np.zeros(self.oshape, dtype=np.float64)
+        _capi.check(self._h, self._lib.surfh_forward_host(self._h, _capi.ptr(x), _capi.ptr(y)))
+        return y
+
+    def adjoint(self, inarray):
+        """x = H^T y in the model's adjoint_mode."""
+        if _is_torch(inarray):
+            import torch
+            y = self._dev_in(inarray, self.osize)
+            x = torch.empty(self.ishape, dtype=y.dtype, device=y.device)
+            _capi.check(self._h, self._lib.surfh_adjoint(self._h, y.data_ptr(), x.data_ptr(), self.mode_code,
+                                                         self._stream()))
+            return x
+        y = np.ascontiguousarray(np.asarray(inarray, dtype=np.float64).reshape(-1))
+        if y.size != self.osize:
+            raise ValueError(f"expected {self.osize} samples, got {y.size}")
+        x = np.empty(self.ishape, dtype=np.float64)
+        _capi.check(self._h, self._lib.surfh_adjoint_host(self._h, _capi.ptr(y), _capi.ptr(x), self.mode_code))
+        return x
+
+    def fwadj(self, maps):
+        """H^T H maps without the detector vector leaving the device."""
+        import torch
+        was_numpy = not _is_torch(maps)
+        x = torch.as_tensor(np.ascontiguousarray(maps, dtype=np.float64), device="cuda") if was_numpy else maps
+        x = self._dev_in(x, self.isize)
+        out = torch.empty(self.ishape, dtype=x.dtype, device=x.device)
+        _capi.check(self._h, self._lib.surfh_fwadj(self._h, x.data_ptr(), out.data_ptr(), self.mode_code, None,
+                                                   self._stream()))
+        return out.cpu().numpy().astype(np.float64) if was_numpy else out
+
+    fwback = fwadj
+
+    def matvec(self, point):
+        return self.forward(point.reshape(self.ishape)).reshape(-1)
+
+    def rmatvec(self, point):
+        return self.adjoint(point.reshape(-1)).reshape(-1)
+
+    # ---------------------------------------------------------------- result export / scaling
+    def mapsToCube(self, maps):
+        """float32 cube = T maps (spectroModel.py:190-192)."""
+        import torch
+        if not self.lmm:
+            raise ValueError("mapsToCube needs templates")
+        was_numpy = not _is_torch(maps)
+        x = torch.as_tensor(np.ascontiguousarray(maps, dtype=np.float64), device="cuda") if was_numpy else maps
+        x = self._dev_in(x, self.isize)
+        cube = torch.empty(self.cube_shape, dtype=torch.float32, device=x.device)
+        _capi.check(self._h, self._lib.surfh_maps_to_cube(self._h, x.data_ptr(), cube.data_ptr(), self._stream()))
+        return cube.cpu().numpy() if was_numpy else cube
+
+    def cubeTomaps(self, cube):
+        """maps[k] = sum_l cube[l] * templates[k, l] (spectroModel.py:187-188); host-side export helper."""
+        return np.einsum("lij,kl->kij", np.asarray(cube), self.templates)
+
+    def real_data_janskySR_to_jansky(self, data: np.ndarray) -> np.ndarray:
+        """Jy/sr -> Jy: every slit scaled by (sum of its beta weights) * srf (spectroModel.py:225-239)."""
+        out = np.zeros_like(data)
+        for c, t in enumerate(self.band_tables):
+            block = np.array(data[self._idx[c]: self._idx[c + 1]], dtype=np.float64).reshape(self.instrs_oshape[c])
+            scale = t.weights.sum(axis=1) * t.srf
+            out[self._idx[c]: self._idx[c + 1]] = (block * scale[None, :, None, None]).ravel()
+        return out
+
+    # -------------------------------------------------------------------------- diagnostics
+    def launch_count(self) -> int:
+        return int(self._lib.surfh_launch_count(self._h))
+
+    def own_launch_count(self) -> int:
+        return int(self._lib.surfh_own_launch_count(self._h))
+
+    def workspace_bytes(self) -> int:
+        return int(self._lib.surfh_workspace_bytes(self._h))
+
+    def profile(self, enable: bool) -> None:
+        _capi.check(self._h, self._lib.surfh_profile_enable(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        cap = 32
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        nbytes = (C.c_double * cap)()
+        flops = (C.c_double * cap)()
+        n = self._lib.surfh_profile_read(self._h, cap, names, ms, nbytes, flops)
+        if n < 0:
+            raise _capi.SurfhError(n, "profile_read failed")
+        return [dict(stage=names[i].decode(), ms=float(ms[i]), bytes=float(nbytes[i]), flops=float(flops[i]))
+                for i in range(n)]
+
+
+# the reference's callers import the class under this module alias too
+SpectroLMM = spectroSigRLSCT

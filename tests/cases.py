@@ -1,0 +1,13 @@
+"""Seeded configurations shared by the oracle-vs-golden and CUDA-vs-oracle tests.  The names match
+the fixtures written by oracle/make_golden.py."""
+from surfh_b200 import synthetic
+
+CASES = {
+    "mini_1band_1p": lambda: synthetic.mini_config(1, 1),
+    "mini_2band_4p": lambda: synthetic.mini_config(2, 4),
+    "mini_2band_2p_cube": lambda: synthetic.mini_config(2, 2, lmm=False, n_pix=96),
+    "c1_band1a": lambda: synthetic.baseline_config("c1"),
+    "band2a_4p": lambda: synthetic.mrs_config(["2a"], 251, 4, 4, seed=3, name="band2a_4p"),
+}
+MINI = ["mini_1band_1p", "mini_2band_4p", "mini_2band_2p_cube"]
+FULL = ["c1_band1a", "band2a_4p"]

@@ -1,0 +1,94 @@
+"""CUDA path vs the CPU oracle and vs the golden vectors made by the reference's own code.
+Tolerances are BASELINE.json's: relative L2 <= 1e-10 in fp64, <= 1e-5 in fp32; dot-test 1e-6."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES, FULL, MINI
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"float64": 1e-10, "float32": 1e-5}
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a.ravel() - b.ravel()) / np.linalg.norm(b.ravel()))
+
+
+@pytest.fixture(scope="module")
+def built():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    from surfh_b200.model import spectroSigRLSCT
+    return spectroSigRLSCT
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", MINI)
+def test_mini_vs_oracle_and_golden(built, golden_dir, name, dtype):
+    from surfh_oracle import model as om
+    cfg = CASES[name]()
+    args = cfg.model_args()
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    v = np.random.default_rng(1234).standard_normal(int(gold["idx"][-1]))
+    for mode in ("reference", "exact"):
+        gpu = built(**args, dtype=dtype, adjoint_mode=mode)
+        cpu = om.SpectroLMM(**args, adjoint_mode=mode)
+        assert gpu.ishape == cpu.ishape and gpu.oshape == cpu.oshape
+        assert np.array_equal(gpu._idx, gold["idx"])
+        y = gpu.forward(cfg.maps)
+        assert y.shape == cpu.oshape and y.dtype == np.float64
+        assert rel(y, cpu.forward(cfg.maps)) <= TOL[dtype]
+        x = gpu.adjoint(v)
+        assert x.shape == cpu.ishape
+        assert rel(x, cpu.adjoint(v)) <= TOL[dtype]
+        if mode == "reference":  # the reference's own outputs
+            assert rel(y, gold["fwd"]) <= TOL[dtype]
+            assert rel(x, gold["adj"]) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_full_size_vs_reference_golden(built, golden_dir, name):
+    cfg = CASES[name]()
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    gpu = built(**cfg.model_args(), dtype="float64", adjoint_mode="reference")
+    y = gpu.forward(cfg.maps)
+    stride = int(gold["fwd_stride"])
+    assert rel(y[::stride], gold["fwd_sample"]) <= 1e-10
+    assert abs(np.linalg.norm(y) - float(gold["fwd_norm"])) <= 1e-10 * float(gold["fwd_norm"])
+    v = np.random.default_rng(1234).standard_normal(gpu.osize)
+    x = gpu.adjoint(v)
+    assert rel(x[:, ::7, ::7], gold["adj_sample"]) <= 1e-10
+    assert abs(np.linalg.norm(x) - float(gold["adj_norm"])) <= 1e-10 * float(gold["adj_norm"])
+
+
+@pytest.mark.parametrize("name", ["mini_2band_4p", "c1_band1a"])
+def test_dot_test_exact_adjoint(built, name):
+    """<Hx, y> = <x, H^T y> to 1e-6 (BASELINE.json) in exact mode; it holds to ~1e-13 in fp64."""
+    cfg = CASES[name]()
+    gpu = built(**cfg.model_args(), dtype="float64", adjoint_mode="exact")
+    rng = np.random.default_rng(0)
+    for _ in range(2):
+        u, v = rng.standard_normal(gpu.isize), rng.standard_normal(gpu.osize)
+        left = float(np.vdot(gpu.rmatvec(v), u))
+        right = float(np.vdot(v, gpu.matvec(u)))
+        assert abs(left - right) <= 1e-6 * abs(right)
+        assert abs(left - right) <= 1e-11 * abs(right)
+
+
+def test_device_tensors_and_fwadj(built):
+    import torch
+    cfg = CASES["mini_2band_4p"]()
+    gpu = built(**cfg.model_args(), dtype="float64", adjoint_mode="exact")
+    x = torch.as_tensor(cfg.maps, device="cuda")
+    y = gpu.forward(x)
+    assert y.is_cuda and y.shape == (gpu.osize,)
+    assert rel(y.cpu().numpy(), gpu.forward(cfg.maps)) <= 1e-14
+    q = gpu.fwadj(x)
+    assert rel(q.cpu().numpy(), gpu.adjoint(gpu.forward(cfg.maps))) <= 1e-13
+    # deterministic: bitwise-identical across runs (no atomics anywhere on the path)
+    assert torch.equal(q, gpu.fwadj(x))
+    assert torch.equal(gpu.adjoint(y), gpu.adjoint(y))
