@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the LMM instrument operator (forward + adjoint application) and of the CG loop.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c4] [--dtype float64]
+    python bench.py --impl reference ...      # the reference's CPU path (oracle) on the host cores
+
+One JSON line on stdout (rank 0).  A "step" is one application of the normal operator
+H^T H (one `forward` + one `adjoint`, the unit of work of one CG iteration) on the synthetic
+configuration named in `config.workload`:
+
+  value      applications/s, maps resident in HBM, detector vector never leaves the device
+             (timed with CUDA events on the launching stream, max over ranks)
+  e2e        the same application through the reference-facing LinOp calls with HOST buffers:
+             numpy maps -> forward -> numpy y -> adjoint -> numpy maps (H2D/D2H inside)
+  cg_iters_per_s   K iterations of the device-resident CG (fwadj + fused vector kernels
+             (+ NCCL all-reduce of the map gradient when sharded))
+  roofline   dominant hand-written kernel, achieved vs measured peak; `stages` lists every stage
+  cpu_baseline     the CPU oracle (numpy/scipy restatement of the reference path) on a bounded
+             sample of the same workload, same box, same run (rank 0, N=1)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lmm_fwd_adj_applications_per_s"
+UNIT = "applications/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c4", help="c1..c4 of BASELINE.md (default: c4, the 12-band workload)")
+    ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
+    ap.add_argument("--adjoint", default="reference", choices=["reference", "exact"])
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-pointings", type=int, default=1)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_config(name: str):
+    from surfh_b200 import synthetic
+    return synthetic.baseline_config(name)
+
+
+def band_costs(cfg, dtype_bytes):
+    """Cost model per band from the instrument table alone (no tables built)."""
+    from surfh_b200 import dist, geometry, instru
+    srfs = instru.get_srf([i.det_pix_size for i in cfg.instrs], cfg.step_degree * 3600)
+    costs = []
+    for ifu, srf, pts in zip(cfg.instrs, srfs, cfg.pointings):
+        band = ifu.pix(cfg.step_degree)
+        la, lb = geometry.local_axes(band.fov, cfg.step_degree, geometry.N_MARGIN_PIX * cfg.step_degree)
+        _, _, na, nbw, _ = geometry.slit_layout(band, cfg.beta_axis, la, lb, srf)
+        wsl = band.wslice(cfg.wavelength_axis, geometry.WAVE_MARGIN_UM)
+        costs.append(dist.band_cost(wsl.stop - wsl.start, band.n_wavel, nbw, len(pts), band.n_slit, na,
+                                    len(cfg.alpha_axis), len(la), len(lb), dtype_bytes))
+    return costs
+
+
+# ------------------------------------------------------------------- CPU reference legs
+def cpu_sample(cfg, n_pointings: int, repeats: int, warmup: int):
+    """Time the CPU oracle on a bounded sample of the workload: the first band of the configuration
+    on its own wavelength window, `n_pointings` pointings, same N, K, dtype fp64, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from surfh_b200 import synthetic
+    from surfh_oracle import model as om  # executed here only as the timed CPU baseline
+
+    band = cfg.band_names[0]
+    k = cfg.templates.shape[0]
+    sub = synthetic.mrs_config([band], len(cfg.alpha_axis), k, n_pointings, seed=0, name=f"{cfg.name}-sample")
+    model = om.SpectroLMM(**sub.model_args(), adjoint_mode="reference")
+    times = []
+    for it in range(warmup + repeats):
+        t0 = time.perf_counter()
+        y = model.forward(sub.maps)
+        model.adjoint(y)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    full_out = full_output_size(cfg)
+    frac = model.osize / full_out
+    t = float(np.median(times))
+    sample = (f"band {band.upper()} of {cfg.name} only (cube axis = that band's window, {len(sub.wavelength_axis)} "
+              f"wavelengths), {n_pointings} pointing(s), K={k}, N={len(cfg.alpha_axis)}, fp64: "
+              f"{model.osize} of {full_out} detector samples = {frac:.4f} of one application in {t:.2f} s "
+              f"(median of {repeats}); value = fraction / seconds")
+    return {"value": frac / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample,
+            "seconds_per_sample": t, "sample_fraction": frac}
+
+
+def full_output_size(cfg) -> int:
+    from surfh_b200 import geometry, instru
+    srfs = instru.get_srf([i.det_pix_size for i in cfg.instrs], cfg.step_degree * 3600)
+    total = 0
+    for ifu, srf, pts in zip(cfg.instrs, srfs, cfg.pointings):
+        band = ifu.pix(cfg.step_degree)
+        la, lb = geometry.local_axes(band.fov, cfg.step_degree, geometry.N_MARGIN_PIX * cfg.step_degree)
+        _, _, na, _, _ = geometry.slit_layout(band, cfg.beta_axis, la, lb, srf)
+        total += len(pts) * band.n_slit * band.n_wavel * na
+    return total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = build_config(args.config)
+    steps, warm = max(1, min(args.steps, 3)), 1
+    base = cpu_sample(cfg, args.cpu_sample_pointings, steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 / base["value"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_description(cfg, "float64", args),
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_description(cfg, dtype, args):
+    return {"workload": f"{cfg.name}: {len(cfg.instrs)} MRS band(s) {','.join(cfg.band_names)}, "
+                        f"K={cfg.templates.shape[0]} templates, {len(cfg.alpha_axis)}x{len(cfg.beta_axis)} maps, "
+                        f"{len(cfg.wavelength_axis)} cube wavelengths, {len(cfg.pointings[0])} pointings; "
+                        f"one step = one forward + one adjoint (H^T H) application",
+            "adjoint_mode": args.adjoint, "compute_dtype": dtype,
+            "l2_policy": "inputs larger than L2: every step streams the OTF and cube chunks (GBs) through HBM",
+            "parallelism": f"bands sharded over {args.gpus} GPU(s), all-reduce of the [K,N,N] map gradient"}
+
+
+# ------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    from surfh_b200 import dist as sdist
+    from surfh_b200 import fusion_CT, synthetic
+    from surfh_b200.model import spectroSigRLSCT
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; surfh_b200 has no CPU fallback")
+    comm = sdist.init_from_env("nccl")
+    rank = comm.rank if comm else 0
+    world = comm.world_size if comm else 1
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    tdtype = torch.float64 if args.dtype == "float64" else torch.float32
+    esz = 8 if args.dtype == "float64" else 4
+
+    cfg = build_config(args.config)
+    costs = band_costs(cfg, esz)
+    local = sdist.local_band_indices(costs, comm)
+    shape = cfg.imshape
+    t_setup = time.time()
+    sotf = lambda lo, hi: synthetic.ir2fr_device(cfg.psf[lo:hi], shape, dev, torch.float64)  # noqa: E731
+    model = spectroSigRLSCT(sotf, cfg.templates, cfg.alpha_axis, cfg.beta_axis, cfg.wavelength_axis, cfg.instrs,
+                            cfg.step_degree, cfg.pointings, dtype=args.dtype, adjoint_mode=args.adjoint,
+                            local_bands=local, chunk=args.chunk, device=local_rank)
+    setup_s = time.time() - t_setup
+
+    x = torch.as_tensor(cfg.maps, device=dev, dtype=tdtype)
+    q = torch.empty_like(x)
+    lib, h = model._lib, model.handle
+    from surfh_b200 import _capi
+
+    def application():
+        _capi.check(h, lib.surfh_fwadj(h, x.data_ptr(), q.data_ptr(), model.mode_code, None,
+                                       torch.cuda.current_stream().cuda_stream))
+        if comm:
+            comm.allreduce_sum(q)
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if comm:
+            comm.barrier()
+        torch.cuda.synchronize()
+        if profile:
+            model.profile(True)
+        launches0 = model.own_launch_count()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if comm:
+            comm.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if comm:
+            comm.allreduce_max(ms)
+        stages = model.profile_read() if profile else None
+        if profile:
+            model.profile(False)
+        return float(ms.item()), model.own_launch_count() - launches0, clocks, stages
+
+    # ---- device-resident applications (the headline `value`), stage events inside the timed region
+    ms_total, launches, clocks, stages = timed(application, args.steps, args.warmup, profile=True)
+    ms_step = ms_total / args.steps
+    value = 1e3 / ms_step
+
+    # ---- CG iterations
+    y = model.forward(x)
+    if comm:  # every rank needs only its own slices; keep the local result
+        pass
+    cg = fusion_CT.DeviceCG(model, y, 1.0, 5e3, comm=comm)
+    cg.start(np.zeros(model.ishape), args.steps + args.warmup + 8)
+    ms_cg, _, _, _ = timed(lambda: cg.step(False), args.steps, args.warmup)
+    cg_iters = 1e3 * args.steps / ms_cg
+
+    # ---- end to end through the LinOp API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        maps_host = torch.from_numpy(cfg.maps.copy()).pin_memory()
+        y_host = torch.empty(model.osize, dtype=torch.float64).pin_memory()
+        out_host = torch.empty(model.ishape, dtype=torch.float64).pin_memory()
+        n_out = int(lib.surfh_output_size(h))
+
+        def application_host():
+            _capi.check(h, lib.surfh_forward_host(h, maps_host.data_ptr(), y_host.data_ptr()))
+            _capi.check(h, lib.surfh_adjoint_host(h, y_host.data_ptr(), out_host.data_ptr(), model.mode_code))
+            if comm:
+                part = out_host.to(dev, non_blocking=True)
+                comm.allreduce_sum(part)
+                out_host.copy_(part)
+
+        steps_h = max(1, min(args.steps, 5))
+        application_host()
+        torch.cuda.synchronize()
+        if comm:
+            comm.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps_h):
+            application_host()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if comm:
+            comm.allreduce_max(dt)
+        h2d = 8 * (model.isize + n_out)
+        d2h = 8 * (n_out + model.isize)
+        e2e = {"value": steps_h / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": steps_h,
+               "path": "surfh_forward_host + surfh_adjoint_host (pinned numpy buffers, fp64 on the host side)"}
+
+    if rank != 0:
+        return
+
+    # ---- roofline from the stage events of the timed region
+    hbm_peak, peak_src = measured_peaks()
+    own_hbm = {"lmm_otf_fwd", "lmm_otf_adj", "slit_gather", "slit_scatter", "cg_fused"}
+    own_fma = {"spectral_gemm_fwd", "spectral_gemm_adj"}
+    stage_rows = []
+    tot_ms = sum(s["ms"] for s in stages) or 1.0
+    for s in stages:
+        per_step_ms = s["ms"] / args.steps
+        row = {"stage": s["stage"], "ms_per_step": per_step_ms, "share": s["ms"] / tot_ms,
+               "own": s["stage"] in own_hbm | own_fma}
+        if s["stage"] in own_fma:
+            row.update(bound="fma_" + ("fp64" if esz == 8 else "fp32"), unit="TFLOP/s",
+                       achieved=s["flops"] / (s["ms"] * 1e-3) / 1e12 if s["ms"] > 0 else None)
+        else:
+            row.update(bound="hbm", unit="GB/s",
+                       achieved=s["bytes"] / (s["ms"] * 1e-3) / 1e9 if s["ms"] > 0 else None)
+            if row["achieved"] is not None:
+                row["frac"] = row["achieved"] / hbm_peak
+        stage_rows.append(row)
+    own_hbm_rows = [r for r in stage_rows if r["stage"] in own_hbm and r.get("achieved")]
+    top = max(own_hbm_rows, key=lambda r: r["ms_per_step"]) if own_hbm_rows else None
+    roofline = None
+    if top:
+        roofline = {"kernel": top["stage"], "bound": "hbm", "achieved": top["achieved"], "peak": hbm_peak,
+                    "unit": "GB/s", "frac": top["achieved"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "share_of_step": top["share"]}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_sample(cfg, args.cpu_sample_pointings, 1, 0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if esz == 8 else "f32", "data": "synthetic", "config": workload_description(cfg, args.dtype, args),
+        "cg_iters_per_s": cg_iters, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "stages": stage_rows, "cpu_baseline": cpu,
+        "setup_s": setup_s, "local_bands_rank0": local, "workspace_gb": model.workspace_bytes() / 1e9,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

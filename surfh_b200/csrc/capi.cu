@@ -432,6 +432,12 @@ template <typename T> struct ModelImpl : surfh_model {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         SURFH_CUDA(cudaFuncSetAttribute(otgemm_kernel<T, G::BM, G::BN, G::BK, G::TM, G::TN, false, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (std::is_same<T, double>::value) {
+            SURFH_CUDA(cudaFuncSetAttribute(dgemm_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)dgemm_smem_bytes<true, true>()));
+            SURFH_CUDA(cudaFuncSetAttribute(dgemm_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)dgemm_smem_bytes<false, false>()));
+        }
         SURFH_CUDA(cudaDeviceSynchronize());
         finalized = true;
     }
@@ -488,34 +494,47 @@ template <typename T> struct ModelImpl : surfh_model {
             SURFH_FFT(FftTraits<T>::inv(p, reinterpret_cast<C*>(in), reinterpret_cast<T*>(out)));
     }
 
-    void gemm_forward(BandT<T>& b, T* y, cudaStream_t st) {
-        using G = GemmCfg<T>;
+    GemmArgs<T> gemm_args(BandT<T>& b, T* y, bool adjoint) {
         GemmArgs<T> g;
-        g.M = b.nd; g.N = b.Nn; g.K = b.KB;
-        g.A = b.lsf.template as<T>(); g.aM = b.t_wrow.template as<int32_t>(); g.aK = b.t_ident.template as<int32_t>();
-        g.B = b.G.template as<T>(); g.bK = b.t_gK.template as<int32_t>(); g.bN = b.t_gN.template as<int32_t>();
-        g.C = y + b.out_offset; g.cM = b.t_yM.template as<int32_t>(); g.cN = b.t_yN.template as<int32_t>();
+        if (!adjoint) {  // y = W . G
+            g.M = b.nd; g.N = b.Nn; g.K = b.KB;
+            g.A = b.lsf.template as<T>(); g.aM = b.t_wrow.template as<int32_t>(); g.aK = b.t_ident.template as<int32_t>();
+            g.B = b.G.template as<T>(); g.bK = b.t_gK.template as<int32_t>(); g.bN = b.t_gN.template as<int32_t>();
+            g.C = y + b.out_offset; g.cM = b.t_yM.template as<int32_t>(); g.cN = b.t_yN.template as<int32_t>();
+        } else {  // Gt = W^T . y
+            g.M = b.KB; g.N = b.Nn; g.K = b.nd;
+            g.A = b.lsf.template as<T>(); g.aM = b.t_ident.template as<int32_t>(); g.aK = b.t_wrow.template as<int32_t>();
+            g.B = y + b.out_offset; g.bK = b.t_yM.template as<int32_t>(); g.bN = b.t_yN.template as<int32_t>();
+            g.C = b.G.template as<T>(); g.cM = b.t_gK.template as<int32_t>(); g.cN = b.t_gN.template as<int32_t>();
+        }
+        return g;
+    }
+
+    // SIMT path (fp32): one launch per band
+    void gemm_simt(BandT<T>& b, T* y, bool adjoint, cudaStream_t st) {
+        using G = GemmCfg<T>;
+        GemmArgs<T> g = gemm_args(b, y, adjoint);
         dim3 grid(ceil_div(g.N, G::BN), ceil_div(g.M, G::BM));
         const double bytes = sizeof(T) * ((double)b.nd * b.KB + (double)b.nl * b.ncol + (double)b.out_size);
-        Scope sc(this, ST_GEMM_FWD, st, bytes, 2.0 * g.M * g.N * g.K, 1, true);
-        otgemm_kernel<T, G::BM, G::BN, G::BK, G::TM, G::TN, true, true>
-            <<<grid, (G::BM / G::TM) * (G::BN / G::TN), otgemm_smem_bytes<T, G::BM, G::BN, G::BK>(), st>>>(g);
+        Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, 2.0 * g.M * g.N * g.K, 1, true);
+        const int threads = (G::BM / G::TM) * (G::BN / G::TN);
+        const size_t smem = otgemm_smem_bytes<T, G::BM, G::BN, G::BK>();
+        if (!adjoint)
+            otgemm_kernel<T, G::BM, G::BN, G::BK, G::TM, G::TN, true, true><<<grid, threads, smem, st>>>(g);
+        else
+            otgemm_kernel<T, G::BM, G::BN, G::BK, G::TM, G::TN, false, false><<<grid, threads, smem, st>>>(g);
         SURFH_CUDA(cudaGetLastError());
     }
 
-    void gemm_adjoint(BandT<T>& b, const T* y, cudaStream_t st) {
-        using G = GemmCfg<T>;
-        GemmArgs<T> g;
-        g.M = b.KB; g.N = b.Nn; g.K = b.nd;
-        g.A = b.lsf.template as<T>(); g.aM = b.t_ident.template as<int32_t>(); g.aK = b.t_wrow.template as<int32_t>();
-        g.B = y + b.out_offset; g.bK = b.t_yM.template as<int32_t>(); g.bN = b.t_yN.template as<int32_t>();
-        g.C = b.G.template as<T>(); g.cM = b.t_gK.template as<int32_t>(); g.cN = b.t_gN.template as<int32_t>();
-        dim3 grid(ceil_div(g.N, G::BN), ceil_div(g.M, G::BM));
-        const double bytes = sizeof(T) * ((double)b.nd * b.KB + (double)b.nl * b.ncol + (double)b.out_size);
-        Scope sc(this, ST_GEMM_ADJ, st, bytes, 2.0 * g.M * g.N * g.K, 1, true);
-        otgemm_kernel<T, G::BM, G::BN, G::BK, G::TM, G::TN, false, false>
-            <<<grid, (G::BM / G::TM) * (G::BN / G::TN), otgemm_smem_bytes<T, G::BM, G::BN, G::BK>(), st>>>(g);
-        SURFH_CUDA(cudaGetLastError());
+    // FP64 tensor path: all bands in one grouped launch (per group of kMaxGemmGroup bands)
+    void gemm_grouped_f64(double* y, bool adjoint, cudaStream_t st);
+
+    void gemm_all(T* y, bool adjoint, cudaStream_t st) {
+        if (std::is_same<T, double>::value) {
+            gemm_grouped_f64(reinterpret_cast<double*>(y), adjoint, st);
+        } else {
+            for (auto& bp : bands) gemm_simt(*bp, y, adjoint, st);
+        }
     }
 
     static constexpr int kLB = 4;  // wavelengths per thread in the slit kernels
@@ -595,7 +614,7 @@ template <typename T> struct ModelImpl : surfh_model {
                 gather_chunk(c0, c1, st);
             }
         }
-        for (auto& bp : bands) gemm_forward(*bp, y, st);
+        gemm_all(y, false, st);
     }
 
     void adjoint(const void* yv, void* xv, int mode, cudaStream_t st) override {
@@ -604,7 +623,7 @@ template <typename T> struct ModelImpl : surfh_model {
         SURFH_REQUIRE(mode == SURFH_ADJ_EXACT || mode == SURFH_ADJ_REFERENCE, "unknown adjoint mode");
         const T* y = reinterpret_cast<const T*>(yv);
         T* x = reinterpret_cast<T*>(xv);
-        for (auto& bp : bands) gemm_adjoint(*bp, y, st);
+        gemm_all(const_cast<T*>(y), true, st);
         if (K == 0) {
             Scope sc(this, ST_MEMSET, st, (double)Nl * plane * sizeof(T), 0, 1, false);
             SURFH_CUDA(cudaMemsetAsync(x, 0, (size_t)Nl * plane * sizeof(T), st));
@@ -770,6 +789,36 @@ template <typename T> struct ModelImpl : surfh_model {
         SURFH_CUDA(cudaGetLastError());
     }
 };
+
+template <> void ModelImpl<float>::gemm_grouped_f64(double*, bool, cudaStream_t) {
+    throw Error(SURFH_ESTATE, "internal: fp64 GEMM on an fp32 model");
+}
+
+template <> void ModelImpl<double>::gemm_grouped_f64(double* y, bool adjoint, cudaStream_t st) {
+    for (size_t first = 0; first < bands.size(); first += kMaxGemmGroup) {
+        GemmBatch batch;
+        batch.count = 0;
+        batch.tile_start[0] = 0;
+        double bytes = 0, flops = 0;
+        for (size_t i = first; i < std::min(bands.size(), first + (size_t)kMaxGemmGroup); ++i) {
+            BandT<double>& b = *bands[i];
+            GemmArgs<double> g = gemm_args(b, y, adjoint);
+            batch.p[batch.count] = g;
+            batch.tile_start[batch.count + 1] =
+                batch.tile_start[batch.count] + ceil_div(g.M, kDBM) * ceil_div(g.N, kDBN);
+            batch.count++;
+            bytes += sizeof(double) * ((double)b.nd * b.KB + (double)b.nl * b.ncol + (double)b.out_size);
+            flops += 2.0 * g.M * g.N * g.K;
+        }
+        Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, flops, 1, true);
+        const int tiles = batch.tile_start[batch.count];
+        if (!adjoint)
+            dgemm_mma_kernel<true, true><<<tiles, 256, dgemm_smem_bytes<true, true>(), st>>>(batch);
+        else
+            dgemm_mma_kernel<false, false><<<tiles, 256, dgemm_smem_bytes<false, false>(), st>>>(batch);
+        SURFH_CUDA(cudaGetLastError());
+    }
+}
 
 }  // namespace surfh
 

@@ -119,7 +119,7 @@ cg_step_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ d, co
     double total;
     if (finish_reduction(bs, sc.partial, sc.ticket, smem, total)) {
         const int it = (int)s[4] + 1;
-        s[2] = alpha;
+        if (!REFRESH) s[2] = alpha;
         s[3] = total / rho;
         s[0] = total;
         s[4] = (double)it;
@@ -130,8 +130,9 @@ cg_step_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ d, co
 // x += alpha d only (first phase of a refresh iteration)
 template <typename T>
 __global__ void __launch_bounds__(kCgThreads)
-cg_axpy_alpha_kernel(T* __restrict__ x, const T* __restrict__ d, size_t n, const double* __restrict__ s) {
+cg_axpy_alpha_kernel(T* __restrict__ x, const T* __restrict__ d, size_t n, double* __restrict__ s) {
     const double alpha = s[0] / s[1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) s[2] = alpha;  // nobody reads s[2] in this kernel
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         x[i] = (T)((double)x[i] + alpha * (double)d[i]);
 }

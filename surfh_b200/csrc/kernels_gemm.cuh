@@ -189,4 +189,195 @@ constexpr size_t otgemm_smem_bytes() {
     return sizeof(T) * 2 * BK * ((BM + 2) + (BN + 2));
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP64 path: the same offset-table contraction on the FP64 tensor pipe (DMMA,
+// mma.sync.aligned.m8n8k4.f64), grouped over all bands of the model in ONE launch so that the
+// 128x64 tiles of every band fill the 148 SMs in many waves instead of 1.5 per band.
+//
+//   CTA tile 128x64, BK = 16, 8 warps as 4 (m) x 2 (n), warp tile 32x32 = 4x4 m8n8 tiles,
+//   two CTAs per SM (<= 128 registers, 2 x 60 KB shared memory).
+//   Shared layouts follow the operand's contiguous direction so global->shared needs no transpose:
+//     K-fast operand  -> [row][k], leading dimension BK + 4
+//     row-fast operand-> [k][row], leading dimension rows + 4
+//   Both leading dimensions are = 4 (mod 16) doubles, which makes the m8n8k4 fragment reads
+//   (4 k-lanes x 8 row-lanes, 64-bit each) bank-conflict-free.
+constexpr int kMaxGemmGroup = 16;
+
+struct GemmBatch {
+    int count;
+    int tile_start[kMaxGemmGroup + 1];  // prefix sum of CTA tiles per problem
+    GemmArgs<double> p[kMaxGemmGroup];
+};
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int kDBM = 128, kDBN = 64, kDBK = 16;
+constexpr int kDLdK = kDBK + 4;    // [row][k] layouts
+constexpr int kDLdM = kDBM + 4;    // A as [k][m]
+constexpr int kDLdN = kDBN + 4;    // B as [k][n]
+
+template <bool A_KFAST, bool B_KFAST>
+constexpr size_t dgemm_smem_bytes() {
+    return sizeof(double) * 2 * ((A_KFAST ? kDBM * kDLdK : kDBK * kDLdM) + (B_KFAST ? kDBN * kDLdK : kDBK * kDLdN));
+}
+
+template <bool A_KFAST, bool B_KFAST>
+__global__ void __launch_bounds__(256, 2)
+dgemm_mma_kernel(const __grid_constant__ GemmBatch batch) {
+    constexpr int NT = 256;
+    constexpr int EA = kDBM * kDBK / NT;  // 8
+    constexpr int EB = kDBN * kDBK / NT;  // 4
+    constexpr int A_STAGE = A_KFAST ? kDBM * kDLdK : kDBK * kDLdM;
+    constexpr int B_STAGE = B_KFAST ? kDBN * kDLdK : kDBK * kDLdN;
+    extern __shared__ __align__(16) unsigned char gemm_smem[];
+    double* As = reinterpret_cast<double*>(gemm_smem);
+    double* Bs = As + 2 * A_STAGE;
+
+    // ---- which problem, which tile --------------------------------------------------------
+    int pi = 0;
+    while (pi + 1 < batch.count && (int)blockIdx.x >= batch.tile_start[pi + 1]) ++pi;
+    const GemmArgs<double>& g = batch.p[pi];
+    const int local_tile = blockIdx.x - batch.tile_start[pi];
+    const int tiles_n = (g.N + kDBN - 1) / kDBN;
+    const int m0 = (local_tile / tiles_n) * kDBM, n0 = (local_tile % tiles_n) * kDBN;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps
+    const int gq = lane >> 2, tq = lane & 3;
+
+    // ---- loader mapping (see otgemm_kernel) ----------------------------------------------
+    int32_t a_fix[A_KFAST ? EA : 1], b_fix[B_KFAST ? EB : 1];
+    bool a_ok[A_KFAST ? EA : 1], b_ok[B_KFAST ? EB : 1];
+    if (A_KFAST) {
+#pragma unroll
+        for (int i = 0; i < EA; ++i) {
+            const int m = m0 + tid / kDBK + i * (NT / kDBK);
+            a_ok[i] = m < g.M;
+            a_fix[i] = a_ok[i] ? __ldg(g.aM + m) : 0;
+        }
+    } else {
+        const int m = m0 + tid % kDBM;
+        a_ok[0] = m < g.M;
+        a_fix[0] = a_ok[0] ? __ldg(g.aM + m) : 0;
+    }
+    if (B_KFAST) {
+#pragma unroll
+        for (int i = 0; i < EB; ++i) {
+            const int n = n0 + tid / kDBK + i * (NT / kDBK);
+            b_ok[i] = n < g.N;
+            b_fix[i] = b_ok[i] ? __ldg(g.bN + n) : 0;
+        }
+    } else {
+        const int n = n0 + tid % kDBN;
+        b_ok[0] = n < g.N;
+        b_fix[0] = b_ok[0] ? __ldg(g.bN + n) : 0;
+    }
+    double ra[EA], rb[EB];
+    auto load_slab = [&](int k0) {
+        if (A_KFAST) {
+            const int k = k0 + tid % kDBK;
+            const bool kok = k < g.K;
+            const int32_t ko = kok ? __ldg(g.aK + k) : 0;
+#pragma unroll
+            for (int i = 0; i < EA; ++i) ra[i] = (kok && a_ok[i]) ? __ldg(g.A + a_fix[i] + ko) : 0.0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < EA; ++i) {
+                const int k = k0 + tid / kDBM + i * (NT / kDBM);
+                ra[i] = (k < g.K && a_ok[0]) ? __ldg(g.A + a_fix[0] + __ldg(g.aK + k)) : 0.0;
+            }
+        }
+        if (B_KFAST) {
+            const int k = k0 + tid % kDBK;
+            const bool kok = k < g.K;
+            const int32_t ko = kok ? __ldg(g.bK + k) : 0;
+#pragma unroll
+            for (int i = 0; i < EB; ++i) rb[i] = (kok && b_ok[i]) ? __ldg(g.B + b_fix[i] + ko) : 0.0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < EB; ++i) {
+                const int k = k0 + tid / kDBN + i * (NT / kDBN);
+                rb[i] = (k < g.K && b_ok[0]) ? __ldg(g.B + b_fix[0] + __ldg(g.bK + k)) : 0.0;
+            }
+        }
+    };
+    auto store_slab = [&](int buf) {
+        double* a = As + buf * A_STAGE;
+        double* b = Bs + buf * B_STAGE;
+        if (A_KFAST) {
+#pragma unroll
+            for (int i = 0; i < EA; ++i) a[(tid / kDBK + i * (NT / kDBK)) * kDLdK + tid % kDBK] = ra[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < EA; ++i) a[(tid / kDBM + i * (NT / kDBM)) * kDLdM + tid % kDBM] = ra[i];
+        }
+        if (B_KFAST) {
+#pragma unroll
+            for (int i = 0; i < EB; ++i) b[(tid / kDBK + i * (NT / kDBK)) * kDLdK + tid % kDBK] = rb[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < EB; ++i) b[(tid / kDBN + i * (NT / kDBN)) * kDLdN + tid % kDBN] = rb[i];
+        }
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    load_slab(0);
+    store_slab(0);
+    __syncthreads();
+    const int n_slab = (g.K + kDBK - 1) / kDBK;
+    for (int sidx = 0; sidx < n_slab; ++sidx) {
+        const int buf = sidx & 1;
+        if (sidx + 1 < n_slab) load_slab((sidx + 1) * kDBK);
+        const double* a = As + buf * A_STAGE;
+        const double* b = Bs + buf * B_STAGE;
+#pragma unroll
+        for (int kk = 0; kk < kDBK; kk += 4) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = wm * 32 + i * 8 + gq;
+                fa[i] = A_KFAST ? a[row * kDLdK + kk + tq] : a[(kk + tq) * kDLdM + row];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = wn * 32 + j * 8 + gq;
+                fb[j] = B_KFAST ? b[col * kDLdK + kk + tq] : b[(kk + tq) * kDLdN + col];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        }
+        if (sidx + 1 < n_slab) {
+            store_slab(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogue ----------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + wn * 32 + j * 8 + tq * 2;
+        const bool ok0 = n < g.N, ok1 = n + 1 < g.N;
+        const int32_t c0 = ok0 ? __ldg(g.cN + n) : 0, c1 = ok1 ? __ldg(g.cN + n + 1) : 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + wm * 32 + i * 8 + gq;
+            if (m < g.M) {
+                const int32_t cm = __ldg(g.cM + m);
+                if (ok0) g.C[cm + c0] = acc[i][j][0];
+                if (ok1) g.C[cm + c1] = acc[i][j][1];
+            }
+        }
+    }
+}
+
 }  // namespace surfh

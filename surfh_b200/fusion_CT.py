@@ -1,0 +1,277 @@
+"""Quadratic-regularised fusion solve, API of `surfh.Simulation.fusion_CT`, run on the device.
+
+    J(x) = 1/2 ( mu_spectro * ||y - H x||^2  +  mu_reg * (||D_r x||^2 + ||D_c x||^2) )
+
+solved by linear conjugate gradient on  Q x = b,  Q = mu_s H^T H + mu_r (D_r^T D_r + D_c^T D_c),
+b = mu_s H^T y.  The whole iteration stays on the GPU: H^T H through `surfh_fwadj`, the
+regulariser stencil + <d,Qd>, the x/r updates + <r,r> and the direction update are three fused
+kernels whose scalars never visit the host; the host reads the gradient norm only when a callback
+or the stopping test asks for it.
+
+Reference interface mirrored (paths relative to /root/reference):
+    NpDiff_r, NpDiff_c                       surfh/Simulation/fusion_CT.py:16-43
+    QuadCriterion_MRS(...).run_method(...)   surfh/Simulation/fusion_CT.py:67-238
+    QuadCriterion_MRS.get_crit_val           surfh/Simulation/fusion_CT.py:242-265
+    qmm.lcg (third party, restated; recurrences and stopping rule as documented in
+    the test oracle's thirdparty module -- parity with qmm itself is unpinned)
+"""
+from __future__ import annotations
+
+import time
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _capi
+from .linop import LinOp
+
+REFRESH_PERIOD = 50  # lcg recomputes r = b - Q x exactly on iterations 0, 50, 100, ...
+
+
+class NpDiff_r(LinOp):
+    """Circular first difference along rows: (D x)[k,i,j] = x[k,i-1,j] - x[k,i,j]."""
+
+    def __init__(self, maps_shape):
+        super().__init__(ishape=maps_shape, oshape=maps_shape)
+
+    def forward(self, x):
+        return np.roll(x, 1, axis=1) - x
+
+    def adjoint(self, y):
+        return np.roll(y, -1, axis=1) - y
+
+
+class NpDiff_c(LinOp):
+    """Circular first difference along columns: (D x)[k,i,j] = x[k,i,j-1] - x[k,i,j]."""
+
+    def __init__(self, maps_shape):
+        super().__init__(ishape=maps_shape, oshape=maps_shape)
+
+    def forward(self, x):
+        return np.roll(x, 1, axis=2) - x
+
+    def adjoint(self, y):
+        return np.roll(y, -1, axis=2) - y
+
+
+class OptimizeResult(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class DeviceCG:
+    """Device-resident state of one lcg solve on a `spectroSigRLSCT` model."""
+
+    def __init__(self, model, y, mu_spectro: float, mu_reg: float, comm=None):
+        torch = _torch()
+        self.model = model
+        self.lib = model._lib
+        self.h = model.handle
+        self.mu_s, self.mu_r = float(mu_spectro), float(mu_reg)
+        self.comm = comm
+        self.tdtype = model._torch_dtype()
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.y = self._to_dev(y).reshape(-1)
+        if self.y.numel() != model.osize:
+            raise ValueError(f"data has {self.y.numel()} samples, model produces {model.osize}")
+        self.n = model.isize
+
+    def _to_dev(self, a):
+        torch = _torch()
+        if isinstance(a, np.ndarray):
+            a = torch.from_numpy(np.ascontiguousarray(a))
+        return a.to(device=self.dev, dtype=self.tdtype).contiguous()
+
+    def _stream(self):
+        return _torch().cuda.current_stream().cuda_stream
+
+    def _check(self, code):
+        _capi.check(self.h, code)
+
+    def hessp(self, v, out):
+        """out = mu_s H^T H v + mu_r (D_r^T D_r + D_c^T D_c) v ; s[1] = <v, out>."""
+        self._check(self.lib.surfh_fwadj(self.h, v.data_ptr(), out.data_ptr(), self.model.mode_code, None,
+                                         self._stream()))
+        if self.comm is not None:
+            self.comm.allreduce_sum(out)
+        self._check(self.lib.surfh_cg_regularise_dot(self.h, v.data_ptr(), out.data_ptr(), self.mu_s, self.mu_r,
+                                                     self.s.data_ptr(), self._stream()))
+
+    def start(self, x0, max_iter: int):
+        torch = _torch()
+        self.x = self._to_dev(x0).reshape(-1).clone()
+        self.s = torch.zeros(_capi.CG_NSCALARS + max_iter + 2, dtype=torch.float64, device=self.dev)
+        self.b = torch.empty(self.n, dtype=self.tdtype, device=self.dev)
+        self._check(self.lib.surfh_adjoint(self.h, self.y.data_ptr(), self.b.data_ptr(), self.model.mode_code,
+                                           self._stream()))
+        if self.comm is not None:
+            self.comm.allreduce_sum(self.b)
+        if self.mu_s != 1.0:
+            self.b.mul_(self.mu_s)
+        self.q = torch.empty_like(self.b)
+        self.r = torch.empty_like(self.b)
+        self.d = torch.empty_like(self.b)
+        self.hessp(self.x, self.q)
+        self._check(self.lib.surfh_cg_start(self.h, self.b.data_ptr(), self.q.data_ptr(), self.r.data_ptr(),
+                                            self.d.data_ptr(), self.s.data_ptr(), self._stream()))
+        self.iteration = 0
+
+    def step(self, refresh: bool):
+        self.hessp(self.d, self.q)
+        if refresh:
+            self._check(self.lib.surfh_cg_refresh(self.h, 0, self.x.data_ptr(), None, self.d.data_ptr(), None, None,
+                                                  self.s.data_ptr(), self._stream()))
+            self.hessp(self.x, self.q)
+            self._check(self.lib.surfh_cg_refresh(self.h, 1, None, self.r.data_ptr(), self.d.data_ptr(),
+                                                  self.b.data_ptr(), self.q.data_ptr(), self.s.data_ptr(),
+                                                  self._stream()))
+        else:
+            self._check(self.lib.surfh_cg_update(self.h, self.x.data_ptr(), self.r.data_ptr(), self.d.data_ptr(),
+                                                 self.q.data_ptr(), self.s.data_ptr(), self._stream()))
+        self.iteration += 1
+
+    def grad_norm_history(self):
+        return self.s[_capi.CG_NSCALARS: _capi.CG_NSCALARS + self.iteration + 1].cpu().numpy()
+
+    def criterion(self, x) -> float:
+        """J(x), everything reduced on the device; the only host traffic is two doubles."""
+        torch = _torch()
+        x = self._to_dev(x).reshape(-1)
+        hx = self.model.forward(x.reshape(self.model.ishape))
+        out = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        total = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        idx = self.model._idx
+        first = True
+        for it in self.model.local_bands:
+            lo, hi = int(idx[it]), int(idx[it + 1])
+            esz = hx.element_size()
+            self._check(self.lib.surfh_criterion_terms(
+                self.h, self.y.data_ptr() + lo * esz, hx.data_ptr() + lo * esz, hi - lo,
+                x.data_ptr() if first else None, out.data_ptr(), self._stream()))
+            total += out
+            first = False
+        if self.comm is not None:
+            data = total[:1].clone()
+            self.comm.allreduce_sum(data)
+            total[0] = data[0]
+        t = total.cpu().numpy()
+        return float((self.mu_s * t[0] + self.mu_r * t[1]) / 2)
+
+
+def lcg(model, y, mu_spectro=1.0, mu_reg=1.0, x0=None, tol=1e-4, max_iter=500, min_iter=0,
+        callback: Optional[Callable] = None, refresh: int = REFRESH_PERIOD, check_every: int = 10, comm=None,
+        numpy_result: bool = True) -> OptimizeResult:
+    """Linear CG on the device.  `res.x` is a flat device tensor while iterating (callbacks may
+    `.reshape` it) and, at return, a numpy array of the model's input shape (`numpy_result`)."""
+    torch = _torch()
+    cg = DeviceCG(model, y, mu_spectro, mu_reg, comm=comm)
+    if x0 is None:
+        x0 = np.zeros(model.ishape)
+    cg.start(x0, max_iter)
+    res = OptimizeResult(x=cg.x, success=True, status=99, nit=max_iter, grad_norm=[], time=[time.time()],
+                         message="maximum number of iterations reached")
+    size_tol = cg.n * tol
+    for iteration in range(max_iter):
+        cg.step(refresh=bool(refresh) and iteration % refresh == 0)
+        last = iteration == max_iter - 1
+        if callback is not None or last or (iteration + 1) % check_every == 0:
+            res["grad_norm"] = list(cg.grad_norm_history())
+            res["time"].append(time.time())
+            if callback is not None:
+                callback(res)
+            if np.sqrt(res["grad_norm"][-1]) < size_tol and iteration >= min_iter:
+                res["status"], res["nit"] = 1, iteration + 1
+                res["message"] = "gradient norm below tolerance"
+                break
+    torch.cuda.current_stream().synchronize()
+    res["grad_norm"] = list(cg.grad_norm_history())
+    res["time"].append(time.time())
+    res["x"] = cg.x.reshape(model.ishape).cpu().numpy().astype(np.float64) if numpy_result \
+        else cg.x.reshape(model.ishape)
+    res["solver"] = cg
+    return res
+
+
+class QuadCriterion_MRS:
+    """Same constructor and `run_method` as the reference class; 'separated' gradients and the
+    'lcg' method run on the device.  ('joint' gradients and qmm.mmmg are SURVEY section 8f items.)"""
+
+    def __init__(self, mu_spectro, y_spectro, model_spectro, mu_reg, printing=False, gradient="separated",
+                 comm=None):
+        self.mu_spectro = mu_spectro
+        self.y_spectro = y_spectro
+        self.model_spectro = model_spectro
+        self.n_spec = model_spectro.ishape[0]
+        self.it = 1
+        assert isinstance(mu_reg, (float, int, list, np.ndarray))
+        self.mu_reg = mu_reg
+        if isinstance(mu_reg, (list, np.ndarray)):
+            assert len(mu_reg) == self.n_spec
+        shape_target = model_spectro.ishape[1:]
+        self.shape_of_output = (self.n_spec, shape_target[0], shape_target[1])
+        if gradient != "separated":
+            raise NotImplementedError("only gradient='separated' is implemented on the device")
+        self.npdiff_r = NpDiff_r(self.shape_of_output)
+        self.npdiff_c = NpDiff_c(self.shape_of_output)
+        self.L_mu = np.copy(mu_reg) if isinstance(mu_reg, (list, np.ndarray)) else np.ones(self.n_spec) * mu_reg
+        self.printing = printing
+        self.gradient = gradient
+        self.comm = comm
+        self.L_crit_val = []
+        self._cg: Optional[DeviceCG] = None
+
+    def _solver(self) -> DeviceCG:
+        if self._cg is None:
+            self._cg = DeviceCG(self.model_spectro, self.y_spectro, self.mu_spectro, self.mu_reg, comm=self.comm)
+        return self._cg
+
+    def run_method(self, method="lcg", maximum_iterations=10, tolerance=1e-12, calc_crit=False, perf_crit=None,
+                   value_init=0.5):
+        assert isinstance(self.mu_reg, (int, float))
+        if method != "lcg":
+            raise NotImplementedError("only method='lcg' is implemented on the device")
+        if isinstance(value_init, (float, int)):
+            init = np.ones(self.shape_of_output) * value_init
+        else:
+            assert tuple(value_init.shape) == self.shape_of_output
+            init = value_init
+        self.L_crit_val = []
+
+        def perf_crit_with_reshape(res):
+            crit_val = self.get_crit_val(res.x.reshape(self.shape_of_output))
+            self.L_crit_val.append(crit_val)
+            if self.printing:
+                print(f"Criterion value = {crit_val}\n")
+
+        def print_last_grad_norm(res):
+            if self.printing:
+                print(f"Iteration n°{self.it}, Grad norm = {res.grad_norm[-1]}")
+            self.it = self.it + 1
+
+        def print_last_grad_norm_and_crit(res):
+            print_last_grad_norm(res)
+            if self.it % 5 == 2:
+                perf_crit_with_reshape(res)
+
+        if calc_crit and perf_crit is None:
+            callback = lambda res: self.L_crit_val.append(self.get_crit_val(res.x.reshape(self.shape_of_output)))  # noqa: E731
+        elif not calc_crit and perf_crit is not None:
+            callback = print_last_grad_norm
+        elif calc_crit and perf_crit is not None:
+            callback = print_last_grad_norm_and_crit
+        else:
+            callback = None
+        t1 = time.time()
+        res = lcg(self.model_spectro, self.y_spectro, self.mu_spectro, self.mu_reg, init, tol=tolerance,
+                  max_iter=maximum_iterations, callback=callback, comm=self.comm)
+        if self.printing:
+            print(f"Total time needed for {method} :", round(time.time() - t1, 3))
+        return res
+
+    def get_crit_val(self, x_hat) -> float:
+        return self._solver().criterion(x_hat)

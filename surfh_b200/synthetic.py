@@ -48,7 +48,7 @@ def mrs_detector_axis(name: str) -> np.ndarray:
 
 def cube_wavelength_axis(lo: float, hi: float, ratio: float = 1.0005) -> np.ndarray:
     """Log-spaced cube axis lambda_{i+1} / lambda_i = ratio (R ~ 2000 for 1.0005)."""
-    n = int(np.floor(np.log(hi / lo) / np.log(ratio))) + 1
+    n = int(np.floor(np.log(hi / lo) / np.log(ratio)))
     return lo * ratio ** np.arange(n)
 
 

@@ -1,0 +1,109 @@
+"""Device-resident CG (surfh_b200.fusion_CT) against the oracle's restated qmm.lcg driving the
+oracle operator, plus the result-export helpers.  fp64 tolerance 1e-10 on iterates (BASELINE.json)."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a.ravel() - b.ravel()) / np.linalg.norm(b.ravel()))
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    return torch
+
+
+def noisy_data(oracle, cfg):
+    fwd = oracle.forward(cfg.maps)
+    return fwd + 0.01 * np.sqrt(np.mean(fwd ** 2)) * np.random.default_rng(99).standard_normal(fwd.shape)
+
+
+@pytest.mark.parametrize("mode", ["reference", "exact"])
+def test_cg_iterates_match_oracle(torch_cuda, mode):
+    from surfh_b200 import fusion_CT
+    from surfh_b200.model import spectroSigRLSCT
+    from surfh_oracle import model as om
+    cfg = CASES["mini_2band_4p"]()
+    args = cfg.model_args()
+    oracle = om.SpectroLMM(**args, adjoint_mode=mode)
+    gpu = spectroSigRLSCT(**args, adjoint_mode=mode)
+    y = noisy_data(oracle, cfg)
+    mu = 5.0
+    n_it = 12
+    ref = om.solve_lcg(oracle, y, 1.0, mu, n_it, value_init=0.0, refresh=5)
+    res = fusion_CT.lcg(gpu, y, 1.0, mu, np.zeros(gpu.ishape), tol=1e-12, max_iter=n_it, refresh=5)
+    assert res.x.shape == gpu.ishape
+    assert rel(res.x, ref.x) <= 1e-10
+    assert np.allclose(res.grad_norm, ref.grad_norm, rtol=1e-9)
+    # criterion on device == criterion on host
+    crit = fusion_CT.QuadCriterion_MRS(1, y, gpu, mu)
+    j_gpu = crit.get_crit_val(res.x)
+    j_cpu = om.criterion(oracle, y, ref.x, 1, mu)
+    assert abs(j_gpu - j_cpu) <= 1e-10 * abs(j_cpu)
+
+
+def test_run_method_like_main_fusion_and_golden(torch_cuda, golden_dir):
+    """Same call sequence as scripts/main_fusion.py:160-204; iterates vs the golden trace that the
+    reference's own QuadCriterion_MRS produced (with the restated lcg)."""
+    from surfh_b200 import fusion_CT
+    from surfh_b200.model import spectroSigRLSCT
+    from surfh_oracle import model as om
+    cfg = CASES["mini_1band_1p"]()
+    gold = np.load(os.path.join(golden_dir, "mini_1band_1p.npz"))
+    args = cfg.model_args()
+    gpu = spectroSigRLSCT(**args)  # default: reference adjoint, fp64
+    y = noisy_data(om.SpectroLMM(**args), cfg)
+    quad = fusion_CT.QuadCriterion_MRS(mu_spectro=1, y_spectro=np.copy(y), model_spectro=gpu, mu_reg=5.0,
+                                       printing=False, gradient="separated")
+    assert abs(quad.get_crit_val(cfg.maps) - float(gold["crit_at_maps"])) <= 1e-10 * float(gold["crit_at_maps"])
+    res = quad.run_method("lcg", 6, perf_crit=1, calc_crit=True, value_init=0)
+    assert rel(res.x, gold["cg_x"]) <= 1e-10
+    assert np.allclose(res.grad_norm, gold["cg_grad_norm"], rtol=1e-9)
+    assert np.allclose(quad.L_crit_val, gold["cg_crit"], rtol=1e-10)
+    cube = gpu.mapsToCube(res.x)
+    assert cube.dtype == np.float32 and cube.shape == gpu.cube_shape
+    expect = np.einsum("kij,kl->lij", res.x.astype(np.float32), cfg.templates.astype(np.float32))
+    assert rel(cube, expect) <= 1e-6
+    assert rel(gpu.cubeTomaps(cube.astype(np.float64)), om.lmm_cube2maps(cube.astype(np.float64), cfg.templates)) < 1e-13
+
+
+def test_fp32_cg_tracks_fp64(torch_cuda):
+    from surfh_b200 import fusion_CT
+    from surfh_b200.model import spectroSigRLSCT
+    from surfh_oracle import model as om
+    cfg = CASES["mini_1band_1p"]()
+    args = cfg.model_args()
+    y = noisy_data(om.SpectroLMM(**args), cfg)
+    r64 = fusion_CT.lcg(spectroSigRLSCT(**args, adjoint_mode="exact"), y, 1.0, 5.0, max_iter=5, tol=1e-12)
+    r32 = fusion_CT.lcg(spectroSigRLSCT(**args, adjoint_mode="exact", dtype="float32"), y, 1.0, 5.0, max_iter=5,
+                        tol=1e-12)
+    assert rel(r32.x, r64.x) <= 1e-4
+
+
+def test_jansky_scaling_matches_reference_rule(torch_cuda):
+    from surfh_b200.model import spectroSigRLSCT
+    from surfh_oracle import model as om
+    cfg = CASES["mini_2band_4p"]()
+    args = cfg.model_args()
+    gpu = spectroSigRLSCT(**args)
+    oracle = om.SpectroLMM(**args)
+    data = np.random.default_rng(4).random(gpu.osize)
+    out = gpu.real_data_janskySR_to_jansky(data)
+    expect = np.zeros_like(data)
+    for c, ch in enumerate(oracle.channels):  # spectroModel.py:225-239 restated
+        block = data[oracle._idx[c]: oracle._idx[c + 1]].reshape(oracle.instrs_oshape[c]).copy()
+        for s in range(ch.band.n_slit):
+            w = ch.slicer.slit_weights(s, ch.slicer.slit_slices(s))
+            block[:, s] = block[:, s] * np.sum(w[0, 0, :]) * oracle.srfs[c]
+        expect[oracle._idx[c]: oracle._idx[c + 1]] = block.ravel()
+    assert rel(out, expect) < 1e-15
