@@ -110,19 +110,28 @@ def build_config(name: str):
     return synthetic.baseline_config(name)
 
 
-def band_costs(cfg, dtype_bytes):
-    """Cost model per band from the instrument table alone (no tables built)."""
-    from surfh_b200 import dist, geometry, instru
+def band_summaries(cfg):
+    """Sizes of every band from the instrument table alone (no device tables built)."""
+    from surfh_b200 import geometry, instru
     srfs = instru.get_srf([i.det_pix_size for i in cfg.instrs], cfg.step_degree * 3600)
-    costs = []
+    out = []
     for ifu, srf, pts in zip(cfg.instrs, srfs, cfg.pointings):
         band = ifu.pix(cfg.step_degree)
         la, lb = geometry.local_axes(band.fov, cfg.step_degree, geometry.N_MARGIN_PIX * cfg.step_degree)
         _, _, na, nbw, _ = geometry.slit_layout(band, cfg.beta_axis, la, lb, srf)
         wsl = band.wslice(cfg.wavelength_axis, geometry.WAVE_MARGIN_UM)
-        costs.append(dist.band_cost(wsl.stop - wsl.start, band.n_wavel, nbw, len(pts), band.n_slit, na,
-                                    len(cfg.alpha_axis), len(la), len(lb), dtype_bytes))
-    return costs
+        out.append(dict(wave_start=wsl.start, n_wave=wsl.stop - wsl.start, n_det=band.n_wavel, nb=nbw,
+                        n_pointing=len(pts), n_slit=band.n_slit, na=na, local_a=len(la), local_b=len(lb)))
+    return out
+
+
+def shard_for_rank(cfg, comm, dtype_bytes):
+    """Contiguous wavelength range of this rank (None when single-process)."""
+    if comm is None:
+        return None
+    from surfh_b200 import dist
+    costs = dist.lambda_costs(len(cfg.wavelength_axis), band_summaries(cfg), len(cfg.alpha_axis), dtype_bytes)
+    return dist.partition_lambda(costs, comm.world_size)[comm.rank]
 
 
 # ------------------------------------------------------------------- CPU reference legs
@@ -184,7 +193,7 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_description(cfg, dtype, args):
@@ -194,7 +203,8 @@ def workload_description(cfg, dtype, args):
                         f"one step = one forward + one adjoint (H^T H) application",
             "adjoint_mode": args.adjoint, "compute_dtype": dtype,
             "l2_policy": "inputs larger than L2: every step streams the OTF and cube chunks (GBs) through HBM",
-            "parallelism": f"bands sharded over {args.gpus} GPU(s), all-reduce of the [K,N,N] map gradient"}
+            "parallelism": f"cube wavelength axis sharded over {args.gpus} GPU(s) (contiguous, cost-balanced); per "
+                           f"application: all-reduce of the detector vector (partial sums) and of the [K,N,N] maps"}
 
 
 # ------------------------------------------------------------------------- GPU arm
@@ -216,14 +226,13 @@ def run_b200(args):
     esz = 8 if args.dtype == "float64" else 4
 
     cfg = build_config(args.config)
-    costs = band_costs(cfg, esz)
-    local = sdist.local_band_indices(costs, comm)
+    lam_range = shard_for_rank(cfg, comm, esz)
     shape = cfg.imshape
     t_setup = time.time()
     sotf = lambda lo, hi: synthetic.ir2fr_device(cfg.psf[lo:hi], shape, dev, torch.float64)  # noqa: E731
     model = spectroSigRLSCT(sotf, cfg.templates, cfg.alpha_axis, cfg.beta_axis, cfg.wavelength_axis, cfg.instrs,
                             cfg.step_degree, cfg.pointings, dtype=args.dtype, adjoint_mode=args.adjoint,
-                            local_bands=local, chunk=args.chunk, device=local_rank)
+                            lambda_range=lam_range, comm=comm, chunk=args.chunk, device=local_rank)
     setup_s = time.time() - t_setup
 
     x = torch.as_tensor(cfg.maps, device=dev, dtype=tdtype)
@@ -232,10 +241,7 @@ def run_b200(args):
     from surfh_b200 import _capi
 
     def application():
-        _capi.check(h, lib.surfh_fwadj(h, x.data_ptr(), q.data_ptr(), model.mode_code, None,
-                                       torch.cuda.current_stream().cuda_stream))
-        if comm:
-            comm.allreduce_sum(q)
+        model.fwadj_into(x, q)  # sharded: forward | all-reduce(y) | adjoint | all-reduce(maps)
 
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
@@ -273,8 +279,6 @@ def run_b200(args):
 
     # ---- CG iterations
     y = model.forward(x)
-    if comm:  # every rank needs only its own slices; keep the local result
-        pass
     cg = fusion_CT.DeviceCG(model, y, 1.0, 5e3, comm=comm)
     cg.start(np.zeros(model.ishape), args.steps + args.warmup + 8)
     ms_cg, _, _, _ = timed(lambda: cg.step(False), args.steps, args.warmup)
@@ -284,12 +288,18 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         maps_host = torch.from_numpy(cfg.maps.copy()).pin_memory()
-        y_host = torch.empty(model.osize, dtype=torch.float64).pin_memory()
+        y_host = torch.zeros(model.osize, dtype=torch.float64).pin_memory()
         out_host = torch.empty(model.ishape, dtype=torch.float64).pin_memory()
         n_out = int(lib.surfh_output_size(h))
 
+        y_dev = torch.empty(model.osize, dtype=torch.float64, device=dev) if comm else None
+
         def application_host():
             _capi.check(h, lib.surfh_forward_host(h, maps_host.data_ptr(), y_host.data_ptr()))
+            if comm:  # partial sums of the wavelength shards -> full detector vector on every host
+                y_dev.copy_(y_host, non_blocking=True)
+                comm.allreduce_sum(y_dev)
+                y_host.copy_(y_dev)
             _capi.check(h, lib.surfh_adjoint_host(h, y_host.data_ptr(), out_host.data_ptr(), model.mode_code))
             if comm:
                 part = out_host.to(dev, non_blocking=True)
@@ -355,13 +365,31 @@ def run_b200(args):
         "dtype": "f64" if esz == 8 else "f32", "data": "synthetic", "config": workload_description(cfg, args.dtype, args),
         "cg_iters_per_s": cg_iters, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "stages": stage_rows, "cpu_baseline": cpu,
-        "setup_s": setup_s, "local_bands_rank0": local, "workspace_gb": model.workspace_bytes() / 1e9,
+        "setup_s": setup_s, "lambda_range_rank0": lam_range, "workspace_gb": model.workspace_bytes() / 1e9,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line goes to the real stdout; everything else any library prints (NCCL's version
+    banner, warnings) has been routed to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -67,6 +67,12 @@ struct DevBuf {
     void ensure(size_t n) {
         if (bytes < n) alloc(n);
     }
+    void ensure_zeroed(size_t n) {  // zero-filled on (re)allocation only
+        if (bytes < n) {
+            alloc(n);
+            if (cudaMemset(p, 0, n) != cudaSuccess) throw Error(SURFH_ECUDA, "cudaMemset failed");
+        }
+    }
     template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
 };
 
@@ -711,7 +717,7 @@ template <typename T> struct ModelImpl : surfh_model {
         cudaStream_t st = 0;
         const size_t ni = (size_t)input_size(), no = (size_t)output_size();
         to_device(x, x_stage, ni, st);
-        y_stage.ensure(no * sizeof(T));
+        y_stage.ensure_zeroed(no * sizeof(T));  // slices of bands this handle does not own stay zero
         forward(x_stage.p, y_stage.p, st);
         to_host(y_stage, y, no, st);
     }

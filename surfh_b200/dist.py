@@ -38,6 +38,45 @@ def partition_bands(costs: Sequence[float], world_size: int) -> List[List[int]]:
     return [sorted(p) for p in parts]
 
 
+def partition_lambda(cost_per_lambda: Sequence[float], world_size: int) -> List[tuple]:
+    """Cut the cube wavelength axis into `world_size` contiguous ranges of (nearly) equal cumulative
+    cost.  The FFT / OTF stages shard perfectly by wavelength; a band whose window straddles a cut is
+    simply computed as two partial sums (its spectral contraction is split along K = (lambda, beta))
+    that the all-reduce of the detector vector adds up."""
+    c = np.asarray(cost_per_lambda, dtype=np.float64)
+    n = len(c)
+    total = float(c.sum())
+    if total <= 0:
+        raise ValueError("no wavelength carries any work")
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    cuts = [0]
+    for r in range(1, world_size):
+        target = total * r / world_size
+        k = int(np.searchsorted(cum, target, side="left"))
+        k = min(max(k, cuts[-1] + 1), n - (world_size - r))
+        cuts.append(k)
+    cuts.append(n)
+    return [(cuts[i], cuts[i + 1]) for i in range(world_size)]
+
+
+def lambda_costs(n_lambda: int, bands: Sequence[dict], n_pix: int, bytes_per_real: int = 8) -> np.ndarray:
+    """Per-wavelength cost model.  `bands`: dicts with wave_start, n_wave, n_det, nb, n_pointing, n_slit,
+    na, local_a, local_b.  A covered wavelength costs one FFT pair + OTF streams (HBM-bound), plus, per
+    band covering it, its share of the gather/scatter and of the spectral contraction (FMA-bound)."""
+    cost = np.zeros(n_lambda)
+    covered = np.zeros(n_lambda, dtype=bool)
+    nf = n_pix * (n_pix // 2 + 1)
+    plane_cost = 18.0e-6 * (n_pix / 501.0) ** 2 * (bytes_per_real / 8.0)  # measured: ~9 us per 501^2 fp64 FFT
+    for b in bands:
+        sl = slice(b["wave_start"], b["wave_start"] + b["n_wave"])
+        covered[sl] = True
+        flops = 4.0 * b["n_det"] * b["nb"] * b["n_pointing"] * b["n_slit"] * b["na"]
+        stream = 2.0 * b["n_pointing"] * (b["local_a"] * b["local_b"] + b["n_slit"] * b["na"] * b["nb"]) * bytes_per_real
+        cost[sl] += flops / 2.7e13 + stream / 1.5e12
+    cost[covered] += plane_cost + 4.0 * nf * 2 * bytes_per_real / 6.0e12
+    return cost
+
+
 class Comm:
     """Thin wrapper over torch.distributed for the one collective the path needs."""
 

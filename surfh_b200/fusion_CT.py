@@ -73,7 +73,9 @@ class DeviceCG:
         self.lib = model._lib
         self.h = model.handle
         self.mu_s, self.mu_r = float(mu_spectro), float(mu_reg)
-        self.comm = comm
+        self.comm = comm if comm is not None else getattr(model, "comm", None)
+        if self.comm is not None and getattr(model, "comm", None) is None:
+            model.comm = self.comm
         self.tdtype = model._torch_dtype()
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self.y = self._to_dev(y).reshape(-1)
@@ -95,10 +97,7 @@ class DeviceCG:
 
     def hessp(self, v, out):
         """out = mu_s H^T H v + mu_r (D_r^T D_r + D_c^T D_c) v ; s[1] = <v, out>."""
-        self._check(self.lib.surfh_fwadj(self.h, v.data_ptr(), out.data_ptr(), self.model.mode_code, None,
-                                         self._stream()))
-        if self.comm is not None:
-            self.comm.allreduce_sum(out)
+        self.model.fwadj_into(v, out)
         self._check(self.lib.surfh_cg_regularise_dot(self.h, v.data_ptr(), out.data_ptr(), self.mu_s, self.mu_r,
                                                      self.s.data_ptr(), self._stream()))
 
@@ -106,11 +105,7 @@ class DeviceCG:
         torch = _torch()
         self.x = self._to_dev(x0).reshape(-1).clone()
         self.s = torch.zeros(_capi.CG_NSCALARS + max_iter + 2, dtype=torch.float64, device=self.dev)
-        self.b = torch.empty(self.n, dtype=self.tdtype, device=self.dev)
-        self._check(self.lib.surfh_adjoint(self.h, self.y.data_ptr(), self.b.data_ptr(), self.model.mode_code,
-                                           self._stream()))
-        if self.comm is not None:
-            self.comm.allreduce_sum(self.b)
+        self.b = self.model.adjoint(self.y).reshape(-1)  # all-reduced over shards when the model has a comm
         if self.mu_s != 1.0:
             self.b.mul_(self.mu_s)
         self.q = torch.empty_like(self.b)
@@ -146,19 +141,14 @@ class DeviceCG:
         out = torch.zeros(2, dtype=torch.float64, device=self.dev)
         total = torch.zeros(2, dtype=torch.float64, device=self.dev)
         idx = self.model._idx
-        first = True
-        for it in self.model.local_bands:
-            lo, hi = int(idx[it]), int(idx[it + 1])
-            esz = hx.element_size()
-            self._check(self.lib.surfh_criterion_terms(
-                self.h, self.y.data_ptr() + lo * esz, hx.data_ptr() + lo * esz, hi - lo,
-                x.data_ptr() if first else None, out.data_ptr(), self._stream()))
-            total += out
-            first = False
-        if self.comm is not None:
-            data = total[:1].clone()
-            self.comm.allreduce_sum(data)
-            total[0] = data[0]
+        # forward() returns the complete detector vector on every rank (all-reduced when sharded),
+        # so the criterion is evaluated redundantly and needs no scalar collective
+        if self.comm is None and getattr(self.model, "partial", False):
+            raise ValueError("a sharded model needs a comm to evaluate the criterion")
+        n = int(idx[-1])
+        self._check(self.lib.surfh_criterion_terms(self.h, self.y.data_ptr(), hx.data_ptr(), n, x.data_ptr(),
+                                                   out.data_ptr(), self._stream()))
+        total += out
         t = total.cpu().numpy()
         return float((self.mu_s * t[0] + self.mu_r * t[1]) / 2)
 

@@ -62,13 +62,14 @@ class BandTables:
     local_beta_axis: np.ndarray
     slices: List[Tuple[slice, slice]]
     weights: np.ndarray               # [S, nb]
-    wslice: slice
+    wslice: slice                     # the band's full wavelength window in the cube
+    wave_local: slice                 # the part of it this process computes (lambda sharding)
     n_det: int
     na: int
     nb: int
     slit_a0: np.ndarray
     slit_b0: np.ndarray
-    lsf: np.ndarray                   # [n_det, n_wave, nb]
+    lsf: np.ndarray                   # [n_det, n_wave (local), nb]
     grid_base: np.ndarray             # int32 [P, A*B]
     grid_frac: np.ndarray             # float64 [P, A*B, 2]
     adj_exact: Optional[Csr] = None
@@ -90,7 +91,12 @@ class BandTables:
 
     @property
     def n_wave(self) -> int:
-        return self.wslice.stop - self.wslice.start
+        """Wavelengths handled locally (== the whole window unless lambda-sharded)."""
+        return self.wave_local.stop - self.wave_local.start
+
+    @property
+    def is_local(self) -> bool:
+        return self.n_wave > 0
 
     @property
     def oshape(self) -> Tuple[int, int, int, int]:
@@ -304,8 +310,12 @@ def build_adjoint_tables(tb: "BandTables", alpha_axis: np.ndarray, beta_axis: np
 # ---------------------------------------------------------------------------- bands
 def build_band(ifu: instru.IFU, alpha_axis: np.ndarray, beta_axis: np.ndarray, wavelength_axis: np.ndarray,
                srf: int, pointings: Sequence[instru.Coord], step_degree: float,
-               with_adjoint: bool = True) -> BandTables:
-    """All tables of one band (reference: Channel.__init__, spectroModelChannel.py:27-108)."""
+               with_adjoint: bool = True, lambda_range: Optional[Tuple[int, int]] = None) -> BandTables:
+    """All tables of one band (reference: Channel.__init__, spectroModelChannel.py:27-108).
+
+    `lambda_range` = (l0, l1) restricts the band to the cube wavelengths [l0, l1) (sharding of the
+    wavelength axis across GPUs): the LSF keeps only those columns (its normalisation still runs
+    over the band's full window), so forward yields this shard's partial sum of y."""
     alpha_axis = np.asarray(alpha_axis, dtype=np.float64)
     beta_axis = np.asarray(beta_axis, dtype=np.float64)
     wavelength_axis = np.asarray(wavelength_axis, dtype=np.float64)
@@ -314,7 +324,16 @@ def build_band(ifu: instru.IFU, alpha_axis: np.ndarray, beta_axis: np.ndarray, w
     la, lb = local_axes(band.fov, step_degree, N_MARGIN_PIX * step_degree)
     slices, weights, na, nbw, npix_alpha = slit_layout(band, beta_axis, la, lb, srf)
     wsl = band.wslice(wavelength_axis, WAVE_MARGIN_UM)
-    lsf = lsf_table(band, wavelength_axis[wsl], nbw, beta_axis[1] - beta_axis[0])
+    if lambda_range is None:
+        local = wsl
+    else:
+        lo, hi = max(wsl.start, int(lambda_range[0])), min(wsl.stop, int(lambda_range[1]))
+        local = slice(lo, max(lo, hi))
+    if local.stop > local.start:
+        lsf = lsf_table(band, wavelength_axis[wsl], nbw, beta_axis[1] - beta_axis[0])
+        lsf = np.ascontiguousarray(lsf[:, local.start - wsl.start: local.stop - wsl.start, :])
+    else:
+        lsf = np.zeros((band.n_wavel, 0, nbw))
 
     n_b = len(beta_axis)
     base = np.empty((len(points), len(la) * len(lb)), dtype=np.int32)
@@ -330,10 +349,11 @@ def build_band(ifu: instru.IFU, alpha_axis: np.ndarray, beta_axis: np.ndarray, w
         frac[p, :, 0], frac[p, :, 1] = t0, t1
 
     tb = BandTables(name=ifu.name, instr=band, pointings=points, srf=int(srf), local_alpha_axis=la,
-                    local_beta_axis=lb, slices=slices, weights=weights, wslice=wsl, n_det=band.n_wavel, na=na,
+                    local_beta_axis=lb, slices=slices, weights=weights, wslice=wsl, wave_local=local, n_det=band.n_wavel,
+                    na=na,
                     nb=nbw, slit_a0=np.array([s[0].start for s in slices], dtype=np.int32),
                     slit_b0=np.array([s[1].start for s in slices], dtype=np.int32), lsf=lsf, grid_base=base,
                     grid_frac=frac, npix_slit_alpha_width=npix_alpha)
-    if with_adjoint:
+    if with_adjoint and tb.is_local:
         build_adjoint_tables(tb, alpha_axis, beta_axis)
     return tb

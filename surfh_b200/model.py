@@ -84,8 +84,12 @@ class spectroSigRLSCT(LinOp):
       dtype          "float64" (default; parity <= 1e-10 vs the reference numpy path) or "float32"
       adjoint_mode   "reference" (default: bug-for-bug `gridding_t` interpolation) or "exact"
                      (true transpose; <Hx,y> = <x,H^T y> to rounding)
-      local_bands    indices of the bands this process computes (band sharding across GPUs);
-                     other bands' slices of y are left at zero / ignored
+      lambda_range   (l0, l1): this process computes only cube wavelengths [l0, l1) (wavelength
+                     sharding across GPUs, see surfh_b200.dist): `forward` then yields this shard's
+                     partial sum of y and `adjoint` its partial maps
+      local_bands    indices of the bands this process computes (coarser band sharding)
+      comm           surfh_b200.dist.Comm: when given, device-tensor forward/adjoint/fwadj all-reduce
+                     their partial results so every rank returns the full operator's output
       chunk          wavelengths per pipeline chunk (0 = library default)
       device         CUDA device index (default: current device)
       sotf           may also be a torch CUDA complex tensor, or a callable (l0, l1) -> complex
@@ -95,7 +99,7 @@ class spectroSigRLSCT(LinOp):
     def __init__(self, sotf, templates, alpha_axis, beta_axis, wavelength_axis,
                  instrs: List[instru.IFU], step_degree: float, pointings: Sequence[instru.CoordList],
                  dtype="float64", adjoint_mode: str = "reference", local_bands: Optional[Sequence[int]] = None,
-                 chunk: int = 0, device: Optional[int] = None):
+                 chunk: int = 0, device: Optional[int] = None, lambda_range=None, comm=None):
         self._h = None
         self._lib = _capi.load()
         if adjoint_mode not in _capi.ADJOINT_MODES:
@@ -115,14 +119,19 @@ class spectroSigRLSCT(LinOp):
         self.srfs = instru.get_srf([i.det_pix_size for i in instrs], step_degree * 3600)
         n_bands = len(instrs)
         self.local_bands = list(range(n_bands)) if local_bands is None else sorted(int(b) for b in local_bands)
+        self.lambda_range = None if lambda_range is None else (int(lambda_range[0]), int(lambda_range[1]))
+        self.comm = comm
         if device is not None:
             import torch
             torch.cuda.set_device(device)
 
         self.band_tables: List[geometry.BandTables] = [
             geometry.build_band(instr, self.alpha_axis, self.beta_axis, self.wavelength_axis, srf, pointings[it],
-                                step_degree, with_adjoint=(it in self.local_bands))
+                                step_degree, with_adjoint=(it in self.local_bands),
+                                lambda_range=self.lambda_range if it in self.local_bands else (0, 0))
             for it, (srf, instr) in enumerate(zip(self.srfs, instrs))]
+        self.local_bands = [it for it in self.local_bands if self.band_tables[it].is_local]
+        self.partial = self.lambda_range is not None or len(self.local_bands) < n_bands
         n_point = len(pointings[0])
         self.instrs_oshape = [(n_point, t.n_slit, t.n_det, t.na) for t in self.band_tables]
         self._idx = np.cumsum([0] + [int(np.prod(s)) for s in self.instrs_oshape])
@@ -149,6 +158,8 @@ class spectroSigRLSCT(LinOp):
         code = self._lib.surfh_create(C.byref(desc), C.byref(handle))
         _capi.check(None, code)
         self._h = handle
+        if not self.local_bands:
+            raise ValueError("this process has no band / wavelength to compute (empty shard)")
         self._upload_otf(sotf)
         for it in self.local_bands:
             self._add_band(self.band_tables[it])
@@ -162,7 +173,7 @@ class spectroSigRLSCT(LinOp):
     def _needed_planes(self):
         need = np.zeros(len(self.wavelength_axis), dtype=bool)
         for it in self.local_bands:
-            need[self.band_tables[it].wslice] = True
+            need[self.band_tables[it].wave_local] = True
         return need
 
     def _upload_otf(self, sotf, planes_per_call: int = 128):
@@ -200,7 +211,7 @@ class spectroSigRLSCT(LinOp):
             return _capi.ptr(a)
 
         d = _capi.BandDesc(
-            t.n_pointing, t.n_slit, t.na, t.nb, t.srf, t.local_shape[0], t.local_shape[1], t.wslice.start,
+            t.n_pointing, t.n_slit, t.na, t.nb, t.srf, t.local_shape[0], t.local_shape[1], t.wave_local.start,
             t.n_wave, t.n_det, t.out_offset,
             arr(t.slit_a0, np.int32), arr(t.slit_b0, np.int32), arr(t.weights, np.float64),
             arr(t.lsf, np.float64), arr(t.grid_base, np.int32), arr(t.grid_frac, np.float64),
@@ -254,6 +265,8 @@ class spectroSigRLSCT(LinOp):
             alloc = torch.empty if len(self.local_bands) == len(self.band_tables) else torch.zeros
             y = alloc(self.osize, dtype=x.dtype, device=x.device)
             _capi.check(self._h, self._lib.surfh_forward(self._h, x.data_ptr(), y.data_ptr(), self._stream()))
+            if self.comm is not None:
+                self.comm.allreduce_sum(y)
             return y
         x = np.ascontiguousarray(np.asarray(maps, dtype=np.float64).reshape(self.ishape))
         y = np.zeros(self.oshape, dtype=np.float64)
@@ -268,6 +281,8 @@ class spectroSigRLSCT(LinOp):
             x = torch.empty(self.ishape, dtype=y.dtype, device=y.device)
             _capi.check(self._h, self._lib.surfh_adjoint(self._h, y.data_ptr(), x.data_ptr(), self.mode_code,
                                                          self._stream()))
+            if self.comm is not None:
+                self.comm.allreduce_sum(x)
             return x
         y = np.ascontiguousarray(np.asarray(inarray, dtype=np.float64).reshape(-1))
         if y.size != self.osize:
@@ -282,10 +297,31 @@ class spectroSigRLSCT(LinOp):
         was_numpy = not _is_torch(maps)
         x = torch.as_tensor(np.ascontiguousarray(maps, dtype=np.float64), device="cuda") if was_numpy else maps
         x = self._dev_in(x, self.isize)
-        out = torch.empty(self.ishape, dtype=x.dtype, device=x.device)
-        _capi.check(self._h, self._lib.surfh_fwadj(self._h, x.data_ptr(), out.data_ptr(), self.mode_code, None,
-                                                   self._stream()))
+        out = self.fwadj_into(x, torch.empty(self.ishape, dtype=x.dtype, device=x.device))
         return out.cpu().numpy().astype(np.float64) if was_numpy else out
+
+    def fwadj_into(self, x, out):
+        """out = H^T H x on device tensors.  Sharded (partial) models exchange the detector vector
+        (all-reduce of the partial sums over wavelength shards) between the two halves and the
+        [K, N, N] result at the end; unsharded models run the fused library call."""
+        if self.comm is None or not self.partial:
+            _capi.check(self._h, self._lib.surfh_fwadj(self._h, x.data_ptr(), out.data_ptr(), self.mode_code, None,
+                                                       self._stream()))
+            if self.comm is not None:
+                self.comm.allreduce_sum(out)
+            return out
+        import torch
+        if getattr(self, "_y_shard", None) is None or self._y_shard.dtype != x.dtype:
+            self._y_shard = torch.zeros(self.osize, dtype=x.dtype, device=x.device)
+        y = self._y_shard
+        if len(self.local_bands) < len(self.band_tables):
+            y.zero_()  # slices of bands this shard does not touch must not carry the previous sum
+        _capi.check(self._h, self._lib.surfh_forward(self._h, x.data_ptr(), y.data_ptr(), self._stream()))
+        self.comm.allreduce_sum(y)
+        _capi.check(self._h, self._lib.surfh_adjoint(self._h, y.data_ptr(), out.data_ptr(), self.mode_code,
+                                                     self._stream()))
+        self.comm.allreduce_sum(out)
+        return out
 
     fwback = fwadj
 

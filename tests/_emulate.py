@@ -30,7 +30,7 @@ def forward(model_tables, blurred, n_beta):
     """Detector vector from the blurred cube, bands concatenated like the reference."""
     out = []
     for tb in model_tables:
-        G = gather(tb, blurred[tb.wslice], n_beta)
+        G = gather(tb, blurred[tb.wave_local], n_beta)
         y = np.einsum("mlb,lpsab->psma", tb.lsf, G, optimize=True)
         out.append(y.ravel())
     return np.concatenate(out)
@@ -44,6 +44,8 @@ def adjoint_cube(model_tables, y, cube_shape, mode):
         n = int(np.prod(tb.oshape))
         yb = y[off:off + n].reshape(tb.oshape)
         off += n
+        if tb.n_wave == 0:
+            continue
         Gt = np.einsum("mlb,psma->lpsab", tb.lsf, yb, optimize=True).reshape(tb.n_wave, -1)
         csr = tb.adj_exact if mode == "exact" else tb.adj_reference
         contrib = np.zeros((tb.n_wave, cube_shape[1] * cube_shape[2]))
@@ -52,5 +54,5 @@ def adjoint_cube(model_tables, y, cube_shape, mode):
         for l in range(tb.n_wave):
             acc = np.bincount(rows, weights=csr.val * Gt[l, csr.col], minlength=csr.n_rows)
             contrib[l, csr.row_pixel] = acc
-        cube[tb.wslice] += contrib.reshape((tb.n_wave,) + tuple(cube_shape[1:]))
+        cube[tb.wave_local] += contrib.reshape((tb.n_wave,) + tuple(cube_shape[1:]))
     return cube
