@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SURFH_ABI_VERSION 1
+#define SURFH_ABI_VERSION 2
 
 enum { SURFH_F32 = 0, SURFH_F64 = 1 };
 
@@ -37,6 +37,7 @@ enum { SURFH_F32 = 0, SURFH_F64 = 1 };
  * bilinear interpolation, not the transpose of `gridding`; SURFH_ADJ_REFERENCE reproduces it,
  * SURFH_ADJ_EXACT applies the true transpose (dot-test to rounding). */
 enum { SURFH_ADJ_EXACT = 0, SURFH_ADJ_REFERENCE = 1 };
+enum { SURFH_SPECTRAL_LSF = 0, SURFH_SPECTRAL_BETA_SUM = 1 };
 
 enum {
     SURFH_OK = 0,
@@ -87,6 +88,11 @@ typedef struct {
     int32_t wave_start;  /* first cube wavelength of the band (wslice.start)                   */
     int32_t n_wave;      /* Lambda  = wslice.stop - wslice.start                               */
     int32_t n_det;       /* Lambda' = detector wavelength samples                              */
+    int32_t spectral_mode; /* SURFH_SPECTRAL_LSF: y = sum_{l,b} lsf * G (spectroSigRLSCT);
+                            SURFH_SPECTRAL_BETA_SUM: y[l] = sum_b G[l] (no spectral response, one
+                            output row per cube wavelength: MRSBlurred, spectro_blind.py:191-207);
+                            then n_det = rows of the band's y block and lsf may be NULL          */
+    int32_t det_start;   /* beta-sum mode: y row of the first local wavelength (0 unless sharded) */
     int64_t out_offset;  /* element offset of this band in the caller's y vector (_idx[band])  */
     const int32_t* slit_a0;   /* [S]      first local row of the slit                          */
     const int32_t* slit_b0;   /* [S]      first local column of the slit                       */

@@ -229,10 +229,42 @@ CASES = {
 }
 
 
+def blind_cases():
+    """Single-wavelength MRSBlurred inputs (surfh/Models/spectro_blind.py): (name, cfg, wavelength index)."""
+    mini = synthetic.mini_config(1, 2, lmm=False, n_pix=96, n_slit_a=11)  # MRSBlurred needs n_slit >= nb
+    full = synthetic.mrs_config(["1c"], 301, 0, 4, seed=5, name="blind_1c", lmm=False,
+                                wavel=np.array([6.9, 7.0, 7.1]))
+    return [("blind_mini_2p", mini, 7), ("blind_1c_4p", full, 1)]
+
+
+def run_blind(ref_instru, name, cfg, l_idx):
+    import surfh.Models.spectro_blind as blind_mod
+    instrs, pointings = to_reference_objects(ref_instru, cfg)
+    sotf = cfg.sotf()[l_idx]
+    model = blind_mod.MRSBlurred(sotf, cfg.alpha_axis, cfg.beta_axis, instrs[0], cfg.step_degree, pointings[0])
+    x = cfg.maps[l_idx]
+    fwd = np.asarray(model.forward(x))
+    v = np.random.default_rng(1234).standard_normal(fwd.shape[0])
+    adj = np.asarray(model.adjoint(v))
+    sl = [model.get_slit_slices(s) for s in range(instrs[0].n_slit)]
+    rec = {"fwd": fwd, "adj": adj, "l_idx": np.array(l_idx), "slices_shape": np.array(model.slices_shape),
+           "slices": np.array([[a.start, a.stop, b.start, b.stop] for a, b in sl]),
+           "weights": np.array([model.get_slit_weights(s, sl[s])[0, 0, :] for s in range(instrs[0].n_slit)]),
+           "jansky": np.asarray(model.real_data_janskySR_to_jansky(fwd.copy()))}
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **rec)
+    print(f"{name}: oshape={fwd.shape[0]} |fwd|={np.linalg.norm(fwd):.6e} |adj|={np.linalg.norm(adj):.6e} "
+          f"-> {os.path.getsize(path) / 1e3:.0f} kB")
+
+
 def main(names=None):
     pkg = prepare_scratch()
     model_mod, ref_instru = import_reference(pkg)
     os.makedirs(GOLDEN, exist_ok=True)
+    for name, cfg, l_idx in blind_cases():
+        if names and name not in names:
+            continue
+        run_blind(ref_instru, name, cfg, l_idx)
     for name, (factory, full, with_cg) in CASES.items():
         if names and name not in names:
             continue

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 F32, F64 = 0, 1
 ADJ_EXACT, ADJ_REFERENCE = 0, 1
 CG_NSCALARS = 8
+ABI_VERSION = 2
+SPECTRAL_LSF, SPECTRAL_BETA_SUM = 0, 1
 
 ADJOINT_MODES = {"exact": ADJ_EXACT, "reference": ADJ_REFERENCE}
 
@@ -41,7 +43,8 @@ class CsrDesc(C.Structure):
 class BandDesc(C.Structure):
     _fields_ = [("n_pointing", C.c_int32), ("n_slit", C.c_int32), ("na", C.c_int32), ("nb", C.c_int32),
                 ("srf", C.c_int32), ("local_a", C.c_int32), ("local_b", C.c_int32), ("wave_start", C.c_int32),
-                ("n_wave", C.c_int32), ("n_det", C.c_int32), ("out_offset", C.c_int64),
+                ("n_wave", C.c_int32), ("n_det", C.c_int32), ("spectral_mode", C.c_int32), ("det_start", C.c_int32),
+                ("out_offset", C.c_int64),
                 ("slit_a0", C.c_void_p), ("slit_b0", C.c_void_p), ("slit_w", C.c_void_p), ("lsf", C.c_void_p),
                 ("grid_base", C.c_void_p), ("grid_frac", C.c_void_p),
                 ("adj_exact", CsrDesc), ("adj_reference", CsrDesc)]
@@ -101,7 +104,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.surfh_abi_version() != 1:
+    if lib.surfh_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version mismatch")
     _lib = lib
     return lib

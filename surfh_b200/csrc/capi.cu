@@ -162,7 +162,7 @@ struct surfh_model {
 namespace surfh {
 
 template <typename T> struct BandT {
-    int P, S, na, nb, srf, A, B, l0, nl, nd, ncol, Nn, KB;
+    int P, S, na, nb, srf, A, B, l0, nl, nd, ncol, Nn, KB, mode, det_start;
     int64_t out_offset, out_size;
     DevBuf slit_a0, slit_b0, slit_w, lsf, grid_base, grid_frac;
     DevBuf csr_pix[2], csr_ptr[2], csr_col[2], csr_val[2];
@@ -297,18 +297,26 @@ template <typename T> struct ModelImpl : surfh_model {
         SURFH_REQUIRE(d->n_pointing > 0 && d->n_slit > 0 && d->na > 0 && d->nb > 0 && d->srf > 0, "bad band sizes");
         SURFH_REQUIRE(d->local_a > 1 && d->local_b > 1 && d->n_det > 0 && d->n_wave > 0, "bad band sizes");
         SURFH_REQUIRE(d->wave_start >= 0 && d->wave_start + d->n_wave <= Nl, "band wavelength window outside the cube");
-        SURFH_REQUIRE(d->slit_a0 && d->slit_b0 && d->slit_w && d->lsf && d->grid_base && d->grid_frac, "NULL band table");
+        SURFH_REQUIRE(d->slit_a0 && d->slit_b0 && d->slit_w && d->grid_base && d->grid_frac, "NULL band table");
+        SURFH_REQUIRE(d->spectral_mode == SURFH_SPECTRAL_LSF || d->spectral_mode == SURFH_SPECTRAL_BETA_SUM,
+                      "unknown spectral_mode");
+        SURFH_REQUIRE(d->spectral_mode == SURFH_SPECTRAL_BETA_SUM || d->lsf, "NULL lsf table");
+        SURFH_REQUIRE(d->spectral_mode == SURFH_SPECTRAL_LSF ||
+                          (d->det_start >= 0 && d->det_start + d->n_wave <= d->n_det),
+                      "beta-sum band: local wavelengths outside the band's output rows");
         auto b = std::make_unique<BandT<T>>();
         b->P = d->n_pointing; b->S = d->n_slit; b->na = d->na; b->nb = d->nb; b->srf = d->srf;
         b->A = d->local_a; b->B = d->local_b; b->l0 = d->wave_start; b->nl = d->n_wave; b->nd = d->n_det;
+        b->mode = d->spectral_mode; b->det_start = d->det_start;
         b->Nn = b->P * b->S * b->na;
         b->ncol = b->Nn * b->nb;
         b->KB = b->nl * b->nb;
         b->out_offset = d->out_offset;
         b->out_size = (int64_t)b->Nn * b->nd;
         SURFH_REQUIRE(d->out_offset >= 0, "negative out_offset");
-        SURFH_REQUIRE((int64_t)b->nd * b->KB < (1ll << 31) && (int64_t)b->nl * b->ncol < (1ll << 31) &&
-                          b->out_size < (1ll << 31), "band too large for 32-bit operand offsets");
+        SURFH_REQUIRE(b->mode == SURFH_SPECTRAL_BETA_SUM ||
+                          ((int64_t)b->nd * b->KB < (1ll << 31) && (int64_t)b->nl * b->ncol < (1ll << 31) &&
+                           b->out_size < (1ll << 31)), "band too large for 32-bit operand offsets");
         const int AB = b->A * b->B;
         for (int s = 0; s < b->S; ++s) {
             SURFH_REQUIRE(d->slit_a0[s] >= 0 && d->slit_a0[s] < b->A, "slit_a0 out of the local grid");
@@ -326,7 +334,7 @@ template <typename T> struct ModelImpl : surfh_model {
         upload_converted<int32_t>(b->slit_a0, d->slit_a0, b->S);
         upload_converted<int32_t>(b->slit_b0, d->slit_b0, b->S);
         upload_converted<T>(b->slit_w, d->slit_w, (size_t)b->S * b->nb);
-        upload_converted<T>(b->lsf, d->lsf, (size_t)b->nd * b->KB);
+        if (b->mode == SURFH_SPECTRAL_LSF) upload_converted<T>(b->lsf, d->lsf, (size_t)b->nd * b->KB);
         upload_converted<int32_t>(b->grid_base, d->grid_base, (size_t)b->P * AB);
         upload_converted<T>(b->grid_frac, d->grid_frac, (size_t)b->P * AB * 2);
         const surfh_csr* cs[2] = {&d->adj_exact, &d->adj_reference};
@@ -340,7 +348,7 @@ template <typename T> struct ModelImpl : surfh_model {
             upload_converted<T>(b->csr_val[m], cs[m]->val, cs[m]->nnz);
         }
         // GEMM offset tables
-        {
+        if (b->mode == SURFH_SPECTRAL_LSF) {
             const int nmax = std::max(b->KB, b->nd);
             std::vector<int32_t> v(nmax);
             for (int i = 0; i < nmax; ++i) v[i] = i;
@@ -535,11 +543,31 @@ template <typename T> struct ModelImpl : surfh_model {
     // FP64 tensor path: all bands in one grouped launch (per group of kMaxGemmGroup bands)
     void gemm_grouped_f64(double* y, bool adjoint, cudaStream_t st);
 
+    void beta_sum(BandT<T>& b, T* y, bool adjoint, cudaStream_t st) {
+        const size_t n = (size_t)b.nl * b.Nn * (adjoint ? b.nb : 1);
+        const double bytes = sizeof(T) * ((double)b.nl * b.ncol + (double)b.nl * b.Nn);
+        Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, (double)b.nl * b.ncol, 1, true);
+        if (!adjoint)
+            beta_sum_fwd_kernel<T><<<ceil_div(n, 256), 256, 0, st>>>(b.G.template as<T>(), b.nl, b.Nn, b.nb, b.det_start,
+                                                                   y + b.out_offset);
+        else
+            beta_sum_adj_kernel<T><<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.nl, b.Nn, b.nb, b.det_start,
+                                                                   b.G.template as<T>());
+        SURFH_CUDA(cudaGetLastError());
+    }
+
     void gemm_all(T* y, bool adjoint, cudaStream_t st) {
+        bool any_lsf = false;
+        for (auto& bp : bands) {
+            if (bp->mode == SURFH_SPECTRAL_BETA_SUM) beta_sum(*bp, y, adjoint, st);
+            else any_lsf = true;
+        }
+        if (!any_lsf) return;
         if (std::is_same<T, double>::value) {
             gemm_grouped_f64(reinterpret_cast<double*>(y), adjoint, st);
         } else {
-            for (auto& bp : bands) gemm_simt(*bp, y, adjoint, st);
+            for (auto& bp : bands)
+                if (bp->mode == SURFH_SPECTRAL_LSF) gemm_simt(*bp, y, adjoint, st);
         }
     }
 
@@ -801,13 +829,16 @@ template <> void ModelImpl<float>::gemm_grouped_f64(double*, bool, cudaStream_t)
 }
 
 template <> void ModelImpl<double>::gemm_grouped_f64(double* y, bool adjoint, cudaStream_t st) {
-    for (size_t first = 0; first < bands.size(); first += kMaxGemmGroup) {
+    std::vector<size_t> lsf_bands;
+    for (size_t i = 0; i < bands.size(); ++i)
+        if (bands[i]->mode == SURFH_SPECTRAL_LSF) lsf_bands.push_back(i);
+    for (size_t first = 0; first < lsf_bands.size(); first += kMaxGemmGroup) {
         GemmBatch batch;
         batch.count = 0;
         batch.tile_start[0] = 0;
         double bytes = 0, flops = 0;
-        for (size_t i = first; i < std::min(bands.size(), first + (size_t)kMaxGemmGroup); ++i) {
-            BandT<double>& b = *bands[i];
+        for (size_t j = first; j < std::min(lsf_bands.size(), first + (size_t)kMaxGemmGroup); ++j) {
+            BandT<double>& b = *bands[lsf_bands[j]];
             GemmArgs<double> g = gemm_args(b, y, adjoint);
             batch.p[batch.count] = g;
             batch.tile_start[batch.count + 1] =

@@ -115,4 +115,26 @@ slit_scatter_kernel(const T* __restrict__ Gt, int ncol, int n_l, CsrTable<T> t, 
         if (l0 + u < n_l) dst[(size_t)u * plane] += acc[u];
 }
 
+// No spectral response (MRSBlurred, surfh/Models/spectro_blind.py:191-235): the detector value is the
+// beta-sum of the weighted slit, one output row per cube wavelength; the transpose replicates.
+//   y[(row0 + l) * Nn + n] = sum_b G[l, n*nb + b]          Gt[l, n*nb + b] = y[(row0 + l) * Nn + n]
+template <typename T>
+__global__ void __launch_bounds__(256)
+beta_sum_fwd_kernel(const T* __restrict__ G, int n_l, int Nn, int nb, int row0, T* __restrict__ y) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_l * Nn) return;
+    const T* g = G + idx * nb;
+    T s = T(0);
+    for (int b = 0; b < nb; ++b) s += g[b];
+    y[(size_t)row0 * Nn + idx] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+beta_sum_adj_kernel(const T* __restrict__ y, int n_l, int Nn, int nb, int row0, T* __restrict__ Gt) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_l * Nn * nb) return;
+    Gt[idx] = y[(size_t)row0 * Nn + idx / nb];
+}
+
 }  // namespace surfh

@@ -69,7 +69,7 @@ class BandTables:
     nb: int
     slit_a0: np.ndarray
     slit_b0: np.ndarray
-    lsf: np.ndarray                   # [n_det, n_wave (local), nb]
+    lsf: Optional[np.ndarray]         # [n_det, n_wave (local), nb]; None = beta-sum (MRSBlurred)
     grid_base: np.ndarray             # int32 [P, A*B]
     grid_frac: np.ndarray             # float64 [P, A*B, 2]
     adj_exact: Optional[Csr] = None
@@ -142,8 +142,13 @@ def _interval(grid: np.ndarray, x: np.ndarray):
 
 
 # ---------------------------------------------------------------------------- slits
-def slit_layout(ifu: instru.IFU, beta_axis: np.ndarray, la: np.ndarray, lb: np.ndarray, srf: int):
-    """Index ranges and beta weights of every slit of a band in its local grid."""
+def slit_layout(ifu: instru.IFU, beta_axis: np.ndarray, la: np.ndarray, lb: np.ndarray, srf: int,
+                rules: str = "channel"):
+    """Index ranges and beta weights of every slit of a band in its local grid.
+
+    rules="channel": Slicer as used by Channel (slicer.py:118-168).  rules="blind": the private copies
+    in MRSBlurred (spectro_blind.py:120-167): no even-na alpha adjustment, and the "next slit shares my
+    last column" reset is only evaluated for slit_idx < npix_slit_beta_width - 1 (sic)."""
     n_slit = ifu.n_slit
     aw, bw = ifu.fov.alpha_width, ifu.fov.beta_width
     slit_w = bw / n_slit
@@ -155,7 +160,7 @@ def slit_layout(ifu: instru.IFU, beta_axis: np.ndarray, la: np.ndarray, lb: np.n
     a_start, a_end = 0.0 - aw / 2, 0.0 + aw / 2
     a_lo = int(np.flatnonzero(a_start < la + da / 2)[0])
     a_hi = int(np.flatnonzero(la - da / 2 < a_end)[-1]) + 1
-    if na % 2 == 0 and na < 28:
+    if rules == "channel" and na % 2 == 0 and na < 28:
         if a_hi - a_lo > npix_alpha:
             a_hi -= 1
         elif a_hi - a_lo < npix_alpha:
@@ -195,7 +200,8 @@ def slit_layout(ifu: instru.IFU, beta_axis: np.ndarray, la: np.ndarray, lb: np.n
             weights[s, -1] = w1
         if s > 0 and b_ranges[s - 1][1] - 1 != lo:
             weights[s, 0] = 1
-        if s < n_slit - 1 and hi - 1 != b_ranges[s + 1][0]:
+        last_checked = (n_slit - 1) if rules == "channel" else min(n_slit - 1, nbw - 1)
+        if s < last_checked and hi - 1 != b_ranges[s + 1][0]:
             weights[s, -1] = 1
     slices = [(slice(a_lo, a_hi), slice(lo, hi)) for lo, hi in b_ranges]
     return slices, weights, na, nbw, npix_alpha
@@ -310,7 +316,8 @@ def build_adjoint_tables(tb: "BandTables", alpha_axis: np.ndarray, beta_axis: np
 # ---------------------------------------------------------------------------- bands
 def build_band(ifu: instru.IFU, alpha_axis: np.ndarray, beta_axis: np.ndarray, wavelength_axis: np.ndarray,
                srf: int, pointings: Sequence[instru.Coord], step_degree: float,
-               with_adjoint: bool = True, lambda_range: Optional[Tuple[int, int]] = None) -> BandTables:
+               with_adjoint: bool = True, lambda_range: Optional[Tuple[int, int]] = None,
+               rules: str = "channel") -> BandTables:
     """All tables of one band (reference: Channel.__init__, spectroModelChannel.py:27-108).
 
     `lambda_range` = (l0, l1) restricts the band to the cube wavelengths [l0, l1) (sharding of the
@@ -319,17 +326,20 @@ def build_band(ifu: instru.IFU, alpha_axis: np.ndarray, beta_axis: np.ndarray, w
     alpha_axis = np.asarray(alpha_axis, dtype=np.float64)
     beta_axis = np.asarray(beta_axis, dtype=np.float64)
     wavelength_axis = np.asarray(wavelength_axis, dtype=np.float64)
-    band = ifu.pix(step_degree)
-    points = instru.CoordList(pointings).pix(step_degree)
+    blind = rules == "blind"  # MRSBlurred: instrument and pointings used as given, every wavelength, no LSF
+    band = ifu if blind else ifu.pix(step_degree)
+    points = instru.CoordList(pointings) if blind else instru.CoordList(pointings).pix(step_degree)
     la, lb = local_axes(band.fov, step_degree, N_MARGIN_PIX * step_degree)
-    slices, weights, na, nbw, npix_alpha = slit_layout(band, beta_axis, la, lb, srf)
-    wsl = band.wslice(wavelength_axis, WAVE_MARGIN_UM)
+    slices, weights, na, nbw, npix_alpha = slit_layout(band, beta_axis, la, lb, srf, rules)
+    wsl = slice(0, len(wavelength_axis)) if blind else band.wslice(wavelength_axis, WAVE_MARGIN_UM)
     if lambda_range is None:
         local = wsl
     else:
         lo, hi = max(wsl.start, int(lambda_range[0])), min(wsl.stop, int(lambda_range[1]))
         local = slice(lo, max(lo, hi))
-    if local.stop > local.start:
+    if blind:
+        lsf = None
+    elif local.stop > local.start:
         lsf = lsf_table(band, wavelength_axis[wsl], nbw, beta_axis[1] - beta_axis[0])
         lsf = np.ascontiguousarray(lsf[:, local.start - wsl.start: local.stop - wsl.start, :])
     else:
@@ -349,7 +359,8 @@ def build_band(ifu: instru.IFU, alpha_axis: np.ndarray, beta_axis: np.ndarray, w
         frac[p, :, 0], frac[p, :, 1] = t0, t1
 
     tb = BandTables(name=ifu.name, instr=band, pointings=points, srf=int(srf), local_alpha_axis=la,
-                    local_beta_axis=lb, slices=slices, weights=weights, wslice=wsl, wave_local=local, n_det=band.n_wavel,
+                    local_beta_axis=lb, slices=slices, weights=weights, wslice=wsl, wave_local=local,
+                    n_det=(wsl.stop - wsl.start) if blind else band.n_wavel,
                     na=na,
                     nb=nbw, slit_a0=np.array([s[0].start for s in slices], dtype=np.int32),
                     slit_b0=np.array([s[1].start for s in slices], dtype=np.int32), lsf=lsf, grid_base=base,

@@ -96,6 +96,8 @@ class spectroSigRLSCT(LinOp):
                      array/tensor of planes [l0, l1), so a multi-GB OTF never sits on the host
     """
 
+    _rules = "channel"  # geometry rule set (geometry.build_band); MRSBlurred overrides it
+
     def __init__(self, sotf, templates, alpha_axis, beta_axis, wavelength_axis,
                  instrs: List[instru.IFU], step_degree: float, pointings: Sequence[instru.CoordList],
                  dtype="float64", adjoint_mode: str = "reference", local_bands: Optional[Sequence[int]] = None,
@@ -128,7 +130,8 @@ class spectroSigRLSCT(LinOp):
         self.band_tables: List[geometry.BandTables] = [
             geometry.build_band(instr, self.alpha_axis, self.beta_axis, self.wavelength_axis, srf, pointings[it],
                                 step_degree, with_adjoint=(it in self.local_bands),
-                                lambda_range=self.lambda_range if it in self.local_bands else (0, 0))
+                                lambda_range=self.lambda_range if it in self.local_bands else (0, 0),
+                                rules=self._rules)
             for it, (srf, instr) in enumerate(zip(self.srfs, instrs))]
         self.local_bands = [it for it in self.local_bands if self.band_tables[it].is_local]
         self.partial = self.lambda_range is not None or len(self.local_bands) < n_bands
@@ -212,9 +215,12 @@ class spectroSigRLSCT(LinOp):
 
         d = _capi.BandDesc(
             t.n_pointing, t.n_slit, t.na, t.nb, t.srf, t.local_shape[0], t.local_shape[1], t.wave_local.start,
-            t.n_wave, t.n_det, t.out_offset,
+            t.n_wave, t.n_det,
+            _capi.SPECTRAL_BETA_SUM if t.lsf is None else _capi.SPECTRAL_LSF, t.wave_local.start - t.wslice.start,
+            t.out_offset,
             arr(t.slit_a0, np.int32), arr(t.slit_b0, np.int32), arr(t.weights, np.float64),
-            arr(t.lsf, np.float64), arr(t.grid_base, np.int32), arr(t.grid_frac, np.float64),
+            None if t.lsf is None else arr(t.lsf, np.float64), arr(t.grid_base, np.int32),
+            arr(t.grid_frac, np.float64),
             _capi.csr_desc(t.adj_exact, keep), _capi.csr_desc(t.adj_reference, keep))
         _capi.check(self._h, self._lib.surfh_add_band(self._h, C.byref(d)))
 

@@ -173,13 +173,13 @@ def mrs_config(bands: Sequence[str], n_pix: int, n_templates: int, n_pointings: 
 
 
 def mini_config(n_bands: int = 1, n_pointings: int = 1, n_templates: int = 3, n_pix: int = 96,
-                seed: int = 7, lmm: bool = True) -> Config:
+                seed: int = 7, lmm: bool = True, n_slit_a: int = 5) -> Config:
     """Small instruments (a few slits, tens of wavelengths) exercising every geometry rule:
     band A has an even number of detector pixels per slit (the even-na alpha adjustment),
     band B an odd one and a different super-resolution factor."""
     det_a = np.linspace(5.00, 5.10, 48)
     det_b = np.linspace(5.12, 5.30, 40)
-    band_a = instru.IFU(instru.FOV(1.0 / 3600, 1.1 / 3600, instru.Coord(0, 0), FOV_ANGLE), 0.196, 5,
+    band_a = instru.IFU(instru.FOV(1.0 / 3600, 1.1 / 3600, instru.Coord(0, 0), FOV_ANGLE), 0.196, n_slit_a,
                         instru.SpectralBlur(300.0), None, det_a, "MINIA")
     band_b = instru.IFU(instru.FOV(1.4 / 3600, 1.2 / 3600, instru.Coord(0, 0), -11.0), 0.245, 4,
                         instru.SpectralBlur(260.0), None, det_b, "MINIB")
