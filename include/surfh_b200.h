@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SURFH_ABI_VERSION 2
+#define SURFH_ABI_VERSION 3
 
 enum { SURFH_F32 = 0, SURFH_F64 = 1 };
 
@@ -38,6 +38,9 @@ enum { SURFH_F32 = 0, SURFH_F64 = 1 };
  * SURFH_ADJ_EXACT applies the true transpose (dot-test to rounding). */
 enum { SURFH_ADJ_EXACT = 0, SURFH_ADJ_REFERENCE = 1 };
 enum { SURFH_SPECTRAL_LSF = 0, SURFH_SPECTRAL_BETA_SUM = 1 };
+/* 2-D real FFT pair of the cube planes (jax_utils.py:30-41).  AUTO = the hand-written chirp-z
+ * kernels when both map axes are <= 1024 pixels, cuFFT otherwise. */
+enum { SURFH_FFT_AUTO = 0, SURFH_FFT_CUFFT = 1, SURFH_FFT_OWN = 2 };
 
 enum {
     SURFH_OK = 0,
@@ -61,6 +64,8 @@ typedef struct {
     int32_t n_lambda;     /* cube wavelengths                                                 */
     int32_t chunk;        /* wavelengths per pipeline chunk (0 = library default)             */
     const double* templates; /* [any] [K, n_lambda] row-major, NULL when K == 0               */
+    int32_t fft_backend;  /* SURFH_FFT_*; the environment variable SURFH_FFT_BACKEND
+                             (auto | own | cufft) overrides it                                */
 } surfh_model_desc;
 
 /* Sparse table of one adjoint flavour for one band, pointings merged: cube pixel -> weighted
@@ -135,6 +140,16 @@ int surfh_fwadj(surfh_handle h, const void* x, void* out, int32_t mode, void* y_
 /* cube = T x in float32, result export.  Replaces spectroSigRLSCT.mapsToCube
  * (spectroModel.py:190-192 -> cythons_files.pyx:424-440).  maps: [device] real; cube: [device] float */
 int surfh_maps_to_cube(surfh_handle h, const void* maps, float* cube, void* stream);
+
+/* ---- the 2-D real FFT pair on its own --------------------------------------------------- */
+/* Batched un-normalised 2-D real transforms by the hand-written chirp-z kernels that the operator
+ * uses for its cube planes: inverse == 0: real [batch, n_alpha, n_beta] -> half-complex
+ * [batch, n_alpha, n_beta/2+1] (numpy.fft.rfft2); inverse != 0: the reverse, scaled by
+ * n_alpha*n_beta (numpy.fft.irfft2 * n_alpha*n_beta).  Replaces the rfftn / irfftn calls of
+ * surfh/ToolsDir/jax_utils.py:30-41 (python_utils.py:41-71) up to the "ortho" factor.
+ * in, out: [device], contiguous; axes in [2, 1024]; errors via surfh_last_error(NULL). */
+int surfh_rfft2(int32_t dtype, int32_t n_alpha, int32_t n_beta, int32_t batch, int32_t inverse, const void* in, void* out,
+                void* stream);
 
 /* ---- operator, host buffers (the reference-facing call: numpy in, numpy out) --------------- */
 /* double host arrays whatever the handle dtype; copies through pinned staging, synchronises. */

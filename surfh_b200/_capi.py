@@ -16,8 +16,9 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 F32, F64 = 0, 1
 ADJ_EXACT, ADJ_REFERENCE = 0, 1
 CG_NSCALARS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 SPECTRAL_LSF, SPECTRAL_BETA_SUM = 0, 1
+FFT_BACKENDS = {"auto": 0, "cufft": 1, "own": 2}
 
 ADJOINT_MODES = {"exact": ADJ_EXACT, "reference": ADJ_REFERENCE}
 
@@ -26,13 +27,14 @@ SYMBOLS = [
     "surfh_last_error", "surfh_input_size", "surfh_output_size", "surfh_workspace_bytes", "surfh_forward",
     "surfh_adjoint", "surfh_fwadj", "surfh_maps_to_cube", "surfh_forward_host", "surfh_adjoint_host",
     "surfh_cg_regularise_dot", "surfh_cg_start", "surfh_cg_update", "surfh_cg_refresh", "surfh_criterion_terms",
-    "surfh_launch_count", "surfh_own_launch_count", "surfh_profile_enable", "surfh_profile_read",
+    "surfh_launch_count", "surfh_own_launch_count", "surfh_profile_enable", "surfh_profile_read", "surfh_rfft2",
 ]
 
 
 class ModelDesc(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("n_templates", C.c_int32), ("n_alpha", C.c_int32), ("n_beta", C.c_int32),
-                ("n_lambda", C.c_int32), ("chunk", C.c_int32), ("templates", C.c_void_p)]
+                ("n_lambda", C.c_int32), ("chunk", C.c_int32), ("templates", C.c_void_p),
+                ("fft_backend", C.c_int32)]
 
 
 class CsrDesc(C.Structure):
@@ -94,6 +96,7 @@ def load() -> C.CDLL:
         "surfh_cg_update": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "surfh_cg_refresh": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
         "surfh_criterion_terms": (C.c_int, [vp, vp, vp, i64, vp, vp, vp]),
+        "surfh_rfft2": (C.c_int, [i32, i32, i32, i32, i32, vp, vp, vp]),
         "surfh_launch_count": (i64, [vp]),
         "surfh_own_launch_count": (i64, [vp]),
         "surfh_profile_enable": (C.c_int, [vp, i32]),

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -15,6 +16,8 @@
 
 #include "../../include/surfh_b200.h"
 #include "common.cuh"
+#include "host_util.cuh"
+#include "fft_plan.cuh"
 #include "kernels_cg.cuh"
 #include "kernels_gemm.cuh"
 #include "kernels_lmm.cuh"
@@ -22,74 +25,13 @@
 
 namespace surfh {
 
-struct Error : std::runtime_error {
-    int code;
-    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
-};
-
-#define SURFH_CUDA(expr)                                                                                 \
-    do {                                                                                                 \
-        cudaError_t e_ = (expr);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
-            throw Error(SURFH_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                \
-    } while (0)
-#define SURFH_FFT(expr)                                                                                  \
-    do {                                                                                                 \
-        cufftResult r_ = (expr);                                                                         \
-        if (r_ != CUFFT_SUCCESS) throw Error(SURFH_ECUFFT, std::string(#expr) + ": cufft error " + std::to_string((int)r_)); \
-    } while (0)
-#define SURFH_REQUIRE(cond, msg)                                                                         \
-    do {                                                                                                 \
-        if (!(cond)) throw Error(SURFH_EINVAL, std::string(msg));                                        \
-    } while (0)
-
-static thread_local std::string g_create_error;
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { release(); }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-    void alloc(size_t n) {
-        release();
-        if (n == 0) return;
-        cudaError_t e = cudaMalloc(&p, n);
-        if (e != cudaSuccess) throw Error(SURFH_ENOMEM, "cudaMalloc(" + std::to_string(n) + " bytes): " + cudaGetErrorString(e));
-        bytes = n;
-    }
-    void ensure(size_t n) {
-        if (bytes < n) alloc(n);
-    }
-    void ensure_zeroed(size_t n) {  // zero-filled on (re)allocation only
-        if (bytes < n) {
-            alloc(n);
-            if (cudaMemset(p, 0, n) != cudaSuccess) throw Error(SURFH_ECUDA, "cudaMemset failed");
-        }
-    }
-    template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
-};
-
-template <typename U, typename V> static void upload_converted(DevBuf& dst, const V* src, size_t n) {
-    std::vector<U> tmp(n);
-    for (size_t i = 0; i < n; ++i) tmp[i] = (U)src[i];
-    dst.alloc(n * sizeof(U));
-    SURFH_CUDA(cudaMemcpy(dst.p, tmp.data(), n * sizeof(U), cudaMemcpyHostToDevice));
-}
-
 enum Stage {
     ST_RFFT_MAPS = 0, ST_LMM_OTF_FWD, ST_IRFFT_CUBE, ST_SLIT_GATHER, ST_GEMM_FWD,
     ST_GEMM_ADJ, ST_SLIT_SCATTER, ST_RFFT_CUBE, ST_LMM_OTF_ADJ, ST_IRFFT_MAPS, ST_MEMSET, ST_CG, ST_COUNT
 };
 static const char* kStageNames[ST_COUNT] = {
-    "cufft_rfft_maps", "lmm_otf_fwd", "cufft_irfft_cube", "slit_gather", "spectral_gemm_fwd",
-    "spectral_gemm_adj", "slit_scatter", "cufft_rfft_cube", "lmm_otf_adj", "cufft_irfft_maps", "memset", "cg_fused"};
+    "rfft_maps", "lmm_otf_fwd", "irfft_cube", "slit_gather", "spectral_gemm_fwd",
+    "spectral_gemm_adj", "slit_scatter", "rfft_cube", "lmm_otf_adj", "irfft_maps", "memset", "cg_fused"};
 
 }  // namespace surfh
 
@@ -218,6 +160,10 @@ template <typename T> struct ModelImpl : surfh_model {
     DevBuf spec;      // [chunk][nfp] complex
     DevBuf cubebuf;   // [chunk][plane] real
     DevBuf fft_work;
+    DevBuf zbuf;      // [max(chunk, K)][z_plane] complex: intermediate of the hand-written FFT passes
+    OwnFft2d<T> ownfft;
+    int fft_backend = SURFH_FFT_AUTO;
+    bool use_own_fft = false;
     DevBuf y_internal, x_stage, y_stage, dbl_stage;
     DevBuf cg_partial, cg_ticket;
     std::vector<std::unique_ptr<BandT<T>>> bands;
@@ -239,6 +185,18 @@ template <typename T> struct ModelImpl : surfh_model {
         nf = (size_t)Na * Nh;
         nfp = (nf + 15) / 16 * 16;
         chunk = d->chunk > 0 ? d->chunk : 0;
+        fft_backend = d->fft_backend;
+        if (const char* e = std::getenv("SURFH_FFT_BACKEND")) {  // A/B switch for benchmarks and tests
+            if (!std::strcmp(e, "cufft")) fft_backend = SURFH_FFT_CUFFT;
+            else if (!std::strcmp(e, "own")) fft_backend = SURFH_FFT_OWN;
+            else if (!std::strcmp(e, "auto")) fft_backend = SURFH_FFT_AUTO;
+            else throw Error(SURFH_EINVAL, "SURFH_FFT_BACKEND must be auto, own or cufft");
+        }
+        SURFH_REQUIRE(fft_backend == SURFH_FFT_AUTO || fft_backend == SURFH_FFT_CUFFT || fft_backend == SURFH_FFT_OWN,
+                      "unknown fft_backend");
+        SURFH_REQUIRE(fft_backend != SURFH_FFT_OWN || OwnFft2d<T>::supported(Na, Nb),
+                      "fft_backend = own needs both map axes <= 1024 pixels");
+        use_own_fft = fft_backend == SURFH_FFT_OWN || (fft_backend == SURFH_FFT_AUTO && OwnFft2d<T>::supported(Na, Nb));
         otf.alloc((size_t)Nl * nfp * sizeof(C));
         SURFH_CUDA(cudaMemset(otf.p, 0, otf.bytes));
         otf_set.assign(Nl, 0);
@@ -429,16 +387,23 @@ template <typename T> struct ModelImpl : surfh_model {
         if (K > 0) {
             xhat.alloc((size_t)K * nfp * sizeof(C));
             SURFH_CUDA(cudaMemset(xhat.p, 0, xhat.bytes));
-            make_plan(0, K);
-            make_plan(1, K);
         }
-        for (auto& r : ranges) {
-            const int len = r.second - r.first;
-            if (len >= chunk) { make_plan(0, chunk); make_plan(1, chunk); }
-            if (len % chunk) { make_plan(0, len % chunk); make_plan(1, len % chunk); }
+        if (use_own_fft) {
+            ownfft.init(Na, Nb);
+            zbuf.alloc((size_t)std::max(chunk, K) * ownfft.z_plane() * sizeof(C));
+        } else {
+            if (K > 0) {
+                make_plan(0, K);
+                make_plan(1, K);
+            }
+            for (auto& r : ranges) {
+                const int len = r.second - r.first;
+                if (len >= chunk) { make_plan(0, chunk); make_plan(1, chunk); }
+                if (len % chunk) { make_plan(0, len % chunk); make_plan(1, len % chunk); }
+            }
+            fft_work.alloc(fft_work_bytes);
+            for (auto& kv : plans) SURFH_FFT(cufftSetWorkArea(kv.second, fft_work.p));
         }
-        fft_work.alloc(fft_work_bytes);
-        for (auto& kv : plans) SURFH_FFT(cufftSetWorkArea(kv.second, fft_work.p));
         // opt in to > 48 KB dynamic shared memory for the GEMM kernels
         using G = GemmCfg<T>;
         const int smem = (int)otgemm_smem_bytes<T, G::BM, G::BN, G::BK>();
@@ -463,7 +428,7 @@ template <typename T> struct ModelImpl : surfh_model {
         return m;
     }
     int64_t workspace_bytes() const override {
-        int64_t t = otf.bytes + tpl.bytes + tpl_raw.bytes + xhat.bytes + spec.bytes + cubebuf.bytes + fft_work.bytes +
+        int64_t t = otf.bytes + tpl.bytes + tpl_raw.bytes + xhat.bytes + spec.bytes + cubebuf.bytes + fft_work.bytes + zbuf.bytes +
                     y_internal.bytes + x_stage.bytes + y_stage.bytes + dbl_stage.bytes;
         for (auto& b : bands)
             t += b->lsf.bytes + b->G.bytes + b->grid_base.bytes + b->grid_frac.bytes + b->csr_col[0].bytes +
@@ -499,7 +464,15 @@ template <typename T> struct ModelImpl : surfh_model {
         default: throw Error(SURFH_EINVAL, "unsupported template count");                  \
     }
 
+    int fft_launches() const { return use_own_fft ? 2 : 1; }
     void fft_exec(int kind, int batch, void* in, void* out, cudaStream_t st) {
+        if (use_own_fft) {
+            if (kind == 0)
+                ownfft.r2c(reinterpret_cast<const T*>(in), plane, reinterpret_cast<C*>(out), nfp, zbuf.as<C>(), batch, st);
+            else
+                ownfft.c2r(reinterpret_cast<const C*>(in), nfp, reinterpret_cast<T*>(out), plane, zbuf.as<C>(), batch, st);
+            return;
+        }
         cufftHandle p = plan(kind, batch);
         SURFH_FFT(cufftSetStream(p, st));
         if (kind == 0)
@@ -619,7 +592,7 @@ template <typename T> struct ModelImpl : surfh_model {
         const T* x = reinterpret_cast<const T*>(xv);
         T* y = reinterpret_cast<T*>(yv);
         if (K > 0) {
-            Scope sc(this, ST_RFFT_MAPS, st, (double)K * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+            Scope sc(this, ST_RFFT_MAPS, st, (double)K * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
             fft_exec(0, K, const_cast<T*>(x), xhat.p, st);
         }
         for (auto& r : ranges) {
@@ -632,7 +605,7 @@ template <typename T> struct ModelImpl : surfh_model {
                     SURFH_CUDA(cudaGetLastError());
                 } else {
                     {
-                        Scope sc(this, ST_RFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+                        Scope sc(this, ST_RFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
                         fft_exec(0, nl, const_cast<T*>(x) + (size_t)c0 * plane, spec.p, st);
                     }
                     Scope sc(this, ST_LMM_OTF_FWD, st, (double)nl * nf * sizeof(C) * 3, 6.0 * nl * nf, 1, true);
@@ -642,7 +615,7 @@ template <typename T> struct ModelImpl : surfh_model {
                     SURFH_CUDA(cudaGetLastError());
                 }
                 {
-                    Scope sc(this, ST_IRFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+                    Scope sc(this, ST_IRFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
                     fft_exec(1, nl, spec.p, cubebuf.p, st);
                 }
                 gather_chunk(c0, c1, st);
@@ -668,7 +641,7 @@ template <typename T> struct ModelImpl : surfh_model {
                 const int c1 = std::min(r.second, c0 + chunk), nl = c1 - c0;
                 scatter_chunk(c0, c1, mode, st);
                 {
-                    Scope sc(this, ST_RFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+                    Scope sc(this, ST_RFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
                     fft_exec(0, nl, cubebuf.p, spec.p, st);
                 }
                 if (K > 0) {
@@ -684,14 +657,14 @@ template <typename T> struct ModelImpl : surfh_model {
                             spec.as<C>(), otf.as<C>() + (size_t)c0 * nfp, n, (T)(1.0 / ((double)Na * Nb)));
                         SURFH_CUDA(cudaGetLastError());
                     }
-                    Scope sc(this, ST_IRFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+                    Scope sc(this, ST_IRFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
                     fft_exec(1, nl, spec.p, x + (size_t)c0 * plane, st);
                 }
                 first = false;
             }
         }
         if (K > 0) {
-            Scope sc(this, ST_IRFFT_MAPS, st, (double)K * (plane * sizeof(T) + nf * sizeof(C)), 0, 1, false);
+            Scope sc(this, ST_IRFFT_MAPS, st, (double)K * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
             fft_exec(1, K, xhat.p, x, st);
         }
     }
@@ -879,6 +852,30 @@ template <> void ModelImpl<double>::gemm_grouped_f64(double* y, bool adjoint, cu
     }                                                        \
     return SURFH_OK;
 
+// Stand-alone batched 2-D real FFT pair through the hand-written kernels (plans cached per shape).
+namespace {
+template <typename T> struct FftCacheEntry {
+    surfh::OwnFft2d<T> fft;
+    surfh::DevBuf z;
+};
+template <typename T> int rfft2_impl(int na, int nb, int batch, int inverse, const void* in, void* out, cudaStream_t st) {
+    using Cx = surfh::cplx_t<T>;
+    static std::map<std::pair<int, int>, std::unique_ptr<FftCacheEntry<T>>> cache;
+    if (!surfh::OwnFft2d<T>::supported(na, nb)) throw Error(SURFH_EINVAL, "surfh_rfft2: axes must be in [2, 1024]");
+    if (batch <= 0 || !in || !out) throw Error(SURFH_EINVAL, "surfh_rfft2: bad batch or NULL buffer");
+    auto& e = cache[std::make_pair(na, nb)];
+    if (!e) {
+        e = std::make_unique<FftCacheEntry<T>>();
+        e->fft.init(na, nb);
+    }
+    e->z.ensure((size_t)batch * e->fft.z_plane() * sizeof(Cx));
+    const size_t rp = (size_t)na * nb, sp = (size_t)na * (nb / 2 + 1);
+    if (!inverse) e->fft.r2c(reinterpret_cast<const T*>(in), rp, reinterpret_cast<Cx*>(out), sp, e->z.template as<Cx>(), batch, st);
+    else e->fft.c2r(reinterpret_cast<const Cx*>(in), sp, reinterpret_cast<T*>(out), rp, e->z.template as<Cx>(), batch, st);
+    return SURFH_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int surfh_abi_version(void) { return SURFH_ABI_VERSION; }
@@ -985,6 +982,21 @@ int surfh_criterion_terms(surfh_handle h, const void* y, const void* hx, int64_t
                           void* stream) {
     SURFH_API_BEGIN(h) h->criterion_terms(y, hx, n, x, s_out, (cudaStream_t)stream);
     SURFH_API_END(h)
+}
+
+int surfh_rfft2(int32_t dtype, int32_t n_alpha, int32_t n_beta, int32_t batch, int32_t inverse, const void* in, void* out,
+                void* stream) {
+    try {
+        if (dtype == SURFH_F64) return rfft2_impl<double>(n_alpha, n_beta, batch, inverse, in, out, (cudaStream_t)stream);
+        if (dtype == SURFH_F32) return rfft2_impl<float>(n_alpha, n_beta, batch, inverse, in, out, (cudaStream_t)stream);
+        throw Error(SURFH_EINVAL, "dtype must be SURFH_F32 or SURFH_F64");
+    } catch (const surfh::Error& e) {
+        g_create_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return SURFH_EINVAL;
+    }
 }
 
 int64_t surfh_launch_count(surfh_handle h) { return h ? h->launches : -1; }

@@ -1,0 +1,174 @@
+// Host side of the hand-written 2-D real FFT pair (kernels_fft.cuh): table construction and launches.
+//
+// Replaces the cuFFT plans for the reference's `rfftn` / `irfftn(norm="ortho")` calls
+// (surfh/ToolsDir/jax_utils.py:30-41, python_utils.py:41-71) whenever both map axes are <= 1024
+// pixels; the transforms are un-normalised like cuFFT's.
+#pragma once
+#include <cmath>
+#include <vector>
+
+#include "host_util.cuh"
+#include "kernels_fft.cuh"
+
+namespace surfh {
+
+// Dispatch on the chirp-z length (a power of two in [256, 2048]).
+#define SURFH_DISPATCH_M(m, ...)                                       \
+    switch (m) {                                                       \
+        case 256: { constexpr int MM = 256; __VA_ARGS__; } break;      \
+        case 512: { constexpr int MM = 512; __VA_ARGS__; } break;      \
+        case 1024: { constexpr int MM = 1024; __VA_ARGS__; } break;    \
+        case 2048: { constexpr int MM = 2048; __VA_ARGS__; } break;    \
+        default: throw Error(SURFH_EINVAL, "unsupported chirp-z length"); \
+    }
+
+template <typename S, typename D>
+__global__ void fft_convert_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (D)src[i];
+}
+
+// Tables of one axis length.
+template <typename T> struct FftAxis {
+    using C = cplx_t<T>;
+    int n = 0, m = 0;
+    DevBuf chirp, filt, tw;
+
+    // smallest supported chirp-z length for n points: n <= m/2 (so 2n-1 <= m); 0 when n > 1024
+    static int pick_m(int n) {
+        for (int m = 256; m <= 2048; m *= 2)
+            if (n <= m / 2) return m;
+        return 0;
+    }
+
+    template <int M> static void set_smem_attr() {
+        const int bytes = (int)fft_smem_bytes<T, M>();
+        SURFH_CUDA(cudaFuncSetAttribute(fft_rows_r2c_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        SURFH_CUDA(cudaFuncSetAttribute(fft_cols_r2c_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        SURFH_CUDA(cudaFuncSetAttribute(fft_cols_c2r_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        SURFH_CUDA(cudaFuncSetAttribute(fft_rows_c2r_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    }
+
+    void init(int n_) {
+        n = n_;
+        m = pick_m(n);
+        if (m == 0) throw Error(SURFH_EINVAL, "axis too long for the hand-written FFT (max 1024)");
+        const double pi = 3.14159265358979323846;
+        // everything is evaluated in double, the filter spectrum with the double instantiation of the
+        // very FFT code that consumes it, and only then rounded to T
+        std::vector<double2> h_tw(m), h_chirp(n), h_b(m);
+        for (int j = 0; j < m; ++j) {
+            const double a = -2.0 * pi * (double)j / (double)m;
+            h_tw[j] = make_double2(std::cos(a), std::sin(a));
+            h_b[j] = make_double2(0.0, 0.0);
+        }
+        for (int j = 0; j < n; ++j) {
+            const long long q = ((long long)j * j) % (2ll * n);  // exp(-i pi j^2 / n) has period 2n in j^2
+            const double a = -pi * (double)q / (double)n;
+            h_chirp[j] = make_double2(std::cos(a), std::sin(a));
+            const double2 bj = make_double2(std::cos(a) / m, -std::sin(a) / m);  // conj(chirp) / M
+            h_b[j] = bj;
+            if (j) h_b[m - j] = bj;
+        }
+        DevBuf d_tw, d_b, d_filt;
+        d_tw.alloc(m * sizeof(double2));
+        d_b.alloc(m * sizeof(double2));
+        d_filt.alloc(m * sizeof(double2));
+        SURFH_CUDA(cudaMemcpy(d_tw.p, h_tw.data(), m * sizeof(double2), cudaMemcpyHostToDevice));
+        SURFH_CUDA(cudaMemcpy(d_b.p, h_b.data(), m * sizeof(double2), cudaMemcpyHostToDevice));
+        SURFH_DISPATCH_M(m, {
+            const int bytes = (int)fft_smem_bytes<double, MM>();
+            SURFH_CUDA(cudaFuncSetAttribute(fft_filter_kernel<double, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            fft_filter_kernel<double, MM><<<1, 256, bytes>>>(d_b.as<double2>(), d_tw.as<double2>(), d_filt.as<double2>());
+            set_smem_attr<MM>();
+        });
+        SURFH_CUDA(cudaGetLastError());
+        DevBuf d_chirp;
+        d_chirp.alloc(n * sizeof(double2));
+        SURFH_CUDA(cudaMemcpy(d_chirp.p, h_chirp.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
+        chirp.alloc(n * sizeof(C));
+        filt.alloc(m * sizeof(C));
+        tw.alloc(m * sizeof(C));
+        fft_convert_kernel<double, T><<<ceil_div(2 * n, 256), 256>>>(d_chirp.as<double>(), chirp.as<T>(), (size_t)2 * n);
+        fft_convert_kernel<double, T><<<ceil_div(2 * m, 256), 256>>>(d_filt.as<double>(), filt.as<T>(), (size_t)2 * m);
+        fft_convert_kernel<double, T><<<ceil_div(2 * m, 256), 256>>>(d_tw.as<double>(), tw.as<T>(), (size_t)2 * m);
+        SURFH_CUDA(cudaGetLastError());
+        SURFH_CUDA(cudaDeviceSynchronize());
+    }
+
+    FftPlan1d<T> plan() const {
+        FftPlan1d<T> p;
+        p.chirp = chirp.as<C>();
+        p.filt = filt.as<C>();
+        p.tw = tw.as<C>();
+        p.n = n;
+        return p;
+    }
+};
+
+// Batched 2-D real <-> half-complex transforms of [na][nb] planes.
+template <typename T> struct OwnFft2d {
+    using C = cplx_t<T>;
+    int na = 0, nb = 0, nh = 0;
+    FftAxis<T> axis_a, axis_b_store;
+    const FftAxis<T>* axis_b = nullptr;
+    bool ready = false;
+
+    static bool supported(int na, int nb) { return FftAxis<T>::pick_m(na) && FftAxis<T>::pick_m(nb) && na > 1 && nb > 1; }
+
+    void init(int na_, int nb_) {
+        na = na_; nb = nb_; nh = nb / 2 + 1;
+        axis_a.init(na);
+        if (nb == na) axis_b = &axis_a;
+        else { axis_b_store.init(nb); axis_b = &axis_b_store; }
+        ready = true;
+    }
+
+    // complex elements per plane of the intermediate buffer
+    size_t z_plane() const { return std::max((size_t)((na + 1) / 2) * nb, (size_t)na * nh); }
+
+    FftShape shape(size_t real_plane, size_t spec_plane, int batch) const {
+        FftShape s;
+        s.na = na; s.nb = nb; s.nh = nh; s.npair = (na + 1) / 2; s.zpitch = nb;
+        s.real_plane = real_plane; s.spec_plane = spec_plane; s.z_plane = z_plane(); s.batch = batch;
+        return s;
+    }
+
+    // in: real [batch] planes (stride real_plane) -> spec: [batch][na][nh] (stride spec_plane); z: scratch
+    void r2c(const T* in, size_t real_plane, C* spec, size_t spec_plane, C* z, int batch, cudaStream_t st) const {
+        const FftShape s = shape(real_plane, spec_plane, batch);
+        SURFH_DISPATCH_M(axis_b->m, {
+            using Gm = FftGeom<MM>;
+            const long long items = (long long)batch * s.npair;
+            fft_rows_r2c_kernel<T, MM><<<(unsigned)((items + Gm::G - 1) / Gm::G), 256, fft_smem_bytes<T, MM>(), st>>>(
+                in, z, s, axis_b->plan());
+        });
+        SURFH_DISPATCH_M(axis_a.m, {
+            using Gm = FftGeom<MM>;
+            const int tiles = (nh + Gm::G - 1) / Gm::G;
+            fft_cols_r2c_kernel<T, MM><<<(unsigned)(batch * tiles), 256, fft_smem_bytes<T, MM>(), st>>>(z, spec, s,
+                                                                                                     axis_a.plan());
+        });
+        SURFH_CUDA(cudaGetLastError());
+    }
+
+    // spec: [batch][na][nh] -> out: real planes; z: scratch
+    void c2r(const C* spec, size_t spec_plane, T* out, size_t real_plane, C* z, int batch, cudaStream_t st) const {
+        const FftShape s = shape(real_plane, spec_plane, batch);
+        SURFH_DISPATCH_M(axis_a.m, {
+            using Gm = FftGeom<MM>;
+            const int tiles = (nh + Gm::G - 1) / Gm::G;
+            fft_cols_c2r_kernel<T, MM><<<(unsigned)(batch * tiles), 256, fft_smem_bytes<T, MM>(), st>>>(spec, z, s,
+                                                                                                     axis_a.plan());
+        });
+        SURFH_DISPATCH_M(axis_b->m, {
+            using Gm = FftGeom<MM>;
+            const long long items = (long long)batch * s.npair;
+            fft_rows_c2r_kernel<T, MM><<<(unsigned)((items + Gm::G - 1) / Gm::G), 256, fft_smem_bytes<T, MM>(), st>>>(
+                z, out, s, axis_b->plan());
+        });
+        SURFH_CUDA(cudaGetLastError());
+    }
+};
+
+}  // namespace surfh

@@ -91,6 +91,8 @@ class spectroSigRLSCT(LinOp):
       comm           surfh_b200.dist.Comm: when given, device-tensor forward/adjoint/fwadj all-reduce
                      their partial results so every rank returns the full operator's output
       chunk          wavelengths per pipeline chunk (0 = library default)
+      fft_backend    "auto" (default: hand-written chirp-z FFT kernels for maps up to 1024 pixels a side,
+                     cuFFT beyond), "own" or "cufft"
       device         CUDA device index (default: current device)
       sotf           may also be a torch CUDA complex tensor, or a callable (l0, l1) -> complex
                      array/tensor of planes [l0, l1), so a multi-GB OTF never sits on the host
@@ -101,11 +103,15 @@ class spectroSigRLSCT(LinOp):
     def __init__(self, sotf, templates, alpha_axis, beta_axis, wavelength_axis,
                  instrs: List[instru.IFU], step_degree: float, pointings: Sequence[instru.CoordList],
                  dtype="float64", adjoint_mode: str = "reference", local_bands: Optional[Sequence[int]] = None,
-                 chunk: int = 0, device: Optional[int] = None, lambda_range=None, comm=None):
+                 chunk: int = 0, device: Optional[int] = None, lambda_range=None, comm=None,
+                 fft_backend: str = "auto"):
         self._h = None
         self._lib = _capi.load()
         if adjoint_mode not in _capi.ADJOINT_MODES:
             raise ValueError("adjoint_mode must be 'reference' or 'exact'")
+        if fft_backend not in _capi.FFT_BACKENDS:
+            raise ValueError("fft_backend must be 'auto', 'own' or 'cufft'")
+        self.fft_backend = fft_backend
         self.adjoint_mode = adjoint_mode
         self._dtype_code = _DTYPES[dtype]
         self.np_dtype = np.float64 if self._dtype_code == _capi.F64 else np.float32
@@ -156,7 +162,8 @@ class spectroSigRLSCT(LinOp):
 
         desc = _capi.ModelDesc(self._dtype_code, self.templates.shape[0] if self.lmm else 0,
                                len(self.alpha_axis), len(self.beta_axis), len(self.wavelength_axis), int(chunk),
-                               _capi.ptr(self.templates) if self.lmm else None)
+                               _capi.ptr(self.templates) if self.lmm else None,
+                               _capi.FFT_BACKENDS[fft_backend])
         handle = C.c_void_p()
         code = self._lib.surfh_create(C.byref(desc), C.byref(handle))
         _capi.check(None, code)

@@ -25,13 +25,13 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(_capi.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported"
-    assert lib.surfh_abi_version() == _capi.ABI_VERSION == 2
+    assert lib.surfh_abi_version() == _capi.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():
     from surfh_b200 import _capi
-    # sizes implied by the header on LP64: 6 int32 + pointer; int32 + int64 + 4 pointers; ...
-    assert C.sizeof(_capi.ModelDesc) == 32
+    # sizes implied by the header on LP64: 6 int32 + pointer + int32 (padded); int32 + int64 + 4 pointers; ...
+    assert C.sizeof(_capi.ModelDesc) == 40
     assert C.sizeof(_capi.CsrDesc) == 48
     assert C.sizeof(_capi.BandDesc) == 48 + 8 + 6 * 8 + 2 * 48
 
