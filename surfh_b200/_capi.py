@@ -11,7 +11,9 @@ from typing import Optional
 import numpy as np
 
 LIB_NAME = "libsurfh_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# SURFH_B200_LIB points at an experimental build of the same library (kernel A/B runs); there is still
+# no fallback: whichever path is named must exist.
+LIB_PATH = os.environ.get("SURFH_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 F32, F64 = 0, 1
 ADJ_EXACT, ADJ_REFERENCE = 0, 1

@@ -36,8 +36,9 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    """`out` / `defines` build an experimental variant beside the product library (kernel A/B runs)."""
+    if out == OUT and not force and not needs_build():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cufft = _cufft_dir()
@@ -45,14 +46,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
            "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
-    cmd += ["-o", OUT, "-L" + cufft, lib, "-Xlinker", "-rpath=" + cufft]
+    cmd += ["-D" + d for d in defines]
+    cmd += ["-o", out, "-L" + cufft, lib, "-Xlinker", "-rpath=" + cufft]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libsurfh_b200.so")
     if verbose:
         print(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

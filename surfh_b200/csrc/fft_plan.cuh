@@ -41,12 +41,15 @@ template <typename T> struct FftAxis {
         return 0;
     }
 
+    template <int M, typename Pass> static void set_pass_attr() {
+        SURFH_CUDA(cudaFuncSetAttribute(fft_pass_kernel<T, M, Pass>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)fft_pass_smem_bytes<T, M, Pass>()));
+    }
     template <int M> static void set_smem_attr() {
-        const int bytes = (int)fft_smem_bytes<T, M>();
-        SURFH_CUDA(cudaFuncSetAttribute(fft_rows_r2c_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        SURFH_CUDA(cudaFuncSetAttribute(fft_cols_r2c_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        SURFH_CUDA(cudaFuncSetAttribute(fft_cols_c2r_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        SURFH_CUDA(cudaFuncSetAttribute(fft_rows_c2r_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        set_pass_attr<M, RowsR2C<T, M>>();
+        set_pass_attr<M, ColsR2C<T, M>>();
+        set_pass_attr<M, ColsC2R<T, M>>();
+        set_pass_attr<M, RowsC2R<T, M>>();
     }
 
     void init(int n_) {
@@ -56,12 +59,17 @@ template <typename T> struct FftAxis {
         const double pi = 3.14159265358979323846;
         // everything is evaluated in double, the filter spectrum with the double instantiation of the
         // very FFT code that consumes it, and only then rounded to T
-        std::vector<double2> h_tw(m), h_chirp(n), h_b(m);
-        for (int j = 0; j < m; ++j) {
-            const double a = -2.0 * pi * (double)j / (double)m;
-            h_tw[j] = make_double2(std::cos(a), std::sin(a));
-            h_b[j] = make_double2(0.0, 0.0);
-        }
+        const int tt = m / 16, r3 = m / 256, ntw = m + 16 * r3;
+        std::vector<double2> h_tw(ntw), h_chirp(n), h_b(m);
+        auto root = [&](long long e) {  // exp(-2 pi i e / m)
+            const double a = -2.0 * pi * (double)(e % m) / (double)m;
+            return make_double2(std::cos(a), std::sin(a));
+        };
+        for (int q = 0; q < 16; ++q)
+            for (int t = 0; t < tt; ++t) h_tw[q * tt + t] = root((long long)q * t);
+        for (int q2 = 0; q2 < 16; ++q2)
+            for (int n2 = 0; n2 < r3; ++n2) h_tw[m + q2 * r3 + n2] = root(16ll * n2 * q2);
+        for (int j = 0; j < m; ++j) h_b[j] = make_double2(0.0, 0.0);
         for (int j = 0; j < n; ++j) {
             const long long q = ((long long)j * j) % (2ll * n);  // exp(-i pi j^2 / n) has period 2n in j^2
             const double a = -pi * (double)q / (double)n;
@@ -71,15 +79,15 @@ template <typename T> struct FftAxis {
             if (j) h_b[m - j] = bj;
         }
         DevBuf d_tw, d_b, d_filt;
-        d_tw.alloc(m * sizeof(double2));
+        d_tw.alloc(ntw * sizeof(double2));
         d_b.alloc(m * sizeof(double2));
         d_filt.alloc(m * sizeof(double2));
-        SURFH_CUDA(cudaMemcpy(d_tw.p, h_tw.data(), m * sizeof(double2), cudaMemcpyHostToDevice));
+        SURFH_CUDA(cudaMemcpy(d_tw.p, h_tw.data(), ntw * sizeof(double2), cudaMemcpyHostToDevice));
         SURFH_CUDA(cudaMemcpy(d_b.p, h_b.data(), m * sizeof(double2), cudaMemcpyHostToDevice));
         SURFH_DISPATCH_M(m, {
             const int bytes = (int)fft_smem_bytes<double, MM>();
             SURFH_CUDA(cudaFuncSetAttribute(fft_filter_kernel<double, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            fft_filter_kernel<double, MM><<<1, 256, bytes>>>(d_b.as<double2>(), d_tw.as<double2>(), d_filt.as<double2>());
+            fft_filter_kernel<double, MM><<<1, FftK<double, MM>::NT, bytes>>>(d_b.as<double2>(), d_tw.as<double2>(), d_filt.as<double2>());
             set_smem_attr<MM>();
         });
         SURFH_CUDA(cudaGetLastError());
@@ -88,10 +96,10 @@ template <typename T> struct FftAxis {
         SURFH_CUDA(cudaMemcpy(d_chirp.p, h_chirp.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
         chirp.alloc(n * sizeof(C));
         filt.alloc(m * sizeof(C));
-        tw.alloc(m * sizeof(C));
+        tw.alloc(ntw * sizeof(C));
         fft_convert_kernel<double, T><<<ceil_div(2 * n, 256), 256>>>(d_chirp.as<double>(), chirp.as<T>(), (size_t)2 * n);
         fft_convert_kernel<double, T><<<ceil_div(2 * m, 256), 256>>>(d_filt.as<double>(), filt.as<T>(), (size_t)2 * m);
-        fft_convert_kernel<double, T><<<ceil_div(2 * m, 256), 256>>>(d_tw.as<double>(), tw.as<T>(), (size_t)2 * m);
+        fft_convert_kernel<double, T><<<ceil_div(2 * ntw, 256), 256>>>(d_tw.as<double>(), tw.as<T>(), (size_t)2 * ntw);
         SURFH_CUDA(cudaGetLastError());
         SURFH_CUDA(cudaDeviceSynchronize());
     }
@@ -113,11 +121,15 @@ template <typename T> struct OwnFft2d {
     FftAxis<T> axis_a, axis_b_store;
     const FftAxis<T>* axis_b = nullptr;
     bool ready = false;
+    int n_sm = 148;
 
     static bool supported(int na, int nb) { return FftAxis<T>::pick_m(na) && FftAxis<T>::pick_m(nb) && na > 1 && nb > 1; }
 
     void init(int na_, int nb_) {
         na = na_; nb = nb_; nh = nb / 2 + 1;
+        int dev = 0;
+        SURFH_CUDA(cudaGetDevice(&dev));
+        SURFH_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         axis_a.init(na);
         if (nb == na) axis_b = &axis_a;
         else { axis_b_store.init(nb); axis_b = &axis_b_store; }
@@ -134,20 +146,25 @@ template <typename T> struct OwnFft2d {
         return s;
     }
 
+    // persistent launch: one CTA per resident slot, each walking the items with a grid stride
+    template <int MM, typename Pass> void launch(const Pass& pass, long long n_items, const FftAxis<T>& ax, cudaStream_t st) const {
+        const long long slots = (long long)n_sm * FftK<T, MM>::MINB;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min(n_items, slots));
+        fft_pass_kernel<T, MM, Pass><<<grid, FftK<T, MM>::NT, fft_pass_smem_bytes<T, MM, Pass>(), st>>>(pass, ax.plan());
+    }
+
     // in: real [batch] planes (stride real_plane) -> spec: [batch][na][nh] (stride spec_plane); z: scratch
     void r2c(const T* in, size_t real_plane, C* spec, size_t spec_plane, C* z, int batch, cudaStream_t st) const {
         const FftShape s = shape(real_plane, spec_plane, batch);
         SURFH_DISPATCH_M(axis_b->m, {
-            using Gm = FftGeom<MM>;
-            const long long items = (long long)batch * s.npair;
-            fft_rows_r2c_kernel<T, MM><<<(unsigned)((items + Gm::G - 1) / Gm::G), 256, fft_smem_bytes<T, MM>(), st>>>(
-                in, z, s, axis_b->plan());
+            using Gm = typename FftK<T, MM>::Gm;
+            RowsR2C<T, MM> pass{in, z, s};
+            launch<MM>(pass, ((long long)batch * s.npair + Gm::G - 1) / Gm::G, *axis_b, st);
         });
         SURFH_DISPATCH_M(axis_a.m, {
-            using Gm = FftGeom<MM>;
-            const int tiles = (nh + Gm::G - 1) / Gm::G;
-            fft_cols_r2c_kernel<T, MM><<<(unsigned)(batch * tiles), 256, fft_smem_bytes<T, MM>(), st>>>(z, spec, s,
-                                                                                                     axis_a.plan());
+            using Gm = typename FftK<T, MM>::Gm;
+            ColsR2C<T, MM> pass{z, spec, s};
+            launch<MM>(pass, (long long)batch * ((nh + Gm::G - 1) / Gm::G), axis_a, st);
         });
         SURFH_CUDA(cudaGetLastError());
     }
@@ -156,16 +173,14 @@ template <typename T> struct OwnFft2d {
     void c2r(const C* spec, size_t spec_plane, T* out, size_t real_plane, C* z, int batch, cudaStream_t st) const {
         const FftShape s = shape(real_plane, spec_plane, batch);
         SURFH_DISPATCH_M(axis_a.m, {
-            using Gm = FftGeom<MM>;
-            const int tiles = (nh + Gm::G - 1) / Gm::G;
-            fft_cols_c2r_kernel<T, MM><<<(unsigned)(batch * tiles), 256, fft_smem_bytes<T, MM>(), st>>>(spec, z, s,
-                                                                                                     axis_a.plan());
+            using Gm = typename FftK<T, MM>::Gm;
+            ColsC2R<T, MM> pass{spec, z, s};
+            launch<MM>(pass, (long long)batch * ((nh + Gm::G - 1) / Gm::G), axis_a, st);
         });
         SURFH_DISPATCH_M(axis_b->m, {
-            using Gm = FftGeom<MM>;
-            const long long items = (long long)batch * s.npair;
-            fft_rows_c2r_kernel<T, MM><<<(unsigned)((items + Gm::G - 1) / Gm::G), 256, fft_smem_bytes<T, MM>(), st>>>(
-                z, out, s, axis_b->plan());
+            using Gm = typename FftK<T, MM>::Gm;
+            RowsC2R<T, MM> pass{z, out, s};
+            launch<MM>(pass, ((long long)batch * s.npair + Gm::G - 1) / Gm::G, *axis_b, st);
         });
         SURFH_CUDA(cudaGetLastError());
     }
