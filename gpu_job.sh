@@ -1,7 +1,5 @@
 set -x
-python -m pytest tests/test_gpu_fft.py -x -q 2>&1 | tail -5
-python tools/fft_bench.py 501 512 float64 5
-python tools/fft_bench.py 251 512 float64 5
-python tools/fft_bench.py 501 512 float32 5
-python tools/fft_bench.py 501 128 float64 1 > gpurun_out/plain_fft.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:fft_ -s 8 -c 4 -o gpurun_out/prof_fft3 -f python tools/fft_bench.py 501 128 float64 1 > gpurun_out/ncu_fft.log 2>&1
-tail -3 gpurun_out/ncu_fft.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python bench.py --config c4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/v4_c4.json 2> gpurun_out/v4_c4.err; tail -2 gpurun_out/v4_c4.err
+python bench.py --config c2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/v4_c2.json 2> gpurun_out/v4_c2.err; tail -2 gpurun_out/v4_c2.err
+python bench.py --config c4 --dtype float32 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/v4_c4_f32.json 2> gpurun_out/v4_c4_f32.err; tail -2 gpurun_out/v4_c4_f32.err

@@ -43,12 +43,12 @@ template <typename T> struct FftAxis {
 
     template <int M, typename Pass> static void set_pass_attr() {
         SURFH_CUDA(cudaFuncSetAttribute(fft_pass_kernel<T, M, Pass>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)fft_pass_smem_bytes<T, M, Pass>()));
+                                        (int)FftK<T, M>::SMEM_BYTES));
     }
     template <int M> static void set_smem_attr() {
         set_pass_attr<M, RowsR2C<T, M>>();
-        set_pass_attr<M, ColsR2C<T, M>>();
-        set_pass_attr<M, ColsC2R<T, M>>();
+        set_pass_attr<M, ColsPass<T, M, false>>();
+        set_pass_attr<M, ColsPass<T, M, true>>();
         set_pass_attr<M, RowsC2R<T, M>>();
     }
 
@@ -85,9 +85,11 @@ template <typename T> struct FftAxis {
         SURFH_CUDA(cudaMemcpy(d_tw.p, h_tw.data(), ntw * sizeof(double2), cudaMemcpyHostToDevice));
         SURFH_CUDA(cudaMemcpy(d_b.p, h_b.data(), m * sizeof(double2), cudaMemcpyHostToDevice));
         SURFH_DISPATCH_M(m, {
-            const int bytes = (int)fft_smem_bytes<double, MM>();
+            const int bytes = (int)FftK<double, MM>::SMEM_BYTES_FILTER;
             SURFH_CUDA(cudaFuncSetAttribute(fft_filter_kernel<double, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            fft_filter_kernel<double, MM><<<1, FftK<double, MM>::NT, bytes>>>(d_b.as<double2>(), d_tw.as<double2>(), d_filt.as<double2>());
+            FftPlan1d<double> pd;
+            pd.chirp = nullptr; pd.filt = nullptr; pd.tw = d_tw.as<double2>(); pd.n = n;
+            fft_filter_kernel<double, MM><<<1, FftK<double, MM>::NT, bytes>>>(d_b.as<double2>(), pd, d_filt.as<double2>());
             set_smem_attr<MM>();
         });
         SURFH_CUDA(cudaGetLastError());
@@ -141,30 +143,30 @@ template <typename T> struct OwnFft2d {
 
     FftShape shape(size_t real_plane, size_t spec_plane, int batch) const {
         FftShape s;
-        s.na = na; s.nb = nb; s.nh = nh; s.npair = (na + 1) / 2; s.zpitch = nb;
+        s.na = na; s.nb = nb; s.nh = nh; s.npair = (na + 1) / 2;
         s.real_plane = real_plane; s.spec_plane = spec_plane; s.z_plane = z_plane(); s.batch = batch;
         return s;
     }
 
-    // persistent launch: one CTA per resident slot, each walking the items with a grid stride
-    template <int MM, typename Pass> void launch(const Pass& pass, long long n_items, const FftAxis<T>& ax, cudaStream_t st) const {
-        const long long slots = (long long)n_sm * FftK<T, MM>::MINB;
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min(n_items, slots));
-        fft_pass_kernel<T, MM, Pass><<<grid, FftK<T, MM>::NT, fft_pass_smem_bytes<T, MM, Pass>(), st>>>(pass, ax.plan());
+    // persistent launch: one CTA per SM, each walking the steps (G transforms at a time) with a grid stride
+    template <int MM, typename Pass> void launch(const Pass& pass, long long n_steps, const FftAxis<T>& ax, cudaStream_t st) const {
+        if (n_steps >= (1ll << 31)) throw Error(SURFH_EINVAL, "FFT batch too large");
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(n_steps, n_sm));
+        fft_pass_kernel<T, MM, Pass><<<grid, FftK<T, MM>::NT, FftK<T, MM>::SMEM_BYTES, st>>>(pass, ax.plan());
     }
 
     // in: real [batch] planes (stride real_plane) -> spec: [batch][na][nh] (stride spec_plane); z: scratch
     void r2c(const T* in, size_t real_plane, C* spec, size_t spec_plane, C* z, int batch, cudaStream_t st) const {
         const FftShape s = shape(real_plane, spec_plane, batch);
         SURFH_DISPATCH_M(axis_b->m, {
-            using Gm = typename FftK<T, MM>::Gm;
+            using K = FftK<T, MM>;
             RowsR2C<T, MM> pass{in, z, s};
-            launch<MM>(pass, ((long long)batch * s.npair + Gm::G - 1) / Gm::G, *axis_b, st);
+            launch<MM>(pass, ((long long)batch * s.npair + K::G - 1) / K::G, *axis_b, st);
         });
         SURFH_DISPATCH_M(axis_a.m, {
-            using Gm = typename FftK<T, MM>::Gm;
-            ColsR2C<T, MM> pass{z, spec, s};
-            launch<MM>(pass, (long long)batch * ((nh + Gm::G - 1) / Gm::G), axis_a, st);
+            using K = FftK<T, MM>;
+            ColsPass<T, MM, false> pass{z, spec, s};
+            launch<MM>(pass, (long long)batch * ((nh + K::G - 1) / K::G), axis_a, st);
         });
         SURFH_CUDA(cudaGetLastError());
     }
@@ -173,14 +175,14 @@ template <typename T> struct OwnFft2d {
     void c2r(const C* spec, size_t spec_plane, T* out, size_t real_plane, C* z, int batch, cudaStream_t st) const {
         const FftShape s = shape(real_plane, spec_plane, batch);
         SURFH_DISPATCH_M(axis_a.m, {
-            using Gm = typename FftK<T, MM>::Gm;
-            ColsC2R<T, MM> pass{spec, z, s};
-            launch<MM>(pass, (long long)batch * ((nh + Gm::G - 1) / Gm::G), axis_a, st);
+            using K = FftK<T, MM>;
+            ColsPass<T, MM, true> pass{spec, z, s};
+            launch<MM>(pass, (long long)batch * ((nh + K::G - 1) / K::G), axis_a, st);
         });
         SURFH_DISPATCH_M(axis_b->m, {
-            using Gm = typename FftK<T, MM>::Gm;
+            using K = FftK<T, MM>;
             RowsC2R<T, MM> pass{z, out, s};
-            launch<MM>(pass, ((long long)batch * s.npair + Gm::G - 1) / Gm::G, *axis_b, st);
+            launch<MM>(pass, ((long long)batch * s.npair + K::G - 1) / K::G, *axis_b, st);
         });
         SURFH_CUDA(cudaGetLastError());
     }

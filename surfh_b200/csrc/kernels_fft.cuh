@@ -15,59 +15,78 @@
 // precomputed, identically permuted spectrum of the chirp filter -> the mirrored inverse FFT
 // (decimation in time, natural order out) -> chirp multiply on store.  No bit-reversal pass exists.
 //
-// A CTA of 256 threads runs G = 4096/M transforms side by side; a transform is spread over
-// TT = M/16 threads that hold 16 points each.  Threads of different transforms are interleaved
-// lane-wise (transform = tid % G) so that the G adjacent columns of a column pass are read and
-// written as one contiguous segment per row.  Of the 4 register<->shared exchanges of one chirp-z
-// only 2 need a CTA barrier; the other 2 stay inside a group of R3 lanes of one warp.
+// Execution model: ONE persistent CTA per SM walks the work items with a grid stride.
+//   * All tables (twiddles, filter spectrum, chirp) live in shared memory for the CTA's lifetime, so
+//     every table read has shared-memory latency; the only global traffic is the data itself.
+//   * The inputs of item i+1 are copied global -> shared by cp.async into thread-private slots while
+//     item i is transformed: HBM latency is off the critical path at 12 warps per SM.
+//   * A transform is spread over TT = M/16 threads that hold 16 points each; a CTA runs G transforms
+//     side by side, split into two independent halves that synchronise with their own named barrier
+//     so that one half's shared-memory phases overlap the other half's FP64 phases.
+//   * Of the 4 register<->register exchanges of one chirp-z, 2 go through shared memory (one barrier
+//     each), 2 are transposes among R3 adjacent lanes done with warp shuffles.
 //
-// 2-D real transforms use the two-for-one trick: a pair of real rows is transformed as one complex
-// row; the pass along the other axis separates / re-assembles the two Hermitian spectra on load, so
-// no extra pass or exchange is spent on it.
-//   R2C:  rows_r2c  (real [Na][Nb] -> pair spectra Z [ceil(Na/2)][Nb])  ->  cols_r2c (-> spec [Na][Nh])
-//   C2R:  cols_c2r  (spec [Na][Nh] -> column-transformed [Na][Nh])      ->  rows_c2r (-> real [Na][Nb])
+// 2-D real transforms use the two-for-one trick: a pair of real rows is transformed as one complex row.
+//   R2C:  rows_r2c  real [Na][Nb] -> A/B-separated half spectra Y [Na][Nh]   (separation through the
+//                   transform's own shared buffer)            ->  cols  (-> spec [Na][Nh])
+//   C2R:  cols_c2r  spec [Na][Nh] -> Z [ceil(Na/2)][Nb], Z[p] = W[2p] + i W[2p+1] Hermitian-extended
+//                   (pairing through the shared buffer)       ->  rows_c2r (-> real [Na][Nb])
 #pragma once
 #include "common.cuh"
 
-#ifndef SURFH_FFT_SHFL
-#define SURFH_FFT_SHFL 1
-#endif
-
 namespace surfh {
 
-template <int M, int NT, int W> struct FftGeom {
+// Geometry of one chirp-z length M for arithmetic type T.
+template <typename T, int M> struct FftK {
     static_assert(M == 256 || M == 512 || M == 1024 || M == 2048, "chirp-z length must be 256..2048");
+    using C = cplx_t<T>;
     static constexpr int R3 = M / 256;          // last radix: 1, 2, 4, 8
     static constexpr int TT = M / 16;           // threads per transform
-    static_assert(NT % TT == 0 && NT >= TT, "CTA size must be a multiple of the threads per transform");
-    static constexpr int G = NT / TT;           // transforms per CTA
-    // length of one of the 16 sub-sequences in shared memory; the shared-memory flavour of the
-    // radix-R3 exchange needs a padded transposed staging area, the shuffled one does not
-    static constexpr bool SHFL = SURFH_FFT_SHFL && R3 * G <= 32;
-    static constexpr int TP = SHFL ? 16 * R3 : 16 * (R3 + 1);
-    // per-transform buffer; the tail pad staggers the G buffers over the shared-memory banks: a wavefront
-    // serves W lanes (8 complex doubles or 16 complex floats = 128 bytes), i.e. W/G consecutive t of G
-    // transforms, which must fall into W distinct element slots modulo W
-    static constexpr int PAD = G >= W ? 1 : (W / G) % W;
-    static constexpr int BUF = 16 * TP + PAD;
-    static constexpr int HALF = M / 2;          // the input / output length N must be <= HALF
+    // 16 complex doubles per thread need ~168 registers to stay out of local memory: 384 threads per SM
+    // in fp64 (256 for M = 2048, whose tables are twice as large); fp32 runs 512 threads at 128 registers
+    static constexpr int NT = sizeof(T) == 8 ? (M == 2048 ? 256 : 384) : 512;
+    static constexpr int NH = 2;                // independent halves of the CTA
+    static constexpr int HT = NT / NH;          // threads per half
+    static constexpr int G = NT / TT;           // transforms per CTA step
+    static constexpr int GH = G / NH;           // transforms per half
+    static_assert(GH * NH * TT == NT && HT % 32 == 0, "CTA shape");
+    // per-transform exchange buffer: M elements + a pad that staggers the buffers of the transforms whose
+    // lanes share a 128-byte wavefront (R3 consecutive t of 8/R3 or 16/R3 transforms)
+    static constexpr int BUF = M + R3;
+    static constexpr int N_TW = M + 16 * R3;    // tw1[q*TT + t] then tw2[q2*R3 + n2]
+    static constexpr int HALF = M / 2;          // the transform length N must be <= HALF
+    static constexpr int SLOTS = 8;             // staged complex-sized elements per thread
+    // shared-memory layout, in units of C
+    static constexpr int OFF_TW = 0;
+    static constexpr int OFF_FILT = OFF_TW + N_TW;
+    static constexpr int OFF_CHIRP = OFF_FILT + M;
+    static constexpr int OFF_BUF = OFF_CHIRP + HALF;
+    static constexpr int OFF_STAGE = OFF_BUF + G * BUF;
+    static constexpr int N_SMEM = OFF_STAGE + SLOTS * NT;
+    static constexpr size_t SMEM_BYTES = (size_t)N_SMEM * sizeof(C);
+    static constexpr size_t SMEM_BYTES_FILTER = (size_t)OFF_STAGE * sizeof(C);
 };
 
-// CTA shape per arithmetic type: 16 complex doubles per thread need ~160 registers to stay out of
-// local memory, so fp64 runs 3 CTAs of 128 threads per SM; fp32 fits 2 CTAs of 256 threads.
-template <typename T> struct FftCta;
-template <> struct FftCta<double> { static constexpr int NT = 128, MINB = 3; };
-template <> struct FftCta<float> { static constexpr int NT = 256, MINB = 2; };
-template <int M, int NT> constexpr int fft_cta_threads() { return NT < M / 16 ? M / 16 : NT; }
-template <typename T, int M> struct FftK {
-    static constexpr int NT = fft_cta_threads<M, FftCta<T>::NT>();
-    static constexpr int MINB = FftCta<T>::MINB;
-    using Gm = FftGeom<M, NT, 128 / (2 * (int)sizeof(T))>;
+// Who am I: transform g (of G), thread t (of TT) = q*R3 + n2.  The R3 threads that exchange registers
+// in the last radix stage are adjacent lanes; the GH transforms of a half are interleaved next, so that a
+// warp reads few distinct table entries (broadcast) and touches GH adjacent columns in a column pass.
+template <typename T, int M> struct FftThread {
+    using K = FftK<T, M>;
+    int half, g, t, q, n2;
+    __device__ __forceinline__ FftThread(int tid) {
+        half = tid / K::HT;
+        const int l = tid % K::HT;
+        n2 = l % K::R3;
+        const int c = l / K::R3;
+        g = half * K::GH + c % K::GH;
+        q = c / K::GH;
+        t = q * K::R3 + n2;
+    }
+    // barrier among the threads of this half only
+    __device__ __forceinline__ void sync() const {
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(K::HT) : "memory");
+    }
 };
-
-template <typename T, int M> __host__ __device__ constexpr size_t fft_smem_bytes() {
-    return ((size_t)FftK<T, M>::Gm::G * FftK<T, M>::Gm::BUF * sizeof(cplx_t<T>) + 15) / 16 * 16;
-}
 
 template <typename C> __device__ __forceinline__ C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
 template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
@@ -229,10 +248,9 @@ template <typename C> __device__ __forceinline__ C shfl_xor_c(C a, int lane_mask
     return a;
 }
 
-// In-register transpose among the R3 threads n2 = 0..R3-1 of one group (lane stride G): for every block
-// c of R3 registers, thread n2 ends up with v[c*R3 + n] = (thread n's v[c*R3 + n2]).  Self-inverse.
-// Replaces a shared-memory round trip (16 stores + 16 loads of 16 bytes) by 8 log2(R3) shuffled values.
-template <int R3, int G, typename C> __device__ __forceinline__ void group_transpose(C* v, int n2) {
+// In-register transpose among the R3 adjacent lanes n2 = 0..R3-1 of one group: for every block c of R3
+// registers, thread n2 ends up with v[c*R3 + n] = (thread n's v[c*R3 + n2]).  Self-inverse.
+template <int R3, typename C> __device__ __forceinline__ void group_transpose(C* v, int n2) {
 #pragma unroll
     for (int s = R3 / 2; s >= 1; s >>= 1) {
         const bool up = (n2 & s) != 0;
@@ -244,153 +262,133 @@ template <int R3, int G, typename C> __device__ __forceinline__ void group_trans
                 C& lo = v[c * R3 + j];
                 C& hi = v[c * R3 + (j | s)];
                 const C send = up ? lo : hi;
-                const C recv = shfl_xor_c(send, s * G);
+                const C recv = shfl_xor_c(send, s);
                 if (up) lo = recv; else hi = recv;
             }
     }
 }
 
-// Length-M forward FFT of the sequence held as v[m] = x[t + TT*m]; the result stays in registers in
-// a digit-reversed order that only fft_inv() (and the filter table built by the same code) needs to
-// know.  `buf` is this transform's shared buffer; every thread of the CTA must call.
-template <typename T, int M, bool HALF_IN = false>
-__device__ __forceinline__ void fft_fwd(cplx_t<T>* v, cplx_t<T>* buf, int t, const cplx_t<T>* __restrict__ tw) {
+// Length-M forward FFT of the sequence held as v[m] = x[t + TT*m]; the result stays in registers in a
+// digit-reversed order that only fft_inv() (and the filter table built by the same code) needs to know.
+// `buf` is this transform's shared buffer, `tw` the shared twiddle table.  PRE_SYNC: other threads may
+// still be reading this buffer from the previous step (the passes that post-process through it).
+template <typename T, int M, bool HALF_IN, bool PRE_SYNC>
+__device__ __forceinline__ void fft_fwd(cplx_t<T>* v, cplx_t<T>* buf, const FftThread<T, M>& th, const cplx_t<T>* tw) {
     using C = cplx_t<T>;
-    using Gm = typename FftK<T, M>::Gm;
-    constexpr int R3 = Gm::R3, TP = Gm::TP;
+    using K = FftK<T, M>;
+    constexpr int R3 = K::R3, TT = K::TT;
     if (HALF_IN) dft16_in8<false>(v);  // v[8..15] are the zero padding
     else dft16<false>(v);
+    if (PRE_SYNC) th.sync();
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         C x = v[q];
-        if (q) x = cmul(x, __ldg(tw + q * Gm::TT + t));
-        buf[q * TP + t] = x;
+        if (q) x = cmul(x, tw[q * TT + th.t]);
+        buf[q * TT + th.t] = x;
     }
-    __syncthreads();
-    const int q = t / R3, n2 = t % R3;
-    C* blk = buf + q * TP;
+    th.sync();
+    C* blk = buf + th.q * TT;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) v[m] = blk[n2 + R3 * m];
+    for (int m = 0; m < 16; ++m) v[m] = blk[th.n2 + R3 * m];
     dft16<false>(v);
     if (R3 > 1) {
-        if (Gm::SHFL) {
 #pragma unroll
-            for (int q2 = 1; q2 < 16; ++q2) v[q2] = cmul(v[q2], __ldg(tw + M + q2 * R3 + n2));
-            group_transpose<R3, Gm::G>(v, n2);
+        for (int q2 = 1; q2 < 16; ++q2) v[q2] = cmul(v[q2], tw[M + q2 * R3 + th.n2]);
+        group_transpose<R3>(v, th.n2);
 #pragma unroll
-            for (int c = 0; c < 16 / R3; ++c) dft_r<false, R3>(v + c * R3);
-        } else {
-            __syncwarp();
-#pragma unroll
-            for (int q2 = 0; q2 < 16; ++q2) {
-                C x = v[q2];
-                if (q2) x = cmul(x, __ldg(tw + M + q2 * R3 + n2));
-                blk[(q2 / R3) * (R3 * (R3 + 1)) + n2 * (R3 + 1) + (q2 % R3)] = x;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < 16 / R3; ++c) {
-#pragma unroll
-                for (int n = 0; n < R3; ++n) v[c * R3 + n] = blk[c * (R3 * (R3 + 1)) + n * (R3 + 1) + n2];
-                dft_r<false, R3>(v + c * R3);
-            }
-        }
+        for (int c = 0; c < 16 / R3; ++c) dft_r<false, R3>(v + c * R3);
     }
 }
 
 // Mirror of fft_fwd: takes the digit-reversed spectrum in registers, returns M * x[t + TT*m] in v[m].
-template <typename T, int M, bool HALF_OUT = false>
-__device__ __forceinline__ void fft_inv(cplx_t<T>* v, cplx_t<T>* buf, int t, const cplx_t<T>* __restrict__ tw) {
+template <typename T, int M, bool HALF_OUT>
+__device__ __forceinline__ void fft_inv(cplx_t<T>* v, cplx_t<T>* buf, const FftThread<T, M>& th, const cplx_t<T>* tw) {
     using C = cplx_t<T>;
-    using Gm = typename FftK<T, M>::Gm;
-    constexpr int R3 = Gm::R3, TP = Gm::TP;
-    const int q = t / R3, n2 = t % R3;
-    C* blk = buf + q * TP;
+    using K = FftK<T, M>;
+    constexpr int R3 = K::R3, TT = K::TT;
     if (R3 > 1) {
-        if (Gm::SHFL) {
 #pragma unroll
-            for (int c = 0; c < 16 / R3; ++c) dft_r<true, R3>(v + c * R3);
-            group_transpose<R3, Gm::G>(v, n2);
+        for (int c = 0; c < 16 / R3; ++c) dft_r<true, R3>(v + c * R3);
+        group_transpose<R3>(v, th.n2);
 #pragma unroll
-            for (int q2 = 1; q2 < 16; ++q2) v[q2] = cmul_conj(__ldg(tw + M + q2 * R3 + n2), v[q2]);
-        } else {
-            __syncwarp();  // the group's last reads of blk in fft_fwd precede these writes
-#pragma unroll
-            for (int c = 0; c < 16 / R3; ++c) {
-                dft_r<true, R3>(v + c * R3);
-#pragma unroll
-                for (int n = 0; n < R3; ++n) blk[c * (R3 * (R3 + 1)) + n * (R3 + 1) + n2] = v[c * R3 + n];
-            }
-            __syncwarp();
-#pragma unroll
-            for (int q2 = 0; q2 < 16; ++q2) {
-                C x = blk[(q2 / R3) * (R3 * (R3 + 1)) + n2 * (R3 + 1) + (q2 % R3)];
-                if (q2) x = cmul_conj(__ldg(tw + M + q2 * R3 + n2), x);
-                v[q2] = x;
-            }
-        }
+        for (int q2 = 1; q2 < 16; ++q2) v[q2] = cmul_conj(tw[M + q2 * R3 + th.n2], v[q2]);
     }
     dft16<true>(v);
-    __syncwarp();
+    // these are the very locations this thread read in fft_fwd: no barrier needed before the writes
+    C* blk = buf + th.q * TT;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) blk[n2 + R3 * m] = v[m];
-    __syncthreads();
+    for (int m = 0; m < 16; ++m) blk[th.n2 + R3 * m] = v[m];
+    th.sync();
 #pragma unroll
     for (int qq = 0; qq < 16; ++qq) {
-        C x = buf[qq * TP + t];
-        if (qq) x = cmul_conj(__ldg(tw + qq * Gm::TT + t), x);
+        C x = buf[qq * TT + th.t];
+        if (qq) x = cmul_conj(tw[qq * TT + th.t], x);
         v[qq] = x;
     }
     if (HALF_OUT) dft16_out8<true>(v);  // only x[t + TT*m], m < 8, is wanted
     else dft16<true>(v);
 }
 
-// Device tables of one 1-D chirp-z plan (length N through M-point FFTs).
+// Device tables of one 1-D chirp-z plan (length n through M-point FFTs), in global memory; the kernels
+// copy them to shared memory once per CTA.
 template <typename T> struct FftPlan1d {
-    const cplx_t<T>* chirp;  // [N]   a[n] = exp(-i pi n^2 / N)
+    const cplx_t<T>* chirp;  // [n]   a[j] = exp(-i pi j^2 / n)
     const cplx_t<T>* filt;   // [M]   FFT_M(conj(a) wrapped) / M, in fft_fwd's register order [j*TT + t]
-    const cplx_t<T>* tw;     // [M + 16*R3] twiddles laid out for coalesced reads:
-                             //   tw[q*TT + t] = exp(-2 pi i t q / M), then tw[M + q2*R3 + n2] = exp(-2 pi i n2 q2 / TT)
+    const cplx_t<T>* tw;     // [M + 16*R3]  tw[q*TT + t] = exp(-2 pi i t q / M), then
+                             //              tw[M + q2*R3 + n2] = exp(-2 pi i n2 q2 / TT)
     int n;
 };
 
+template <typename T, int M>
+__device__ __forceinline__ void fft_load_tables(cplx_t<T>* smem, const FftPlan1d<T>& p, bool with_filter) {
+    using K = FftK<T, M>;
+    for (int i = threadIdx.x; i < K::N_TW; i += blockDim.x) smem[K::OFF_TW + i] = p.tw[i];
+    if (with_filter) {
+        for (int i = threadIdx.x; i < M; i += blockDim.x) smem[K::OFF_FILT + i] = p.filt[i];
+        for (int i = threadIdx.x; i < p.n; i += blockDim.x) smem[K::OFF_CHIRP + i] = p.chirp[i];
+    }
+    __syncthreads();
+}
+
 // Circular convolution with the chirp filter: v[m] = (u * conj(a))[t + TT*m] for m < 8, with u given
 // the same way and u[t + TT*m] = 0 for m >= 8 (v[8..15] are ignored on entry, garbage on exit).
-template <typename T, int M>
-__device__ __forceinline__ void chirp_convolve(cplx_t<T>* v, cplx_t<T>* buf, int t, const FftPlan1d<T>& p) {
-    constexpr int TT = FftK<T, M>::Gm::TT;
-    fft_fwd<T, M, true>(v, buf, t, p.tw);
+template <typename T, int M, bool PRE_SYNC>
+__device__ __forceinline__ void chirp_convolve(cplx_t<T>* v, cplx_t<T>* smem, cplx_t<T>* buf, const FftThread<T, M>& th) {
+    using K = FftK<T, M>;
+    fft_fwd<T, M, true, PRE_SYNC>(v, buf, th, smem + K::OFF_TW);
+    const cplx_t<T>* filt = smem + K::OFF_FILT;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = cmul(v[j], __ldg(p.filt + j * TT + t));
-    fft_inv<T, M, true>(v, buf, t, p.tw);
+    for (int j = 0; j < 16; ++j) v[j] = cmul(v[j], filt[j * K::TT + th.t]);
+    fft_inv<T, M, true>(v, buf, th, smem + K::OFF_TW);
 }
 
 // Builds FftPlan1d::filt from the natural-order filter `b` (already scaled by 1/M) with the very code
 // that consumes it, so the digit-reversed order never has to be spelled out.  One CTA.
 template <typename T, int M>
-__global__ void __launch_bounds__(FftK<T, M>::NT)
-fft_filter_kernel(const cplx_t<T>* __restrict__ b, const cplx_t<T>* __restrict__ tw, cplx_t<T>* __restrict__ filt) {
+__global__ void __launch_bounds__(FftK<T, M>::NT, 1)
+fft_filter_kernel(const cplx_t<T>* __restrict__ b, FftPlan1d<T> p, cplx_t<T>* __restrict__ filt) {
     using C = cplx_t<T>;
-    using Gm = typename FftK<T, M>::Gm;
+    using K = FftK<T, M>;
     extern __shared__ __align__(16) unsigned char fft_smem[];
-    const int g = threadIdx.x % Gm::G, t = threadIdx.x / Gm::G;
-    C* buf = reinterpret_cast<C*>(fft_smem) + g * Gm::BUF;
+    C* smem = reinterpret_cast<C*>(fft_smem);
+    fft_load_tables<T, M>(smem, p, false);
+    const FftThread<T, M> th(threadIdx.x);
+    C* buf = smem + K::OFF_BUF + th.g * K::BUF;
     C v[16];
 #pragma unroll
-    for (int m = 0; m < 16; ++m) v[m] = b[t + Gm::TT * m];
-    fft_fwd<T, M>(v, buf, t, tw);
-    if (g == 0)
+    for (int m = 0; m < 16; ++m) v[m] = b[th.t + K::TT * m];
+    fft_fwd<T, M, false, false>(v, buf, th, smem + K::OFF_TW);
+    if (th.g == 0)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) filt[j * Gm::TT + t] = v[j];
+        for (int j = 0; j < 16; ++j) filt[j * K::TT + th.t] = v[j];
 }
 
 struct FftShape {
     int na, nb, nh;          // rows, columns, nb/2+1
     int npair;               // ceil(na / 2)
-    int zpitch;              // row pitch (complex) of the pair-spectrum buffer Z, >= nb
     size_t real_plane;       // elements between real planes
     size_t spec_plane;       // complex elements between spectrum planes ([na][nh], row pitch nh)
-    size_t z_plane;          // complex elements between planes of Z / of the column-transformed buffer
+    size_t z_plane;          // complex elements between planes of the intermediate buffer
     int batch;
 };
 
@@ -405,249 +403,223 @@ template <int BYTES> __device__ __forceinline__ void cp_async(void* smem_dst, co
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Decomposition of a work item into (plane, index within the plane) for the two kinds of pass.
+// A work item of a CTA step, seen from one thread: which plane and which row pair / column.
 struct FftItem {
     bool live;
     int plane, idx;
 };
 
-// ---- R2C pass 1: pairs of real rows -> full complex spectrum of (row_even + i row_odd)
+// ---- R2C pass 1: pairs of real rows -> the two Hermitian half spectra, rows 2p and 2p+1 of Y [Na][Nh]
 template <typename T, int M> struct RowsR2C {
     using C = cplx_t<T>;
-    using Gm = typename FftK<T, M>::Gm;
-    using Elem = T;                       // staged element
-    static constexpr int SLOTS = 16;      // staged elements per thread: 8 points x 2 rows
+    using K = FftK<T, M>;
+    static constexpr bool POST = true;    // post-processes through the shared buffer
     const T* in;
-    C* z;
+    C* y;
     FftShape s;
-    __device__ long long items() const { return ((long long)s.batch * s.npair + Gm::G - 1) / Gm::G; }  // < 2^31 (checked on the host)
-    __device__ FftItem item(long long blk, int g) const {
-        const long long it = blk * Gm::G + g;
+    __device__ int steps() const { return (int)(((long long)s.batch * s.npair + K::G - 1) / K::G); }
+    __device__ FftItem item(int step, int g) const {
+        const long long it = (long long)step * K::G + g;
         FftItem r;
         r.live = it < (long long)s.batch * s.npair;
         r.plane = r.live ? (int)(it / s.npair) : 0;
         r.idx = r.live ? (int)(it % s.npair) : 0;
         return r;
     }
-    __device__ void prefetch(const FftItem& it, int t, Elem* stage, int nt, int tid) const {
+    // staged: 16 reals per thread = 8 complex-sized slots; slot (m, k) at stage[(2m + k) * NT + tid] in reals
+    __device__ void prefetch(const FftItem& it, int t, C* stage_c, int tid) const {
         if (!it.live) return;
+        T* stage = reinterpret_cast<T*>(stage_c);
         const int r0 = 2 * it.idx;
         const T* ra = in + (size_t)it.plane * s.real_plane + (size_t)r0 * s.nb;
         const bool has_b = r0 + 1 < s.na;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int n = t + Gm::TT * m;
+            const int n = t + K::TT * m;
             if (n < s.nb) {
-                cp_async<sizeof(T)>(stage + (2 * m) * nt + tid, ra + n);
-                if (has_b) cp_async<sizeof(T)>(stage + (2 * m + 1) * nt + tid, ra + s.nb + n);
+                cp_async<sizeof(T)>(stage + (2 * m) * K::NT + tid, ra + n);
+                if (has_b) cp_async<sizeof(T)>(stage + (2 * m + 1) * K::NT + tid, ra + s.nb + n);
             }
         }
     }
-    __device__ void load(const FftItem& it, int t, const Elem* stage, int nt, int tid, C* v, const C* chirp) const {
+    __device__ void load(const FftItem& it, int t, const C* stage_c, int tid, C* v, const C* chirp) const {
+        const T* stage = reinterpret_cast<const T*>(stage_c);
         const bool has_b = 2 * it.idx + 1 < s.na;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int n = t + Gm::TT * m;
+            const int n = t + K::TT * m;
             C u = make_c<T>(T(0), T(0));
             if (it.live && n < s.nb) {
-                u.x = stage[(2 * m) * nt + tid];
-                u.y = has_b ? stage[(2 * m + 1) * nt + tid] : T(0);
-                u = cmul(u, __ldg(chirp + n));
+                u.x = stage[(2 * m) * K::NT + tid];
+                u.y = has_b ? stage[(2 * m + 1) * K::NT + tid] : T(0);
+                u = cmul(u, chirp[n]);
             }
             v[m] = u;
         }
     }
-    __device__ void store(const FftItem& it, int t, const C* v, const C* chirp) const {
-        if (!it.live) return;
-        C* dst = z + (size_t)it.plane * s.z_plane + (size_t)it.idx * s.zpitch;
+    // Z[n] = FFT(row_even + i row_odd)[n] is written to the transform's buffer in natural order (these
+    // are the thread's own final-stage locations), then every thread separates A[j] = (Z[j] + conj
+    // Z[nb-j]) / 2 and B[j] = (Z[j] - conj Z[nb-j]) / 2i for its share of j < nh.
+    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C* buf, const C* chirp) const {
+        const int t = th.t;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int n = t + Gm::TT * m;
-            if (n < s.nb) dst[n] = cmul(v[m], __ldg(chirp + n));
+            const int n = t + K::TT * m;
+            if (n < s.nb) buf[n] = cmul(v[m], chirp[n]);
+        }
+        th.sync();
+        if (!it.live) return;
+        const bool has_b = 2 * it.idx + 1 < s.na;
+        C* ya = y + (size_t)it.plane * s.z_plane + (size_t)(2 * it.idx) * s.nh;
+#pragma unroll
+        for (int m = 0; m < 5; ++m) {
+            const int j = t + K::TT * m;
+            if (j < s.nh) {
+                const C a = buf[j], b = buf[j == 0 ? 0 : s.nb - j];
+                ya[j] = make_c<T>(T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y));
+                if (has_b) ya[s.nh + j] = make_c<T>(T(0.5) * (a.y + b.y), T(0.5) * (b.x - a.x));
+            }
         }
     }
 };
 
-// ---- R2C pass 2: column transforms; the two Hermitian row spectra are separated on load
-template <typename T, int M> struct ColsR2C {
+// ---- column transforms of a half-complex plane, forward (R2C pass 2) or inverse (C2R pass 1)
+// INVERSE = false:  Y [Na][Nh] -> spec [Na][Nh]
+// INVERSE = true:   spec [Na][Nh] -> Z [npair][Nb], Z[p][j] = W[2p][j] + i W[2p+1][j] and its Hermitian
+//                   extension Z[p][nb-j] = conj(W[2p][j]) + i conj(W[2p+1][j]), W = inverse column
+//                   transform (conj in, conj out around the forward chirp-z)
+template <typename T, int M, bool INVERSE> struct ColsPass {
     using C = cplx_t<T>;
-    using Gm = typename FftK<T, M>::Gm;
-    using Elem = C;
-    static constexpr int SLOTS = 16;      // 8 points x (Z[j], Z[nb - j])
-    const C* z;
-    C* spec;
+    using K = FftK<T, M>;
+    static constexpr bool POST = INVERSE;
+    const C* src;
+    C* dst;
     FftShape s;
-    __device__ int tiles() const { return (s.nh + Gm::G - 1) / Gm::G; }
-    __device__ long long items() const { return (long long)s.batch * tiles(); }
-    __device__ FftItem item(long long blk, int g) const {
+    __device__ int tiles() const { return (s.nh + K::G - 1) / K::G; }
+    __device__ int steps() const { return s.batch * tiles(); }
+    __device__ FftItem item(int step, int g) const {
         const int tl = tiles();
         FftItem r;
-        r.plane = (int)(blk / tl);
-        r.idx = (int)(blk % tl) * Gm::G + g;
+        r.plane = step / tl;
+        r.idx = (step % tl) * K::G + g;
         r.live = r.idx < s.nh;
         return r;
     }
-    __device__ void prefetch(const FftItem& it, int t, Elem* stage, int nt, int tid) const {
+    __device__ size_t src_plane() const { return INVERSE ? s.spec_plane : s.z_plane; }
+    __device__ void prefetch(const FftItem& it, int t, C* stage, int tid) const {
         if (!it.live) return;
-        const int j = it.idx, jm = j == 0 ? 0 : s.nb - j;
-        const C* zp = z + (size_t)it.plane * s.z_plane;
+        const C* col = src + (size_t)it.plane * src_plane() + it.idx;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int i = t + Gm::TT * m;
-            if (i < s.na) {
-                const C* row = zp + (size_t)(i >> 1) * s.zpitch;
-                cp_async<sizeof(C)>(stage + (2 * m) * nt + tid, row + j);
-                cp_async<sizeof(C)>(stage + (2 * m + 1) * nt + tid, row + jm);
-            }
+            const int i = t + K::TT * m;
+            if (i < s.na) cp_async<sizeof(C)>(stage + m * K::NT + tid, col + (size_t)i * s.nh);
         }
     }
-    __device__ void load(const FftItem& it, int t, const Elem* stage, int nt, int tid, C* v, const C* chirp) const {
+    __device__ void load(const FftItem& it, int t, const C* stage, int tid, C* v, const C* chirp) const {
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int i = t + Gm::TT * m;
+            const int i = t + K::TT * m;
             C u = make_c<T>(T(0), T(0));
             if (it.live && i < s.na) {
-                const C a = stage[(2 * m) * nt + tid], b = stage[(2 * m + 1) * nt + tid];
-                if (i & 1) { u.x = T(0.5) * (a.y + b.y); u.y = T(0.5) * (b.x - a.x); }
-                else { u.x = T(0.5) * (a.x + b.x); u.y = T(0.5) * (a.y - b.y); }
-                u = cmul(u, __ldg(chirp + i));
+                u = stage[m * K::NT + tid];
+                if (INVERSE) u.y = -u.y;
+                u = cmul(u, chirp[i]);
             }
             v[m] = u;
         }
     }
-    __device__ void store(const FftItem& it, int t, const C* v, const C* chirp) const {
-        if (!it.live) return;
-        C* dst = spec + (size_t)it.plane * s.spec_plane + it.idx;
+    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C* buf, const C* chirp) const {
+        const int t = th.t;
+        if (!INVERSE) {
+            if (!it.live) return;
+            C* col = dst + (size_t)it.plane * s.spec_plane + it.idx;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int i = t + Gm::TT * m;
-            if (i < s.na) dst[(size_t)i * s.nh] = cmul(v[m], __ldg(chirp + i));
-        }
-    }
-};
-
-// ---- C2R pass 1: inverse column transforms (conj in, conj out around the forward chirp-z)
-template <typename T, int M> struct ColsC2R {
-    using C = cplx_t<T>;
-    using Gm = typename FftK<T, M>::Gm;
-    using Elem = C;
-    static constexpr int SLOTS = 8;
-    const C* spec;
-    C* w;
-    FftShape s;
-    __device__ int tiles() const { return (s.nh + Gm::G - 1) / Gm::G; }
-    __device__ long long items() const { return (long long)s.batch * tiles(); }
-    __device__ FftItem item(long long blk, int g) const {
-        const int tl = tiles();
-        FftItem r;
-        r.plane = (int)(blk / tl);
-        r.idx = (int)(blk % tl) * Gm::G + g;
-        r.live = r.idx < s.nh;
-        return r;
-    }
-    __device__ void prefetch(const FftItem& it, int t, Elem* stage, int nt, int tid) const {
-        if (!it.live) return;
-        const C* src = spec + (size_t)it.plane * s.spec_plane + it.idx;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int i = t + Gm::TT * m;
-            if (i < s.na) cp_async<sizeof(C)>(stage + m * nt + tid, src + (size_t)i * s.nh);
-        }
-    }
-    __device__ void load(const FftItem& it, int t, const Elem* stage, int nt, int tid, C* v, const C* chirp) const {
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int i = t + Gm::TT * m;
-            C u = make_c<T>(T(0), T(0));
-            if (it.live && i < s.na) {
-                u = stage[m * nt + tid];
-                u.y = -u.y;
-                u = cmul(u, __ldg(chirp + i));
+            for (int m = 0; m < 8; ++m) {
+                const int i = t + K::TT * m;
+                if (i < s.na) col[(size_t)i * s.nh] = cmul(v[m], chirp[i]);
             }
-            v[m] = u;
+            return;
         }
-    }
-    __device__ void store(const FftItem& it, int t, const C* v, const C* chirp) const {
-        if (!it.live) return;
-        C* dst = w + (size_t)it.plane * s.z_plane + it.idx;
+        const int j = it.idx;
+        const int nyq = (s.nb & 1) ? -1 : s.nb / 2;
+        const bool self_mirror = j == 0 || j == nyq;  // numpy's irfft ignores the imaginary part there
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int i = t + Gm::TT * m;
+            const int i = t + K::TT * m;
             if (i < s.na) {
-                C r = cmul(v[m], __ldg(chirp + i));
-                r.y = -r.y;
-                dst[(size_t)i * s.nh] = r;
+                C r = cmul(v[m], chirp[i]);
+                r.y = self_mirror ? T(0) : -r.y;
+                buf[i] = r;
+            }
+        }
+        th.sync();
+        if (!it.live) return;
+        C* zp = dst + (size_t)it.plane * s.z_plane;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int p = t + K::TT * m;
+            if (p < s.npair) {
+                const C a = buf[2 * p];
+                const C b = 2 * p + 1 < s.na ? buf[2 * p + 1] : make_c<T>(T(0), T(0));
+                C* row = zp + (size_t)p * s.nb;
+                row[j] = make_c<T>(a.x - b.y, a.y + b.x);
+                if (!self_mirror) row[s.nb - j] = make_c<T>(a.x + b.y, b.x - a.y);
             }
         }
     }
 };
 
-// ---- C2R pass 2: pairs of Hermitian half-rows -> pairs of real rows
+// ---- C2R pass 2: Z [npair][Nb] -> pairs of real rows
 template <typename T, int M> struct RowsC2R {
     using C = cplx_t<T>;
-    using Gm = typename FftK<T, M>::Gm;
-    using Elem = C;
-    static constexpr int SLOTS = 16;      // 8 points x 2 rows
-    const C* w;
+    using K = FftK<T, M>;
+    static constexpr bool POST = false;
+    const C* z;
     T* out;
     FftShape s;
-    __device__ long long items() const { return ((long long)s.batch * s.npair + Gm::G - 1) / Gm::G; }  // < 2^31 (checked on the host)
-    __device__ FftItem item(long long blk, int g) const {
-        const long long it = blk * Gm::G + g;
+    __device__ int steps() const { return (int)(((long long)s.batch * s.npair + K::G - 1) / K::G); }
+    __device__ FftItem item(int step, int g) const {
+        const long long it = (long long)step * K::G + g;
         FftItem r;
         r.live = it < (long long)s.batch * s.npair;
         r.plane = r.live ? (int)(it / s.npair) : 0;
         r.idx = r.live ? (int)(it % s.npair) : 0;
         return r;
     }
-    __device__ void prefetch(const FftItem& it, int t, Elem* stage, int nt, int tid) const {
+    __device__ void prefetch(const FftItem& it, int t, C* stage, int tid) const {
         if (!it.live) return;
-        const int r0 = 2 * it.idx;
-        const bool has_b = r0 + 1 < s.na;
-        const C* wa = w + (size_t)it.plane * s.z_plane + (size_t)r0 * s.nh;
+        const C* row = z + (size_t)it.plane * s.z_plane + (size_t)it.idx * s.nb;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int n = t + Gm::TT * m;
-            if (n < s.nb) {
-                const int k = n >= s.nh ? s.nb - n : n;
-                cp_async<sizeof(C)>(stage + (2 * m) * nt + tid, wa + k);
-                if (has_b) cp_async<sizeof(C)>(stage + (2 * m + 1) * nt + tid, wa + s.nh + k);
-            }
+            const int n = t + K::TT * m;
+            if (n < s.nb) cp_async<sizeof(C)>(stage + m * K::NT + tid, row + n);
         }
     }
-    __device__ void load(const FftItem& it, int t, const Elem* stage, int nt, int tid, C* v, const C* chirp) const {
-        const bool has_b = 2 * it.idx + 1 < s.na;
-        const int nyq = (s.nb & 1) ? -1 : s.nb / 2;
+    // IFFT(z) = conj(FFT(conj z)) = row_even + i row_odd
+    __device__ void load(const FftItem& it, int t, const C* stage, int tid, C* v, const C* chirp) const {
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int n = t + Gm::TT * m;
+            const int n = t + K::TT * m;
             C u = make_c<T>(T(0), T(0));
             if (it.live && n < s.nb) {
-                // z[n] = A[n] + i B[n] with A, B extended by Hermitian symmetry; conj(z) feeds the forward chirp-z
-                const bool mir = n >= s.nh;
-                const int k = mir ? s.nb - n : n;
-                C a = stage[(2 * m) * nt + tid];
-                C b = has_b ? stage[(2 * m + 1) * nt + tid] : make_c<T>(T(0), T(0));
-                if (k == 0 || k == nyq) { a.y = T(0); b.y = T(0); }
-                if (mir) { a.y = -a.y; b.y = -b.y; }
-                u.x = a.x - b.y;
-                u.y = -(a.y + b.x);
-                u = cmul(u, __ldg(chirp + n));
+                u = stage[m * K::NT + tid];
+                u.y = -u.y;
+                u = cmul(u, chirp[n]);
             }
             v[m] = u;
         }
     }
-    __device__ void store(const FftItem& it, int t, const C* v, const C* chirp) const {
+    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C*, const C* chirp) const {
         if (!it.live) return;
-        const int r0 = 2 * it.idx;
+        const int t = th.t, r0 = 2 * it.idx;
         const bool has_b = r0 + 1 < s.na;
         T* oa = out + (size_t)it.plane * s.real_plane + (size_t)r0 * s.nb;
         T* ob = oa + s.nb;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const int n = t + Gm::TT * m;
+            const int n = t + K::TT * m;
             if (n < s.nb) {
-                const C r = cmul(v[m], __ldg(chirp + n));
+                const C r = cmul(v[m], chirp[n]);
                 oa[n] = r.x;
                 if (has_b) ob[n] = -r.y;
             }
@@ -655,37 +627,32 @@ template <typename T, int M> struct RowsC2R {
     }
 };
 
-template <typename T, int M, typename Pass> __host__ __device__ constexpr size_t fft_pass_smem_bytes() {
-    return fft_smem_bytes<T, M>() + (size_t)Pass::SLOTS * FftK<T, M>::NT * sizeof(typename Pass::Elem);
-}
-
-// Persistent kernel shared by the four passes: a CTA walks the work items with a grid stride; the inputs
-// of item i+1 are in flight (cp.async into thread-private slots) while item i is transformed, which is
-// what hides the HBM latency at 12 warps per SM.
+// Persistent kernel shared by the four passes.
 template <typename T, int M, typename Pass>
-__global__ void __launch_bounds__(FftK<T, M>::NT, FftK<T, M>::MINB) fft_pass_kernel(Pass pass, FftPlan1d<T> p) {
+__global__ void __launch_bounds__(FftK<T, M>::NT, 1) fft_pass_kernel(Pass pass, FftPlan1d<T> p) {
     using C = cplx_t<T>;
-    using Gm = typename FftK<T, M>::Gm;
-    using Elem = typename Pass::Elem;
-    constexpr int NT = FftK<T, M>::NT;
+    using K = FftK<T, M>;
     extern __shared__ __align__(16) unsigned char fft_smem[];
-    const int tid = threadIdx.x, g = tid % Gm::G, t = tid / Gm::G;
-    C* buf = reinterpret_cast<C*>(fft_smem) + g * Gm::BUF;
-    Elem* stage = reinterpret_cast<Elem*>(fft_smem + fft_smem_bytes<T, M>());
-    const int n_items = (int)pass.items();
-    int blk = blockIdx.x;
-    if (blk >= n_items) return;
-    pass.prefetch(pass.item(blk, g), t, stage, NT, tid);
+    C* smem = reinterpret_cast<C*>(fft_smem);
+    const int tid = threadIdx.x;
+    const FftThread<T, M> th(tid);
+    C* buf = smem + K::OFF_BUF + th.g * K::BUF;
+    C* stage = smem + K::OFF_STAGE;
+    const C* chirp = smem + K::OFF_CHIRP;
+    const int n_steps = pass.steps();
+    int step = blockIdx.x;
+    if (step < n_steps) pass.prefetch(pass.item(step, th.g), th.t, stage, tid);
     cp_async_commit();
-    for (; blk < n_items; blk += gridDim.x) {
+    fft_load_tables<T, M>(smem, p, true);
+    for (; step < n_steps; step += gridDim.x) {
         C v[16];
-        const FftItem cur = pass.item(blk, g);
+        const FftItem cur = pass.item(step, th.g);
         cp_async_wait_all();
-        pass.load(cur, t, stage, NT, tid, v, p.chirp);
-        if (blk + (int)gridDim.x < n_items) pass.prefetch(pass.item(blk + gridDim.x, g), t, stage, NT, tid);
+        pass.load(cur, th.t, stage, tid, v, chirp);
+        if (step + (int)gridDim.x < n_steps) pass.prefetch(pass.item(step + gridDim.x, th.g), th.t, stage, tid);
         cp_async_commit();
-        chirp_convolve<T, M>(v, buf, t, p);
-        pass.store(pass.item(blk, g), t, v, p.chirp);
+        chirp_convolve<T, M, Pass::POST>(v, smem, buf, th);
+        pass.finish(pass.item(step, th.g), th, v, buf, chirp);
     }
 }
 
