@@ -105,6 +105,7 @@ namespace surfh {
 
 template <typename T> struct BandT {
     int P, S, na, nb, srf, A, B, l0, nl, nd, ncol, Nn, KB, mode, det_start;
+    int row_lo = 0, row_hi = 0;  // cube rows this band reads (gather) or writes (either adjoint table)
     int64_t out_offset, out_size;
     DevBuf slit_a0, slit_b0, slit_w, lsf, grid_base, grid_frac;
     DevBuf csr_pix[2], csr_ptr[2], csr_col[2], csr_val[2];
@@ -162,8 +163,11 @@ template <typename T> struct ModelImpl : surfh_model {
     DevBuf fft_work;
     DevBuf zbuf;      // [max(chunk, K)][z_plane] complex: intermediate of the hand-written FFT passes
     OwnFft2d<T> ownfft;
+    DevBuf plane_pairs;                   // [Nl] int2 (first row pair, count) each plane's FFT must cover
+    std::vector<int> plane_pair_cnt;      // host copy of the counts
     int fft_backend = SURFH_FFT_AUTO;
     bool use_own_fft = false;
+    bool prune_rows = true;  // SURFH_FFT_PRUNE=0 transforms every row (A/B measurements)
     DevBuf y_internal, x_stage, y_stage, dbl_stage;
     DevBuf cg_partial, cg_ticket;
     std::vector<std::unique_ptr<BandT<T>>> bands;
@@ -196,6 +200,7 @@ template <typename T> struct ModelImpl : surfh_model {
                       "unknown fft_backend");
         SURFH_REQUIRE(fft_backend != SURFH_FFT_OWN || OwnFft2d<T>::supported(Na, Nb),
                       "fft_backend = own needs both map axes <= 1024 pixels");
+        if (const char* e = std::getenv("SURFH_FFT_PRUNE")) prune_rows = std::strcmp(e, "0") != 0;
         use_own_fft = fft_backend == SURFH_FFT_OWN || (fft_backend == SURFH_FFT_AUTO && OwnFft2d<T>::supported(Na, Nb));
         otf.alloc((size_t)Nl * nfp * sizeof(C));
         SURFH_CUDA(cudaMemset(otf.p, 0, otf.bytes));
@@ -288,6 +293,19 @@ template <typename T> struct ModelImpl : surfh_model {
         }
         check_csr(d->adj_exact, (int64_t)plane, b->ncol, "adj_exact");
         check_csr(d->adj_reference, (int64_t)plane, b->ncol, "adj_reference");
+        // hull of the cube rows the band touches: the FFT passes skip every row pair outside it
+        b->row_lo = Na - 1;
+        b->row_hi = 0;
+        for (int64_t q = 0; q < (int64_t)b->P * AB; ++q) {
+            const int i = d->grid_base[q] / Nb;
+            b->row_lo = std::min(b->row_lo, i);
+            b->row_hi = std::max(b->row_hi, i + 1);
+        }
+        for (const surfh_csr* c : {&d->adj_exact, &d->adj_reference})
+            if (c->n_rows > 0) {
+                b->row_lo = std::min(b->row_lo, c->row_pixel[0] / Nb);
+                b->row_hi = std::max(b->row_hi, c->row_pixel[c->n_rows - 1] / Nb);
+            }
 
         upload_converted<int32_t>(b->slit_a0, d->slit_a0, b->S);
         upload_converted<int32_t>(b->slit_b0, d->slit_b0, b->S);
@@ -380,6 +398,7 @@ template <typename T> struct ModelImpl : surfh_model {
             const size_t per_l = nfp * sizeof(C) + plane * sizeof(T);
             chunk = (int)std::max<size_t>(1, std::min<size_t>(512, ((size_t)2 << 30) / per_l));
         }
+        if (use_own_fft) chunk = std::min(chunk, FftK<T, 256>::MAX_PLANES);  // planes per pruned FFT launch
         chunk = std::min(chunk, longest);
         spec.alloc((size_t)chunk * nfp * sizeof(C));
         SURFH_CUDA(cudaMemset(spec.p, 0, spec.bytes));
@@ -391,6 +410,18 @@ template <typename T> struct ModelImpl : surfh_model {
         if (use_own_fft) {
             ownfft.init(Na, Nb);
             zbuf.alloc((size_t)std::max(chunk, K) * ownfft.z_plane() * sizeof(C));
+            std::vector<int2> pr(Nl, make_int2(0, 0));
+            plane_pair_cnt.assign(Nl, 0);
+            for (int l = 0; l < Nl; ++l) {
+                int lo = Na, hi = -1;
+                for (auto& b : bands)
+                    if (l >= b->l0 && l < b->l0 + b->nl) { lo = std::min(lo, b->row_lo); hi = std::max(hi, b->row_hi); }
+                if (hi < lo) continue;
+                pr[l] = make_int2(lo / 2, hi / 2 - lo / 2 + 1);
+                plane_pair_cnt[l] = pr[l].y;
+            }
+            plane_pairs.alloc((size_t)Nl * sizeof(int2));
+            SURFH_CUDA(cudaMemcpy(plane_pairs.p, pr.data(), (size_t)Nl * sizeof(int2), cudaMemcpyHostToDevice));
         } else {
             if (K > 0) {
                 make_plan(0, K);
@@ -465,12 +496,22 @@ template <typename T> struct ModelImpl : surfh_model {
     }
 
     int fft_launches() const { return use_own_fft ? 2 : 1; }
-    void fft_exec(int kind, int batch, void* in, void* out, cudaStream_t st) {
+    // prune_c0 >= 0: the real side is the working cube of planes [prune_c0, prune_c0 + batch), of which only
+    // the rows some band touches matter (C2R: produced; R2C: non-zero)
+    void fft_exec(int kind, int batch, void* in, void* out, cudaStream_t st, int prune_c0 = -1) {
         if (use_own_fft) {
+            const int2* pr = nullptr;
+            long long n_pairs = 0;
+            if (prune_c0 >= 0 && prune_rows) {
+                pr = plane_pairs.as<int2>() + prune_c0;
+                for (int l = prune_c0; l < prune_c0 + batch; ++l) n_pairs += plane_pair_cnt[l];
+            }
             if (kind == 0)
-                ownfft.r2c(reinterpret_cast<const T*>(in), plane, reinterpret_cast<C*>(out), nfp, zbuf.as<C>(), batch, st);
+                ownfft.r2c(reinterpret_cast<const T*>(in), plane, reinterpret_cast<C*>(out), nfp, zbuf.as<C>(), batch, st,
+                           pr, n_pairs);
             else
-                ownfft.c2r(reinterpret_cast<const C*>(in), nfp, reinterpret_cast<T*>(out), plane, zbuf.as<C>(), batch, st);
+                ownfft.c2r(reinterpret_cast<const C*>(in), nfp, reinterpret_cast<T*>(out), plane, zbuf.as<C>(), batch, st,
+                           pr, n_pairs);
             return;
         }
         cufftHandle p = plan(kind, batch);
@@ -616,7 +657,7 @@ template <typename T> struct ModelImpl : surfh_model {
                 }
                 {
                     Scope sc(this, ST_IRFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
-                    fft_exec(1, nl, spec.p, cubebuf.p, st);
+                    fft_exec(1, nl, spec.p, cubebuf.p, st, c0);
                 }
                 gather_chunk(c0, c1, st);
             }
@@ -642,7 +683,7 @@ template <typename T> struct ModelImpl : surfh_model {
                 scatter_chunk(c0, c1, mode, st);
                 {
                     Scope sc(this, ST_RFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
-                    fft_exec(0, nl, cubebuf.p, spec.p, st);
+                    fft_exec(0, nl, cubebuf.p, spec.p, st, c0);
                 }
                 if (K > 0) {
                     Scope sc(this, ST_LMM_OTF_ADJ, st, (double)nl * nf * sizeof(C) * 2 + (double)K * nf * sizeof(C),

@@ -141,10 +141,12 @@ template <typename T> struct OwnFft2d {
     // complex elements per plane of the intermediate buffer
     size_t z_plane() const { return std::max((size_t)((na + 1) / 2) * nb, (size_t)na * nh); }
 
-    FftShape shape(size_t real_plane, size_t spec_plane, int batch) const {
+    FftShape shape(size_t real_plane, size_t spec_plane, int batch, const int2* pair_range) const {
         FftShape s;
         s.na = na; s.nb = nb; s.nh = nh; s.npair = (na + 1) / 2;
         s.real_plane = real_plane; s.spec_plane = spec_plane; s.z_plane = z_plane(); s.batch = batch;
+        s.pair_range = pair_range;
+        if (pair_range && batch > FftK<T, 256>::MAX_PLANES) throw Error(SURFH_EINVAL, "pruned FFT launch: too many planes");
         return s;
     }
 
@@ -156,12 +158,16 @@ template <typename T> struct OwnFft2d {
     }
 
     // in: real [batch] planes (stride real_plane) -> spec: [batch][na][nh] (stride spec_plane); z: scratch
-    void r2c(const T* in, size_t real_plane, C* spec, size_t spec_plane, C* z, int batch, cudaStream_t st) const {
-        const FftShape s = shape(real_plane, spec_plane, batch);
+    // pair_range: [device] per-plane (first row pair, count) outside of which the input rows are zero, or NULL;
+    // n_pairs: sum of the counts (host copy), ignored without pair_range
+    void r2c(const T* in, size_t real_plane, C* spec, size_t spec_plane, C* z, int batch, cudaStream_t st,
+             const int2* pair_range = nullptr, long long n_pairs = 0) const {
+        const FftShape s = shape(real_plane, spec_plane, batch, pair_range);
+        const long long row_items = pair_range ? n_pairs : (long long)batch * s.npair;
         SURFH_DISPATCH_M(axis_b->m, {
             using K = FftK<T, MM>;
             RowsR2C<T, MM> pass{in, z, s};
-            launch<MM>(pass, ((long long)batch * s.npair + K::G - 1) / K::G, *axis_b, st);
+            launch<MM>(pass, (row_items + K::G - 1) / K::G, *axis_b, st);
         });
         SURFH_DISPATCH_M(axis_a.m, {
             using K = FftK<T, MM>;
@@ -172,8 +178,11 @@ template <typename T> struct OwnFft2d {
     }
 
     // spec: [batch][na][nh] -> out: real planes; z: scratch
-    void c2r(const C* spec, size_t spec_plane, T* out, size_t real_plane, C* z, int batch, cudaStream_t st) const {
-        const FftShape s = shape(real_plane, spec_plane, batch);
+    // pair_range: per-plane row pairs of the output that are wanted (the others are left untouched), or NULL
+    void c2r(const C* spec, size_t spec_plane, T* out, size_t real_plane, C* z, int batch, cudaStream_t st,
+             const int2* pair_range = nullptr, long long n_pairs = 0) const {
+        const FftShape s = shape(real_plane, spec_plane, batch, pair_range);
+        const long long row_items = pair_range ? n_pairs : (long long)batch * s.npair;
         SURFH_DISPATCH_M(axis_a.m, {
             using K = FftK<T, MM>;
             ColsPass<T, MM, true> pass{spec, z, s};
@@ -182,7 +191,7 @@ template <typename T> struct OwnFft2d {
         SURFH_DISPATCH_M(axis_b->m, {
             using K = FftK<T, MM>;
             RowsC2R<T, MM> pass{z, out, s};
-            launch<MM>(pass, ((long long)batch * s.npair + K::G - 1) / K::G, *axis_b, st);
+            launch<MM>(pass, (row_items + K::G - 1) / K::G, *axis_b, st);
         });
         SURFH_CUDA(cudaGetLastError());
     }

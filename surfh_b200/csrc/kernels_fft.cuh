@@ -63,7 +63,10 @@ template <typename T, int M> struct FftK {
     static constexpr int OFF_BUF = OFF_CHIRP + HALF;
     static constexpr int OFF_STAGE = OFF_BUF + G * BUF;
     static constexpr int N_SMEM = OFF_STAGE + SLOTS * NT;
-    static constexpr size_t SMEM_BYTES = (size_t)N_SMEM * sizeof(C);
+    // after the complex area: per-plane row-pair ranges of a pruned launch (start[MAX_PLANES+1], lo[MAX_PLANES])
+    static constexpr int MAX_PLANES = 512;
+    static constexpr size_t OFF_RANGES_BYTES = (size_t)N_SMEM * sizeof(C);
+    static constexpr size_t SMEM_BYTES = OFF_RANGES_BYTES + (2 * MAX_PLANES + 2) * sizeof(int);
     static constexpr size_t SMEM_BYTES_FILTER = (size_t)OFF_STAGE * sizeof(C);
 };
 
@@ -390,7 +393,71 @@ struct FftShape {
     size_t spec_plane;       // complex elements between spectrum planes ([na][nh], row pitch nh)
     size_t z_plane;          // complex elements between planes of the intermediate buffer
     int batch;
+    // Pruned transforms: per plane, only the row pairs [lo, lo + cnt) of the real image matter (C2R: the
+    // others are not produced; R2C: the others are known to be zero).  NULL = all rows.  [batch] (lo, cnt)
+    const int2* pair_range;
 };
+
+// Shared-memory view of the row-pair ranges of one launch (built once per CTA).
+struct FftRanges {
+    const int* start;  // [batch + 1] exclusive prefix sum of cnt; NULL when the launch is not pruned
+    const int* lo;     // [batch]
+    int batch;
+    __device__ __forceinline__ int total() const { return start[batch]; }
+    // plane holding work item `it` (0 <= it < total): last p with start[p] <= it
+    __device__ __forceinline__ int plane_of(int it) const {
+        int a = 0, b = batch;
+        while (b - a > 1) {
+            const int mid = (a + b) >> 1;
+            if (start[mid] <= it) a = mid; else b = mid;
+        }
+        return a;
+    }
+    __device__ __forceinline__ int cnt(int p) const { return start[p + 1] - start[p]; }
+};
+
+// Builds the ranges in shared memory: thread-serial chunks + one warp scan (batch <= MAX_PLANES).
+template <int MAX_PLANES>
+__device__ __forceinline__ FftRanges fft_build_ranges(int* smem_i, const int2* pair_range, int batch) {
+    FftRanges r;
+    r.batch = batch;
+    r.start = nullptr;
+    r.lo = nullptr;
+    if (pair_range == nullptr) return r;
+    int* start = smem_i;
+    int* lo = smem_i + MAX_PLANES + 1;
+    if (threadIdx.x < 32) {
+        constexpr int PER = MAX_PLANES / 32;
+        const int base = threadIdx.x * PER;
+        int sum = 0;
+        for (int k = 0; k < PER; ++k) {
+            const int p = base + k;
+            if (p < batch) {
+                const int2 pr = pair_range[p];
+                lo[p] = pr.x;
+                sum += pr.y;
+            }
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += v;
+        }
+        int run = incl - sum;
+        for (int k = 0; k < PER; ++k) {
+            const int p = base + k;
+            if (p < batch) {
+                start[p] = run;
+                run += pair_range[p].y;
+            }
+        }
+        if (threadIdx.x == 31) start[batch] = incl;
+    }
+    r.start = start;
+    r.lo = lo;
+    return r;  // visibility: the caller's __syncthreads (fft_load_tables) follows
+}
 
 // ---- asynchronous staging of the next item's inputs -------------------------------------------
 // Every thread copies exactly the elements it will itself consume into thread-private shared-memory
@@ -417,17 +484,26 @@ template <typename T, int M> struct RowsR2C {
     const T* in;
     C* y;
     FftShape s;
-    __device__ int steps() const { return (int)(((long long)s.batch * s.npair + K::G - 1) / K::G); }
-    __device__ FftItem item(int step, int g) const {
+    __device__ int steps(const FftRanges& rg) const {
+        const long long total = rg.start ? rg.total() : (long long)s.batch * s.npair;
+        return (int)((total + K::G - 1) / K::G);
+    }
+    __device__ FftItem item(int step, int g, const FftRanges& rg) const {
         const long long it = (long long)step * K::G + g;
         FftItem r;
-        r.live = it < (long long)s.batch * s.npair;
-        r.plane = r.live ? (int)(it / s.npair) : 0;
-        r.idx = r.live ? (int)(it % s.npair) : 0;
+        if (rg.start) {
+            r.live = it < rg.total();
+            r.plane = r.live ? rg.plane_of((int)it) : 0;
+            r.idx = r.live ? rg.lo[r.plane] + ((int)it - rg.start[r.plane]) : 0;
+        } else {
+            r.live = it < (long long)s.batch * s.npair;
+            r.plane = r.live ? (int)(it / s.npair) : 0;
+            r.idx = r.live ? (int)(it % s.npair) : 0;
+        }
         return r;
     }
     // staged: 16 reals per thread = 8 complex-sized slots; slot (m, k) at stage[(2m + k) * NT + tid] in reals
-    __device__ void prefetch(const FftItem& it, int t, C* stage_c, int tid) const {
+    __device__ void prefetch(const FftItem& it, int t, C* stage_c, int tid, const FftRanges&) const {
         if (!it.live) return;
         T* stage = reinterpret_cast<T*>(stage_c);
         const int r0 = 2 * it.idx;
@@ -442,7 +518,7 @@ template <typename T, int M> struct RowsR2C {
             }
         }
     }
-    __device__ void load(const FftItem& it, int t, const C* stage_c, int tid, C* v, const C* chirp) const {
+    __device__ void load(const FftItem& it, int t, const C* stage_c, int tid, C* v, const C* chirp, const FftRanges&) const {
         const T* stage = reinterpret_cast<const T*>(stage_c);
         const bool has_b = 2 * it.idx + 1 < s.na;
 #pragma unroll
@@ -460,7 +536,7 @@ template <typename T, int M> struct RowsR2C {
     // Z[n] = FFT(row_even + i row_odd)[n] is written to the transform's buffer in natural order (these
     // are the thread's own final-stage locations), then every thread separates A[j] = (Z[j] + conj
     // Z[nb-j]) / 2 and B[j] = (Z[j] - conj Z[nb-j]) / 2i for its share of j < nh.
-    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C* buf, const C* chirp) const {
+    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C* buf, const C* chirp, const FftRanges& rg) const {
         const int t = th.t;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
@@ -496,8 +572,8 @@ template <typename T, int M, bool INVERSE> struct ColsPass {
     C* dst;
     FftShape s;
     __device__ int tiles() const { return (s.nh + K::G - 1) / K::G; }
-    __device__ int steps() const { return s.batch * tiles(); }
-    __device__ FftItem item(int step, int g) const {
+    __device__ int steps(const FftRanges&) const { return s.batch * tiles(); }
+    __device__ FftItem item(int step, int g, const FftRanges&) const {
         const int tl = tiles();
         FftItem r;
         r.plane = step / tl;
@@ -506,21 +582,34 @@ template <typename T, int M, bool INVERSE> struct ColsPass {
         return r;
     }
     __device__ size_t src_plane() const { return INVERSE ? s.spec_plane : s.z_plane; }
-    __device__ void prefetch(const FftItem& it, int t, C* stage, int tid) const {
+    // forward direction of a pruned launch: rows outside the plane's range are zero and are not read
+    __device__ void row_window(const FftItem& it, const FftRanges& rg, int& r0, int& r1) const {
+        r0 = 0;
+        r1 = s.na;
+        if (!INVERSE && rg.start) {
+            r0 = 2 * rg.lo[it.plane];
+            r1 = min(s.na, r0 + 2 * rg.cnt(it.plane));
+        }
+    }
+    __device__ void prefetch(const FftItem& it, int t, C* stage, int tid, const FftRanges& rg) const {
         if (!it.live) return;
+        int r0, r1;
+        row_window(it, rg, r0, r1);
         const C* col = src + (size_t)it.plane * src_plane() + it.idx;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int i = t + K::TT * m;
-            if (i < s.na) cp_async<sizeof(C)>(stage + m * K::NT + tid, col + (size_t)i * s.nh);
+            if (i >= r0 && i < r1) cp_async<sizeof(C)>(stage + m * K::NT + tid, col + (size_t)i * s.nh);
         }
     }
-    __device__ void load(const FftItem& it, int t, const C* stage, int tid, C* v, const C* chirp) const {
+    __device__ void load(const FftItem& it, int t, const C* stage, int tid, C* v, const C* chirp, const FftRanges& rg) const {
+        int r0, r1;
+        row_window(it, rg, r0, r1);
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int i = t + K::TT * m;
             C u = make_c<T>(T(0), T(0));
-            if (it.live && i < s.na) {
+            if (it.live && i >= r0 && i < r1) {
                 u = stage[m * K::NT + tid];
                 if (INVERSE) u.y = -u.y;
                 u = cmul(u, chirp[i]);
@@ -528,7 +617,7 @@ template <typename T, int M, bool INVERSE> struct ColsPass {
             v[m] = u;
         }
     }
-    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C* buf, const C* chirp) const {
+    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C* buf, const C* chirp, const FftRanges& rg) const {
         const int t = th.t;
         if (!INVERSE) {
             if (!it.live) return;
@@ -555,10 +644,12 @@ template <typename T, int M, bool INVERSE> struct ColsPass {
         th.sync();
         if (!it.live) return;
         C* zp = dst + (size_t)it.plane * s.z_plane;
+        const int p0 = rg.start ? rg.lo[it.plane] : 0;
+        const int p1 = rg.start ? p0 + rg.cnt(it.plane) : s.npair;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int p = t + K::TT * m;
-            if (p < s.npair) {
+            if (p >= p0 && p < p1) {
                 const C a = buf[2 * p];
                 const C b = 2 * p + 1 < s.na ? buf[2 * p + 1] : make_c<T>(T(0), T(0));
                 C* row = zp + (size_t)p * s.nb;
@@ -577,16 +668,25 @@ template <typename T, int M> struct RowsC2R {
     const C* z;
     T* out;
     FftShape s;
-    __device__ int steps() const { return (int)(((long long)s.batch * s.npair + K::G - 1) / K::G); }
-    __device__ FftItem item(int step, int g) const {
+    __device__ int steps(const FftRanges& rg) const {
+        const long long total = rg.start ? rg.total() : (long long)s.batch * s.npair;
+        return (int)((total + K::G - 1) / K::G);
+    }
+    __device__ FftItem item(int step, int g, const FftRanges& rg) const {
         const long long it = (long long)step * K::G + g;
         FftItem r;
-        r.live = it < (long long)s.batch * s.npair;
-        r.plane = r.live ? (int)(it / s.npair) : 0;
-        r.idx = r.live ? (int)(it % s.npair) : 0;
+        if (rg.start) {
+            r.live = it < rg.total();
+            r.plane = r.live ? rg.plane_of((int)it) : 0;
+            r.idx = r.live ? rg.lo[r.plane] + ((int)it - rg.start[r.plane]) : 0;
+        } else {
+            r.live = it < (long long)s.batch * s.npair;
+            r.plane = r.live ? (int)(it / s.npair) : 0;
+            r.idx = r.live ? (int)(it % s.npair) : 0;
+        }
         return r;
     }
-    __device__ void prefetch(const FftItem& it, int t, C* stage, int tid) const {
+    __device__ void prefetch(const FftItem& it, int t, C* stage, int tid, const FftRanges&) const {
         if (!it.live) return;
         const C* row = z + (size_t)it.plane * s.z_plane + (size_t)it.idx * s.nb;
 #pragma unroll
@@ -596,7 +696,7 @@ template <typename T, int M> struct RowsC2R {
         }
     }
     // IFFT(z) = conj(FFT(conj z)) = row_even + i row_odd
-    __device__ void load(const FftItem& it, int t, const C* stage, int tid, C* v, const C* chirp) const {
+    __device__ void load(const FftItem& it, int t, const C* stage, int tid, C* v, const C* chirp, const FftRanges&) const {
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int n = t + K::TT * m;
@@ -609,7 +709,7 @@ template <typename T, int M> struct RowsC2R {
             v[m] = u;
         }
     }
-    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C*, const C* chirp) const {
+    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C*, const C* chirp, const FftRanges&) const {
         if (!it.live) return;
         const int t = th.t, r0 = 2 * it.idx;
         const bool has_b = r0 + 1 < s.na;
@@ -639,20 +739,23 @@ __global__ void __launch_bounds__(FftK<T, M>::NT, 1) fft_pass_kernel(Pass pass, 
     C* buf = smem + K::OFF_BUF + th.g * K::BUF;
     C* stage = smem + K::OFF_STAGE;
     const C* chirp = smem + K::OFF_CHIRP;
-    const int n_steps = pass.steps();
-    int step = blockIdx.x;
-    if (step < n_steps) pass.prefetch(pass.item(step, th.g), th.t, stage, tid);
-    cp_async_commit();
+    const FftRanges rg = fft_build_ranges<K::MAX_PLANES>(reinterpret_cast<int*>(fft_smem + K::OFF_RANGES_BYTES),
+                                                          pass.s.pair_range, pass.s.batch);
     fft_load_tables<T, M>(smem, p, true);
+    const int n_steps = pass.steps(rg);
+    int step = blockIdx.x;
+    if (step < n_steps) pass.prefetch(pass.item(step, th.g, rg), th.t, stage, tid, rg);
+    cp_async_commit();
     for (; step < n_steps; step += gridDim.x) {
         C v[16];
-        const FftItem cur = pass.item(step, th.g);
+        const FftItem cur = pass.item(step, th.g, rg);
         cp_async_wait_all();
-        pass.load(cur, th.t, stage, tid, v, chirp);
-        if (step + (int)gridDim.x < n_steps) pass.prefetch(pass.item(step + gridDim.x, th.g), th.t, stage, tid);
+        pass.load(cur, th.t, stage, tid, v, chirp, rg);
+        if (step + (int)gridDim.x < n_steps)
+            pass.prefetch(pass.item(step + (int)gridDim.x, th.g, rg), th.t, stage, tid, rg);
         cp_async_commit();
         chirp_convolve<T, M, Pass::POST>(v, smem, buf, th);
-        pass.finish(pass.item(step, th.g), th, v, buf, chirp);
+        pass.finish(cur, th, v, buf, chirp, rg);
     }
 }
 
