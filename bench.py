@@ -62,6 +62,42 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_fp_peak(torch, tdtype):
+    """Arithmetic peak of the compute dtype on this GPU, measured here: cuBLAS GEMM 6144^3 (fp64 runs on the
+    FP64 tensor pipe, fp32 with TF32 off on the FMA pipe), best of 3."""
+    try:
+        n = 6144
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        a = torch.randn((n, n), dtype=tdtype, device="cuda")
+        b = torch.randn((n, n), dtype=tdtype, device="cuda")
+        torch.matmul(a, b)
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        del a, b
+        return {"tflops": 2.0 * n ** 3 / (best * 1e-3) / 1e12, "source": f"measured here: cuBLAS {tdtype} GEMM {n}^3, best of 3"}
+    except Exception as exc:  # noqa: BLE001
+        return {"tflops": None, "source": f"unavailable ({exc})"}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of each stage's kernels from the committed ncu --set full capture of this same
+    command (profiles/traffic.json, written by tools/ncu_traffic.py); {} when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        return json.load(f).get("stages", {})
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -329,30 +365,51 @@ def run_b200(args):
 
     # ---- roofline from the stage events of the timed region
     hbm_peak, peak_src = measured_peaks()
-    own_hbm = {"lmm_otf_fwd", "lmm_otf_adj", "slit_gather", "slit_scatter", "cg_fused"}
-    own_fma = {"spectral_gemm_fwd", "spectral_gemm_adj"}
+    fp_peak = measured_fp_peak(torch, tdtype)  # cuBLAS GEMM of the compute dtype, this GPU, this run
+    traffic = ncu_traffic()
     stage_rows = []
     tot_ms = sum(s["ms"] for s in stages) or 1.0
     for s in stages:
+        name = s["stage"]
         per_step_ms = s["ms"] / args.steps
-        row = {"stage": s["stage"], "ms_per_step": per_step_ms, "share": s["ms"] / tot_ms,
-               "own": s["stage"] in own_hbm | own_fma}
-        if s["stage"] in own_fma:
-            row.update(bound="fma_" + ("fp64" if esz == 8 else "fp32"), unit="TFLOP/s",
-                       achieved=s["flops"] / (s["ms"] * 1e-3) / 1e12 if s["ms"] > 0 else None)
+        own = not (name.startswith("cufft_") or name == "memset")
+        row = {"stage": name, "ms_per_step": per_step_ms, "share": s["ms"] / tot_ms, "own": own,
+               "launches_per_step": s["launches"] / args.steps}
+        sec = s["ms"] * 1e-3
+        if name.startswith("spectral_gemm"):
+            # dense contraction on the FP64 tensor pipe (DMMA) / FP32 FMA: flop-bound, not HBM-bound
+            row.update(bound="tensor" if esz == 8 else "fma_fp32", unit="TFLOP/s",
+                       achieved=s["flops"] / sec / 1e12 if sec > 0 else None, peak=fp_peak["tflops"])
+            if row["achieved"] is not None and fp_peak["tflops"]:
+                row["frac"] = row["achieved"] / fp_peak["tflops"]
         else:
-            row.update(bound="hbm", unit="GB/s",
-                       achieved=s["bytes"] / (s["ms"] * 1e-3) / 1e9 if s["ms"] > 0 else None)
+            row.update(bound="hbm", unit="GB/s", achieved=s["bytes"] / sec / 1e9 if sec > 0 else None, peak=hbm_peak)
             if row["achieved"] is not None:
                 row["frac"] = row["achieved"] / hbm_peak
+            if name.startswith("chirpz_") and sec > 0:
+                # the chirp-z FFT is bounded by the FP64 pipe and the shared-memory crossbar, not by HBM:
+                # report its arithmetic rate beside the (low, by construction) HBM fraction
+                row["tflops"] = s["flops"] / sec / 1e12
+                if fp_peak["tflops"]:
+                    row["frac_of_fp_peak"] = row["tflops"] / fp_peak["tflops"]
+                row["limiter"] = "fp64 pipe + shared-memory crossbar (see profiles/)"
+        if s["launches"]:
+            row["algorithmic_bytes_per_launch"] = s["bytes"] / s["launches"]
+        if name in traffic:
+            row["traffic"] = traffic[name]
         stage_rows.append(row)
-    own_hbm_rows = [r for r in stage_rows if r["stage"] in own_hbm and r.get("achieved")]
-    top = max(own_hbm_rows, key=lambda r: r["ms_per_step"]) if own_hbm_rows else None
+    own_rows = [r for r in stage_rows if r["own"] and r.get("achieved")]
+    top = max(own_rows, key=lambda r: r["ms_per_step"]) if own_rows else None
     roofline = None
     if top:
-        roofline = {"kernel": top["stage"], "bound": "hbm", "achieved": top["achieved"], "peak": hbm_peak,
-                    "unit": "GB/s", "frac": top["achieved"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+        roofline = {"kernel": top["stage"], "bound": top["bound"] if top["bound"] in ("hbm", "tensor") else "hbm",
+                    "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top.get("frac"),
+                    "traffic": top.get("traffic"),
+                    "peak_source": peak_src if top["unit"] == "GB/s" else fp_peak["source"],
                     "share_of_step": top["share"]}
+        for k in ("tflops", "frac_of_fp_peak", "limiter", "algorithmic_bytes_per_launch"):
+            if k in top:
+                roofline[k] = top[k]
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

@@ -184,10 +184,13 @@ int surfh_criterion_terms(surfh_handle h, const void* y, const void* hx, int64_t
 /* number of kernels (own + cuFFT exec calls) this handle has launched since creation */
 int64_t surfh_launch_count(surfh_handle h);
 int64_t surfh_own_launch_count(surfh_handle h);
-/* per-stage CUDA-event timing of the NEXT forward/adjoint call pair: enable, run, then read.
- * names/ms arrays of capacity `cap`; returns number of stages filled (synchronises). */
+/* per-stage CUDA-event timing of the calls made while enabled: enable, run, then read.
+ * Output arrays of capacity `cap` (any may be NULL): stage name ("chirpz_*" = hand-written FFT passes,
+ * "cufft_*" = library FFT), summed milliseconds, algorithmic bytes, flops and kernel launches.
+ * Returns the number of stages filled (synchronises the device). */
 int surfh_profile_enable(surfh_handle h, int32_t on);
-int surfh_profile_read(surfh_handle h, int32_t cap, const char** names, float* ms, double* bytes, double* flops);
+int surfh_profile_read(surfh_handle h, int32_t cap, const char** names, float* ms, double* bytes, double* flops,
+                       int32_t* launches);
 
 #ifdef __cplusplus
 }

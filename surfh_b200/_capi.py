@@ -103,7 +103,7 @@ def load() -> C.CDLL:
         "surfh_own_launch_count": (i64, [vp]),
         "surfh_profile_enable": (C.c_int, [vp, i32]),
         "surfh_profile_read": (C.c_int, [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
-                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -29,9 +30,16 @@ enum Stage {
     ST_RFFT_MAPS = 0, ST_LMM_OTF_FWD, ST_IRFFT_CUBE, ST_SLIT_GATHER, ST_GEMM_FWD,
     ST_GEMM_ADJ, ST_SLIT_SCATTER, ST_RFFT_CUBE, ST_LMM_OTF_ADJ, ST_IRFFT_MAPS, ST_MEMSET, ST_CG, ST_COUNT
 };
+// the four FFT stages are prefixed "chirpz_" (hand-written kernels) or "cufft_" at read time
 static const char* kStageNames[ST_COUNT] = {
     "rfft_maps", "lmm_otf_fwd", "irfft_cube", "slit_gather", "spectral_gemm_fwd",
     "spectral_gemm_adj", "slit_scatter", "rfft_cube", "lmm_otf_adj", "irfft_maps", "memset", "cg_fused"};
+static const char* kStageNamesOwnFft[ST_COUNT] = {
+    "chirpz_rfft_maps", "lmm_otf_fwd", "chirpz_irfft_cube", "slit_gather", "spectral_gemm_fwd",
+    "spectral_gemm_adj", "slit_scatter", "chirpz_rfft_cube", "lmm_otf_adj", "chirpz_irfft_maps", "memset", "cg_fused"};
+static const char* kStageNamesCufft[ST_COUNT] = {
+    "cufft_rfft_maps", "lmm_otf_fwd", "cufft_irfft_cube", "slit_gather", "spectral_gemm_fwd",
+    "spectral_gemm_adj", "slit_scatter", "cufft_rfft_cube", "lmm_otf_adj", "cufft_irfft_maps", "memset", "cg_fused"};
 
 }  // namespace surfh
 
@@ -46,6 +54,7 @@ struct surfh_model {
     std::string last_error;
     int64_t launches = 0, own_launches = 0;
     int device = 0;
+    bool own_fft_names = false;
 
     // profiling
     bool profiling = false;
@@ -202,6 +211,7 @@ template <typename T> struct ModelImpl : surfh_model {
                       "fft_backend = own needs both map axes <= 1024 pixels");
         if (const char* e = std::getenv("SURFH_FFT_PRUNE")) prune_rows = std::strcmp(e, "0") != 0;
         use_own_fft = fft_backend == SURFH_FFT_OWN || (fft_backend == SURFH_FFT_AUTO && OwnFft2d<T>::supported(Na, Nb));
+        own_fft_names = use_own_fft;
         otf.alloc((size_t)Nl * nfp * sizeof(C));
         SURFH_CUDA(cudaMemset(otf.p, 0, otf.bytes));
         otf_set.assign(Nl, 0);
@@ -496,6 +506,28 @@ template <typename T> struct ModelImpl : surfh_model {
     }
 
     int fft_launches() const { return use_own_fft ? 2 : 1; }
+    // Algorithmic bytes of one batched 2-D transform: the half spectrum plus the real rows that matter
+    // (all of them, or the pruned row pairs of planes [c0, c0 + batch) of the working cube).
+    double fft_bytes(int batch, int prune_c0) const {
+        double rows = (double)batch * Na;
+        if (use_own_fft && prune_rows && prune_c0 >= 0) {
+            rows = 0;
+            for (int l = prune_c0; l < prune_c0 + batch; ++l) rows += 2.0 * plane_pair_cnt[l];
+        }
+        return (double)batch * nf * sizeof(C) + rows * Nb * sizeof(T);
+    }
+    // Flops of the chirp-z evaluation (hand-written backend): per 1-D transform two M-point FFTs at
+    // 5 M log2 M, the filter product (6 M) and the two chirp products (6 N each).
+    double fft_flops(int batch, int prune_c0) const {
+        if (!use_own_fft) return 0.0;
+        auto one = [](int m, int n) { return 10.0 * m * std::log2((double)m) + 6.0 * m + 12.0 * n; };
+        double pairs = (double)batch * ((Na + 1) / 2);
+        if (prune_rows && prune_c0 >= 0) {
+            pairs = 0;
+            for (int l = prune_c0; l < prune_c0 + batch; ++l) pairs += plane_pair_cnt[l];
+        }
+        return pairs * one(ownfft.axis_b->m, Nb) + (double)batch * Nh * one(ownfft.axis_a.m, Na);
+    }
     // prune_c0 >= 0: the real side is the working cube of planes [prune_c0, prune_c0 + batch), of which only
     // the rows some band touches matter (C2R: produced; R2C: non-zero)
     void fft_exec(int kind, int batch, void* in, void* out, cudaStream_t st, int prune_c0 = -1) {
@@ -633,7 +665,7 @@ template <typename T> struct ModelImpl : surfh_model {
         const T* x = reinterpret_cast<const T*>(xv);
         T* y = reinterpret_cast<T*>(yv);
         if (K > 0) {
-            Scope sc(this, ST_RFFT_MAPS, st, (double)K * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
+            Scope sc(this, ST_RFFT_MAPS, st, fft_bytes(K, -1), fft_flops(K, -1), fft_launches(), use_own_fft);
             fft_exec(0, K, const_cast<T*>(x), xhat.p, st);
         }
         for (auto& r : ranges) {
@@ -646,7 +678,7 @@ template <typename T> struct ModelImpl : surfh_model {
                     SURFH_CUDA(cudaGetLastError());
                 } else {
                     {
-                        Scope sc(this, ST_RFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
+                        Scope sc(this, ST_RFFT_CUBE, st, fft_bytes(nl, -1), fft_flops(nl, -1), fft_launches(), use_own_fft);
                         fft_exec(0, nl, const_cast<T*>(x) + (size_t)c0 * plane, spec.p, st);
                     }
                     Scope sc(this, ST_LMM_OTF_FWD, st, (double)nl * nf * sizeof(C) * 3, 6.0 * nl * nf, 1, true);
@@ -656,7 +688,7 @@ template <typename T> struct ModelImpl : surfh_model {
                     SURFH_CUDA(cudaGetLastError());
                 }
                 {
-                    Scope sc(this, ST_IRFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
+                    Scope sc(this, ST_IRFFT_CUBE, st, fft_bytes(nl, c0), fft_flops(nl, c0), fft_launches(), use_own_fft);
                     fft_exec(1, nl, spec.p, cubebuf.p, st, c0);
                 }
                 gather_chunk(c0, c1, st);
@@ -682,7 +714,7 @@ template <typename T> struct ModelImpl : surfh_model {
                 const int c1 = std::min(r.second, c0 + chunk), nl = c1 - c0;
                 scatter_chunk(c0, c1, mode, st);
                 {
-                    Scope sc(this, ST_RFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
+                    Scope sc(this, ST_RFFT_CUBE, st, fft_bytes(nl, c0), fft_flops(nl, c0), fft_launches(), use_own_fft);
                     fft_exec(0, nl, cubebuf.p, spec.p, st, c0);
                 }
                 if (K > 0) {
@@ -698,14 +730,14 @@ template <typename T> struct ModelImpl : surfh_model {
                             spec.as<C>(), otf.as<C>() + (size_t)c0 * nfp, n, (T)(1.0 / ((double)Na * Nb)));
                         SURFH_CUDA(cudaGetLastError());
                     }
-                    Scope sc(this, ST_IRFFT_CUBE, st, (double)nl * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
+                    Scope sc(this, ST_IRFFT_CUBE, st, fft_bytes(nl, -1), fft_flops(nl, -1), fft_launches(), use_own_fft);
                     fft_exec(1, nl, spec.p, x + (size_t)c0 * plane, st);
                 }
                 first = false;
             }
         }
         if (K > 0) {
-            Scope sc(this, ST_IRFFT_MAPS, st, (double)K * (plane * sizeof(T) + nf * sizeof(C)), 0, fft_launches(), use_own_fft);
+            Scope sc(this, ST_IRFFT_MAPS, st, fft_bytes(K, -1), fft_flops(K, -1), fft_launches(), use_own_fft);
             fft_exec(1, K, xhat.p, x, st);
         }
     }
@@ -1059,7 +1091,8 @@ int surfh_profile_enable(surfh_handle h, int32_t on) {
     return SURFH_OK;
 }
 
-int surfh_profile_read(surfh_handle h, int32_t cap, const char** names, float* ms, double* bytes, double* flops) {
+int surfh_profile_read(surfh_handle h, int32_t cap, const char** names, float* ms, double* bytes, double* flops,
+                       int32_t* launches) {
     if (!h || cap < 0) return SURFH_EINVAL;
     cudaDeviceSynchronize();
     float acc[ST_COUNT] = {0};
@@ -1070,10 +1103,11 @@ int surfh_profile_read(surfh_handle h, int32_t cap, const char** names, float* m
     int n = 0;
     for (int i = 0; i < ST_COUNT && n < cap; ++i) {
         if (h->stage_launches[i] == 0) continue;
-        if (names) names[n] = kStageNames[i];
+        if (names) names[n] = h->own_fft_names ? kStageNamesOwnFft[i] : kStageNamesCufft[i];
         if (ms) ms[n] = acc[i];
         if (bytes) bytes[n] = h->stage_bytes[i];
         if (flops) flops[n] = h->stage_flops[i];
+        if (launches) launches[n] = h->stage_launches[i];
         ++n;
     }
     return n;

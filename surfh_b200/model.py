@@ -389,11 +389,12 @@ class spectroSigRLSCT(LinOp):
         ms = (C.c_float * cap)()
         nbytes = (C.c_double * cap)()
         flops = (C.c_double * cap)()
-        n = self._lib.surfh_profile_read(self._h, cap, names, ms, nbytes, flops)
+        launches = (C.c_int32 * cap)()
+        n = self._lib.surfh_profile_read(self._h, cap, names, ms, nbytes, flops, launches)
         if n < 0:
             raise _capi.SurfhError(n, "profile_read failed")
-        return [dict(stage=names[i].decode(), ms=float(ms[i]), bytes=float(nbytes[i]), flops=float(flops[i]))
-                for i in range(n)]
+        return [dict(stage=names[i].decode(), ms=float(ms[i]), bytes=float(nbytes[i]), flops=float(flops[i]),
+                     launches=int(launches[i])) for i in range(n)]
 
 
 # the reference's callers import the class under this module alias too
