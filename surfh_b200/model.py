@@ -304,14 +304,27 @@ class spectroSigRLSCT(LinOp):
         _capi.check(self._h, self._lib.surfh_adjoint_host(self._h, _capi.ptr(y), _capi.ptr(x), self.mode_code))
         return x
 
-    def fwadj(self, maps):
-        """H^T H maps without the detector vector leaving the device."""
+    def fwadj(self, maps, out=None):
+        """H^T H maps without the detector vector leaving the device (aljabr.LinOp.fwadj as inherited by
+        the reference class).  numpy in -> numpy out (H2D of the maps, D2H of the result inside the call;
+        `out`: optional float64 host array to fill, e.g. a view of pinned memory); CUDA tensor in -> CUDA
+        tensor out."""
         import torch
-        was_numpy = not _is_torch(maps)
-        x = torch.as_tensor(np.ascontiguousarray(maps, dtype=np.float64), device="cuda") if was_numpy else maps
-        x = self._dev_in(x, self.isize)
-        out = self.fwadj_into(x, torch.empty(self.ishape, dtype=x.dtype, device=x.device))
-        return out.cpu().numpy().astype(np.float64) if was_numpy else out
+        if _is_torch(maps):
+            x = self._dev_in(maps, self.isize)
+            return self.fwadj_into(x, torch.empty(self.ishape, dtype=x.dtype, device=x.device))
+        host = torch.from_numpy(np.ascontiguousarray(np.asarray(maps, dtype=np.float64).reshape(self.ishape)))
+        dt = self._torch_dtype()
+        if getattr(self, "_fwadj_io", None) is None:
+            self._fwadj_io = (torch.empty(self.ishape, dtype=torch.float64, device="cuda"),
+                              torch.empty(self.ishape, dtype=dt, device="cuda"))
+        stage, q = self._fwadj_io
+        stage.copy_(host, non_blocking=True)
+        x = stage if dt == torch.float64 else stage.to(dt)
+        self.fwadj_into(x.reshape(-1), q)
+        res = torch.from_numpy(out).reshape(self.ishape) if out is not None else torch.empty(self.ishape, dtype=torch.float64)
+        res.copy_(q)  # device -> host (converts fp32 results), synchronises
+        return out if out is not None else res.numpy()
 
     def fwadj_into(self, x, out):
         """out = H^T H x on device tensors.  Sharded (partial) models exchange the detector vector

@@ -89,6 +89,12 @@ def test_device_tensors_and_fwadj(built):
     assert rel(y.cpu().numpy(), gpu.forward(cfg.maps)) <= 1e-14
     q = gpu.fwadj(x)
     assert rel(q.cpu().numpy(), gpu.adjoint(gpu.forward(cfg.maps))) <= 1e-13
+    # host path of the same LinOp call: numpy in -> numpy out, optionally into a caller-provided array
+    q_np = gpu.fwadj(cfg.maps)
+    assert isinstance(q_np, np.ndarray) and q_np.shape == gpu.ishape and q_np.dtype == np.float64
+    assert rel(q_np, q.cpu().numpy()) <= 1e-15
+    into = np.empty(gpu.ishape)
+    assert gpu.fwadj(cfg.maps, out=into) is into and np.array_equal(into, q_np)
     # deterministic: bitwise-identical across runs (no atomics anywhere on the path)
     assert torch.equal(q, gpu.fwadj(x))
     assert torch.equal(gpu.adjoint(y), gpu.adjoint(y))
