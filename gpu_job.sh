@@ -1,3 +1,2 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -3 gpurun_out/bench_default.err
+python -m pytest tests/test_gpu_full_size.py tests/test_gpu_fft.py -x -q --durations=8 2>&1 | tail -25
