@@ -34,6 +34,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef SURFH_FFT_TWIDDLE_CHAIN
+#define SURFH_FFT_TWIDDLE_CHAIN 1
+#endif
+
 namespace surfh {
 
 // Geometry of one chirp-z length M for arithmetic type T.
@@ -56,6 +60,11 @@ template <typename T, int M> struct FftK {
     static constexpr int N_TW = M + 16 * R3;    // tw1[q*TT + t] then tw2[q2*R3 + n2]
     static constexpr int HALF = M / 2;          // the transform length N must be <= HALF
     static constexpr int SLOTS = 8;             // staged complex-sized elements per thread
+    // The kernels are bound by shared-memory (LSU) wavefronts while the FP64 pipe has slack, so in fp64 the
+    // inter-stage twiddles w^q, q = 1..15, are generated from the one loaded value w by a multiplication
+    // chain (+14 complex products, -14 table reads of 16 bytes per stage; error <= 15 ulp on |w^q| = 1).
+    // fp32 keeps the table: its FMA pipe is not idle and its tolerance is tighter relative to eps.
+    static constexpr bool CHAIN = SURFH_FFT_TWIDDLE_CHAIN && sizeof(T) == 8;
     // shared-memory layout, in units of C
     static constexpr int OFF_TW = 0;
     static constexpr int OFF_FILT = OFF_TW + N_TW;
@@ -283,11 +292,22 @@ __device__ __forceinline__ void fft_fwd(cplx_t<T>* v, cplx_t<T>* buf, const FftT
     if (HALF_IN) dft16_in8<false>(v);  // v[8..15] are the zero padding
     else dft16<false>(v);
     if (PRE_SYNC) th.sync();
+    if (K::CHAIN) {
+        const C w = tw[TT + th.t];
+        C pw = w;
+        buf[th.t] = v[0];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        C x = v[q];
-        if (q) x = cmul(x, tw[q * TT + th.t]);
-        buf[q * TT + th.t] = x;
+        for (int q = 1; q < 16; ++q) {
+            buf[q * TT + th.t] = cmul(v[q], pw);
+            if (q < 15) pw = cmul(pw, w);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            C x = v[q];
+            if (q) x = cmul(x, tw[q * TT + th.t]);
+            buf[q * TT + th.t] = x;
+        }
     }
     th.sync();
     C* blk = buf + th.q * TT;
@@ -295,8 +315,18 @@ __device__ __forceinline__ void fft_fwd(cplx_t<T>* v, cplx_t<T>* buf, const FftT
     for (int m = 0; m < 16; ++m) v[m] = blk[th.n2 + R3 * m];
     dft16<false>(v);
     if (R3 > 1) {
+        if (K::CHAIN) {
+            const C w = tw[M + R3 + th.n2];
+            C pw = w;
 #pragma unroll
-        for (int q2 = 1; q2 < 16; ++q2) v[q2] = cmul(v[q2], tw[M + q2 * R3 + th.n2]);
+            for (int q2 = 1; q2 < 16; ++q2) {
+                v[q2] = cmul(v[q2], pw);
+                if (q2 < 15) pw = cmul(pw, w);
+            }
+        } else {
+#pragma unroll
+            for (int q2 = 1; q2 < 16; ++q2) v[q2] = cmul(v[q2], tw[M + q2 * R3 + th.n2]);
+        }
         group_transpose<R3>(v, th.n2);
 #pragma unroll
         for (int c = 0; c < 16 / R3; ++c) dft_r<false, R3>(v + c * R3);
@@ -313,8 +343,18 @@ __device__ __forceinline__ void fft_inv(cplx_t<T>* v, cplx_t<T>* buf, const FftT
 #pragma unroll
         for (int c = 0; c < 16 / R3; ++c) dft_r<true, R3>(v + c * R3);
         group_transpose<R3>(v, th.n2);
+        if (K::CHAIN) {
+            const C w = tw[M + R3 + th.n2];
+            C pw = w;
 #pragma unroll
-        for (int q2 = 1; q2 < 16; ++q2) v[q2] = cmul_conj(tw[M + q2 * R3 + th.n2], v[q2]);
+            for (int q2 = 1; q2 < 16; ++q2) {
+                v[q2] = cmul_conj(pw, v[q2]);
+                if (q2 < 15) pw = cmul(pw, w);
+            }
+        } else {
+#pragma unroll
+            for (int q2 = 1; q2 < 16; ++q2) v[q2] = cmul_conj(tw[M + q2 * R3 + th.n2], v[q2]);
+        }
     }
     dft16<true>(v);
     // these are the very locations this thread read in fft_fwd: no barrier needed before the writes
@@ -322,11 +362,22 @@ __device__ __forceinline__ void fft_inv(cplx_t<T>* v, cplx_t<T>* buf, const FftT
 #pragma unroll
     for (int m = 0; m < 16; ++m) blk[th.n2 + R3 * m] = v[m];
     th.sync();
+    if (K::CHAIN) {
+        const C w = tw[TT + th.t];
+        C pw = w;
+        v[0] = buf[th.t];
 #pragma unroll
-    for (int qq = 0; qq < 16; ++qq) {
-        C x = buf[qq * TT + th.t];
-        if (qq) x = cmul_conj(tw[qq * TT + th.t], x);
-        v[qq] = x;
+        for (int qq = 1; qq < 16; ++qq) {
+            v[qq] = cmul_conj(pw, buf[qq * TT + th.t]);
+            if (qq < 15) pw = cmul(pw, w);
+        }
+    } else {
+#pragma unroll
+        for (int qq = 0; qq < 16; ++qq) {
+            C x = buf[qq * TT + th.t];
+            if (qq) x = cmul_conj(tw[qq * TT + th.t], x);
+            v[qq] = x;
+        }
     }
     if (HALF_OUT) dft16_out8<true>(v);  // only x[t + TT*m], m < 8, is wanted
     else dft16<true>(v);
