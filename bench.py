@@ -156,8 +156,11 @@ def band_summaries(cfg):
         la, lb = geometry.local_axes(band.fov, cfg.step_degree, geometry.N_MARGIN_PIX * cfg.step_degree)
         _, _, na, nbw, _ = geometry.slit_layout(band, cfg.beta_axis, la, lb, srf)
         wsl = band.wslice(cfg.wavelength_axis, geometry.WAVE_MARGIN_UM)
+        ang = np.deg2rad(band.fov.angle)
+        hull_rows = len(la) * abs(np.cos(ang)) + len(lb) * abs(np.sin(ang)) + 6  # rotated local grid + dithers
         out.append(dict(wave_start=wsl.start, n_wave=wsl.stop - wsl.start, n_det=band.n_wavel, nb=nbw,
-                        n_pointing=len(pts), n_slit=band.n_slit, na=na, local_a=len(la), local_b=len(lb)))
+                        n_pointing=len(pts), n_slit=band.n_slit, na=na, local_a=len(la), local_b=len(lb),
+                        hull_rows=float(hull_rows)))
     return out
 
 
@@ -313,6 +316,13 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     value = 1e3 / ms_step
 
+    # per-rank kernel time of one application (sum of the stage events): load balance of the wavelength shards
+    rank_ms = torch.zeros(world, dtype=torch.float64, device=dev)
+    rank_ms[rank] = sum(s["ms"] for s in stages) / args.steps
+    if comm:
+        comm.allreduce_sum(rank_ms)
+    rank_ms = [float(v) for v in rank_ms.cpu()]
+
     # ---- CG iterations
     y = model.forward(x)
     cg = fusion_CT.DeviceCG(model, y, 1.0, 5e3, comm=comm)
@@ -425,6 +435,7 @@ def run_b200(args):
         "dtype": "f64" if esz == 8 else "f32", "data": "synthetic", "config": workload_description(cfg, args.dtype, args),
         "cg_iters_per_s": cg_iters, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "stages": stage_rows, "cpu_baseline": cpu,
+        "per_rank_kernel_ms": rank_ms, "exchange_and_idle_ms": ms_step - max(rank_ms),
         "setup_s": setup_s, "lambda_range_rank0": lam_range, "workspace_gb": model.workspace_bytes() / 1e9,
     }
     emit(line)

@@ -60,20 +60,27 @@ def partition_lambda(cost_per_lambda: Sequence[float], world_size: int) -> List[
 
 
 def lambda_costs(n_lambda: int, bands: Sequence[dict], n_pix: int, bytes_per_real: int = 8) -> np.ndarray:
-    """Per-wavelength cost model.  `bands`: dicts with wave_start, n_wave, n_det, nb, n_pointing, n_slit,
-    na, local_a, local_b.  A covered wavelength costs one FFT pair + OTF streams (HBM-bound), plus, per
-    band covering it, its share of the gather/scatter and of the spectral contraction (FMA-bound)."""
+    """Per-wavelength cost model in seconds, calibrated on a B200 with the C4 workload in fp64
+    (profiles/r01_app_kernels.md); only the ratios matter for the partition.  `bands`: dicts with
+    wave_start, n_wave, n_det, nb, n_pointing, n_slit, na, local_a, local_b and, optionally, hull_rows
+    (cube rows the band's field of view touches; default: every row).  A covered wavelength costs
+      * the two column passes of its 2-D FFT pair, the two template x OTF streams and the memset,
+      * the two row passes, proportional to the row pairs in the hull of the bands covering it,
+    plus, per band covering it, its share of the gather / scatter index streams (2.2 TB/s effective)
+    and of the spectral contraction (27.6 TFLOP/s on the FP64 tensor pipe)."""
+    scale = (n_pix / 501.0) ** 2 * (bytes_per_real / 8.0) ** 0.8
+    col_passes, streams, per_pair = 4.8e-6 * scale, 1.6e-6 * scale, 21.2e-9 * (n_pix / 501.0) * (bytes_per_real / 8.0) ** 0.8
+    gemm_rate = 2.76e13 if bytes_per_real == 8 else 1.7e13
     cost = np.zeros(n_lambda)
-    covered = np.zeros(n_lambda, dtype=bool)
-    nf = n_pix * (n_pix // 2 + 1)
-    plane_cost = 18.0e-6 * (n_pix / 501.0) ** 2 * (bytes_per_real / 8.0)  # measured: ~9 us per 501^2 fp64 FFT
+    hull = np.zeros(n_lambda)
     for b in bands:
         sl = slice(b["wave_start"], b["wave_start"] + b["n_wave"])
-        covered[sl] = True
+        hull[sl] = np.maximum(hull[sl], min(n_pix, b.get("hull_rows", n_pix)))
         flops = 4.0 * b["n_det"] * b["nb"] * b["n_pointing"] * b["n_slit"] * b["na"]
         stream = 2.0 * b["n_pointing"] * (b["local_a"] * b["local_b"] + b["n_slit"] * b["na"] * b["nb"]) * bytes_per_real
-        cost[sl] += flops / 2.7e13 + stream / 1.5e12
-    cost[covered] += plane_cost + 4.0 * nf * 2 * bytes_per_real / 6.0e12
+        cost[sl] += flops / gemm_rate + stream / 2.2e12
+    covered = hull > 0
+    cost[covered] += col_passes + streams + per_pair * (hull[covered] / 2.0 + 1.0)
     return cost
 
 
