@@ -165,6 +165,10 @@ int surfh_adjoint_host(surfh_handle h, const double* y, double* x, int32_t mode)
  * Replaces the NpDiff_r / NpDiff_c hessp terms (fusion_CT.py:16-43) and the <d,Qd> dot. */
 int surfh_cg_regularise_dot(surfh_handle h, const void* d, void* q, double mu_s, double mu_r, double* s,
                             void* stream);
+/* out = a*out + b*L(x) on n_maps*[n_alpha,n_beta] vectors, L = circular 5-point Laplacian (x != out;
+ * a == 0 does not read out).  Replaces Difference_Operator_Joint.D / D_t / DtD = L, L, L.L
+ * (fusion_CT.py:45-63: the udft.laplacian(2) impulse response applied in Fourier space). */
+int surfh_laplacian_axpby(surfh_handle h, const void* x, void* out, double a, double b, void* stream);
 /* r = b - q ; d = r ; s[0] = <r,r> ; history[0] = s[0] ; counter = 0 (lcg initialisation) */
 int surfh_cg_start(surfh_handle h, const void* b, const void* q, void* r, void* d, double* s, void* stream);
 /* alpha = s[0]/s[1]; x += alpha d; r -= alpha q; rho' = <r,r>; beta = rho'/rho; d = r + beta d;

@@ -333,3 +333,34 @@ def solve_lcg(model, y, mu_spectro, mu_reg, niter, value_init=0.0, tol=1e-12, ca
             QuadObjective(diff_r, diff_r_t, hyper=mu_reg),
             QuadObjective(diff_c, diff_c_t, hyper=mu_reg)]
     return lcg(objs, init, tol=tol, max_iter=niter, callback=callback, refresh=refresh)
+
+
+def criterion_joint(model, y, x, mu_spectro, mu_reg):
+    """get_crit_val with gradient='joint' (fusion_CT.py:249-250)."""
+    from .thirdparty import laplacian2_circular
+    data_term = mu_spectro * np.sum((y - model.forward(x)) ** 2)
+    return (data_term + mu_reg * np.sum(laplacian2_circular(x) ** 2)) / 2
+
+
+def objectives(model, y, mu_spectro, mu_reg, gradient="separated"):
+    """The QuadObjective list QuadCriterion_MRS.run_method builds (fusion_CT.py:130-162)."""
+    from .thirdparty import QuadObjective, laplacian2_circular
+    objs = [QuadObjective(model.forward, model.adjoint, data=y, hyper=mu_spectro, name="Spectro")]
+    if gradient == "joint":
+        dtd = lambda v: laplacian2_circular(laplacian2_circular(v))  # noqa: E731
+        objs.append(QuadObjective(laplacian2_circular, laplacian2_circular, dtd, hyper=mu_reg, name="Reg joint"))
+    else:
+        objs += [QuadObjective(diff_r, diff_r_t, hyper=mu_reg), QuadObjective(diff_c, diff_c_t, hyper=mu_reg)]
+    return objs
+
+
+def solve(model, y, mu_spectro, mu_reg, niter, method="lcg", gradient="separated", value_init=0.0, tol=1e-12,
+          callback=None, refresh=50):
+    """QuadCriterion_MRS.run_method(method, ...) (fusion_CT.py:118-238): 'lcg' or, for any other name,
+    mmmg; 'separated' or 'joint' gradients."""
+    from .thirdparty import lcg, mmmg
+    init = (np.ones(model.ishape) * value_init) if np.isscalar(value_init) else np.asarray(value_init)
+    objs = objectives(model, y, mu_spectro, mu_reg, gradient)
+    if method == "lcg":
+        return lcg(objs, init, tol=tol, max_iter=niter, callback=callback, refresh=refresh)
+    return mmmg(objs, init, tol=tol, max_iter=niter, callback=callback)

@@ -228,3 +228,73 @@ def lcg(objv_list, x0, tol=1e-4, max_iter=500, min_iter=0, callback=None, refres
             break
     res["x"] = res["x"].reshape(shape)
     return res
+
+
+def mmmg(objv_list, x0, tol=1e-4, max_iter=500, min_iter=0, callback=None):
+    """qmm.mmmg (Majorize-Minimize Memory Gradient, "3MG") as called by
+    surfh/Simulation/fusion_CT.py:196-197 for any method other than 'lcg'.  PARITY UNPINNED: qmm is
+    not installed here and the reference holds no solve trace; restated from the published algorithm
+    (Chouzenoux, Idier, Moussaoui 2011; qmm 0.18 `mmmg`):
+
+        move = 0; op_directions_i = [V_i move, V_i move]; step = (1, 1)
+        each iteration:
+            grad = sum_i gradient_i(x)                      (hyper_i V_i^T (V_i x - data_i))
+            grad_norm.append(|grad|^2); stop when grad_norm[-1] < x.size * tol (after min_iter)
+            directions = [-grad, move]                      (n x 2)
+            op_directions_i = [V_i(-grad), op_directions_i @ step]
+            step = -lstsq(sum_i hyper_i op_directions_i^T op_directions_i, directions^T grad)
+            move = directions @ step;  x += move;  callback(res)
+
+    For QuadObjective the majorant curvature `norm_mat_major` is hyper * vecs^T vecs, i.e. the exact
+    2 x 2 Hessian restricted to the plane, so every iteration is an exact plane search.
+    """
+    if isinstance(objv_list, QuadObjective):
+        objv_list = [objv_list]
+    shape = np.shape(x0)
+    vect = lambda op, v: np.reshape(op(np.reshape(v, shape)), (-1, 1))  # noqa: E731
+
+    res = OptimizeResult()
+    res["x"] = np.array(x0, dtype=np.float64).reshape((-1, 1)).copy()
+    res["success"] = False
+    res["status"] = 99
+    res["nit"] = max_iter
+    res["grad_norm"] = []
+    res["time"] = [time.time()]
+    move = np.zeros_like(res["x"])
+    op_directions = [np.tile(vect(obj.operator, move), 2) for obj in objv_list]
+    step = np.ones((2, 1))
+    for iteration in range(max_iter):
+        arr = res["x"].reshape(shape)
+        grad = np.zeros_like(res["x"])
+        for obj in objv_list:
+            grad = grad + np.reshape(obj.gradient(arr), (-1, 1))
+        res["grad_norm"].append(float(np.sum(grad ** 2)))
+        if res["grad_norm"][-1] < res["x"].size * tol and iteration >= min_iter:
+            res["success"] = True
+            res["status"] = 1
+            res["nit"] = iteration
+            break
+        directions = np.c_[-grad, move]
+        op_directions = [np.c_[vect(obj.operator, directions[:, 0]), prev @ step]
+                         for obj, prev in zip(objv_list, op_directions)]
+        mat = sum(obj.hyper * (od.T @ od) for obj, od in zip(objv_list, op_directions))
+        step = -np.linalg.lstsq(mat, directions.T @ grad, rcond=None)[0]
+        move = directions @ step
+        res["x"] += move
+        res["time"].append(time.time())
+        if callback is not None:
+            callback(res)
+    res["x"] = res["x"].reshape(shape)
+    return res
+
+
+def laplacian2_circular(x):
+    """udft.laplacian(2) = [[0,-1,0],[-1,4,-1],[0,-1,0]] applied the way
+    surfh/Simulation/fusion_CT.py:45-63 (Difference_Operator_Joint.D) does: ir2fr of the CENTRED impulse
+    response, product in Fourier space, inverse transform -- i.e. the circular convolution
+    4 x - x[i-1] - x[i+1] - x[j-1] - x[j+1] on the last two axes (the kernel is symmetric, so D_t = D and
+    DtD = D D).  Evaluated here through the same Fourier route, with ir2fr as restated above."""
+    kernel = np.array([[0.0, -1.0, 0.0], [-1.0, 4.0, -1.0], [0.0, -1.0, 0.0]])
+    shape = x.shape[-2:]
+    d_freq = ir2fr(kernel, shape)
+    return np.fft.irfftn(d_freq * np.fft.rfftn(x, axes=(-2, -1)), s=shape, axes=(-2, -1))

@@ -28,7 +28,7 @@ SYMBOLS = [
     "surfh_abi_version", "surfh_create", "surfh_set_otf", "surfh_add_band", "surfh_finalize", "surfh_destroy",
     "surfh_last_error", "surfh_input_size", "surfh_output_size", "surfh_workspace_bytes", "surfh_forward",
     "surfh_adjoint", "surfh_fwadj", "surfh_maps_to_cube", "surfh_forward_host", "surfh_adjoint_host",
-    "surfh_cg_regularise_dot", "surfh_cg_start", "surfh_cg_update", "surfh_cg_refresh", "surfh_criterion_terms",
+    "surfh_cg_regularise_dot", "surfh_laplacian_axpby", "surfh_cg_start", "surfh_cg_update", "surfh_cg_refresh", "surfh_criterion_terms",
     "surfh_launch_count", "surfh_own_launch_count", "surfh_profile_enable", "surfh_profile_read", "surfh_rfft2",
 ]
 
@@ -94,6 +94,7 @@ def load() -> C.CDLL:
         "surfh_forward_host": (C.c_int, [vp, vp, vp]),
         "surfh_adjoint_host": (C.c_int, [vp, vp, vp, i32]),
         "surfh_cg_regularise_dot": (C.c_int, [vp, vp, vp, dbl, dbl, vp, vp]),
+        "surfh_laplacian_axpby": (C.c_int, [vp, vp, vp, dbl, dbl, vp]),
         "surfh_cg_start": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "surfh_cg_update": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "surfh_cg_refresh": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),

@@ -79,6 +79,7 @@ struct surfh_model {
     virtual void forward_host(const double* x, double* y) = 0;
     virtual void adjoint_host(const double* y, double* x, int mode) = 0;
     virtual void cg_regularise_dot(const void* d, void* q, double mu_s, double mu_r, double* s, cudaStream_t st) = 0;
+    virtual void laplacian_axpby(const void* x, void* out, double a, double b, cudaStream_t st) = 0;
     virtual void cg_start(const void* b, const void* q, void* r, void* d, double* s, cudaStream_t st) = 0;
     virtual void cg_update(void* x, void* r, void* d, const void* q, double* s, cudaStream_t st) = 0;
     virtual void cg_refresh(int phase, void* x, void* r, void* d, const void* b, const void* qx, double* s,
@@ -820,6 +821,14 @@ template <typename T> struct ModelImpl : surfh_model {
                                                                        mu_r, s, scratch());
         SURFH_CUDA(cudaGetLastError());
     }
+    void laplacian_axpby(const void* x, void* out, double a, double b, cudaStream_t st) override {
+        SURFH_REQUIRE(x && out && x != out, "laplacian: NULL or aliased buffers");
+        const size_t n = (size_t)input_size();
+        Scope sc(this, ST_CG, st, 3.0 * n * sizeof(T), 7.0 * n, 1, true);
+        laplacian_axpby_kernel<T><<<cg_grid(n), kCgThreads, 0, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<T*>(out),
+                                                                     n_maps(), Na, Nb, a, b);
+        SURFH_CUDA(cudaGetLastError());
+    }
     void cg_start(const void* b, const void* q, void* r, void* d, double* s, cudaStream_t st) override {
         SURFH_REQUIRE(b && q && r && d && s, "NULL buffer");
         const size_t n = (size_t)input_size();
@@ -1036,6 +1045,10 @@ int surfh_adjoint_host(surfh_handle h, const double* y, double* x, int32_t mode)
 
 int surfh_cg_regularise_dot(surfh_handle h, const void* d, void* q, double mu_s, double mu_r, double* s, void* stream) {
     SURFH_API_BEGIN(h) h->cg_regularise_dot(d, q, mu_s, mu_r, s, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+int surfh_laplacian_axpby(surfh_handle h, const void* x, void* out, double a, double b, void* stream) {
+    SURFH_API_BEGIN(h) h->laplacian_axpby(x, out, a, b, (cudaStream_t)stream);
     SURFH_API_END(h)
 }
 int surfh_cg_start(surfh_handle h, const void* b, const void* q, void* r, void* d, double* s, void* stream) {

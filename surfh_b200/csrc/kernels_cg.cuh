@@ -72,6 +72,25 @@ cg_regularise_dot_kernel(const T* __restrict__ d, T* __restrict__ q, int n_maps,
     if (finish_reduction(b, sc.partial, sc.ticket, smem, total)) s[1] = total;
 }
 
+// out = a * out + b * L(x),  L = circular 5-point Laplacian of every map (the centred impulse response
+// udft.laplacian(2) that Difference_Operator_Joint applies in Fourier space, fusion_CT.py:45-63;
+// also D_r^T D_r + D_c^T D_c).  a == 0 never reads `out`.
+template <typename T>
+__global__ void __launch_bounds__(kCgThreads)
+laplacian_axpby_kernel(const T* __restrict__ x, T* __restrict__ out, int n_maps, int na, int nb, double a, double b) {
+    const size_t npix = (size_t)na * nb, n = npix * n_maps;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t k = idx / npix, p = idx - k * npix;
+        const int i = (int)(p / nb), j = (int)(p - (size_t)i * nb);
+        const T* m = x + k * npix;
+        const int im = i == 0 ? na - 1 : i - 1, ip = i == na - 1 ? 0 : i + 1;
+        const int jm = j == 0 ? nb - 1 : j - 1, jp = j == nb - 1 ? 0 : j + 1;
+        const double lap = 4.0 * (double)m[p] - (double)m[(size_t)im * nb + j] - (double)m[(size_t)ip * nb + j] -
+                           (double)m[(size_t)i * nb + jm] - (double)m[(size_t)i * nb + jp];
+        out[idx] = (T)((a == 0.0 ? 0.0 : a * (double)out[idx]) + b * lap);
+    }
+}
+
 // r = b - q ; d = r ; s[0] = <r,r> ; history[0] = s[0] ; s[4] = 0
 template <typename T>
 __global__ void __launch_bounds__(kCgThreads)

@@ -12,8 +12,13 @@ Reference interface mirrored (paths relative to /root/reference):
     NpDiff_r, NpDiff_c                       surfh/Simulation/fusion_CT.py:16-43
     QuadCriterion_MRS(...).run_method(...)   surfh/Simulation/fusion_CT.py:67-238
     QuadCriterion_MRS.get_crit_val           surfh/Simulation/fusion_CT.py:242-265
-    qmm.lcg (third party, restated; recurrences and stopping rule as documented in
+    Difference_Operator_Joint (gradient="joint")   surfh/Simulation/fusion_CT.py:45-63
+    qmm.lcg, qmm.mmmg (third party, restated; recurrences and stopping rules as documented in
     the test oracle's thirdparty module -- parity with qmm itself is unpinned)
+
+With gradient="joint" the prior is mu_reg * ||L x||^2, L = the circular 5-point Laplacian (the
+udft.laplacian(2) impulse response the reference applies in Fourier space), i.e. Q_reg = mu_reg L L;
+with gradient="separated" Q_reg = mu_reg (D_r^T D_r + D_c^T D_c) = mu_reg L.
 """
 from __future__ import annotations
 
@@ -67,8 +72,12 @@ def _torch():
 class DeviceCG:
     """Device-resident state of one lcg solve on a `spectroSigRLSCT` model."""
 
-    def __init__(self, model, y, mu_spectro: float, mu_reg: float, comm=None):
+    def __init__(self, model, y, mu_spectro: float, mu_reg: float, comm=None, gradient: str = "separated"):
         torch = _torch()
+        if gradient not in ("separated", "joint"):
+            raise ValueError("gradient must be 'separated' or 'joint'")
+        self.gradient = gradient
+        self._lap = None
         self.model = model
         self.lib = model._lib
         self.h = model.handle
@@ -95,11 +104,26 @@ class DeviceCG:
     def _check(self, code):
         _capi.check(self.h, code)
 
+    def laplacian(self, x, out, a: float = 0.0, b: float = 1.0):
+        """out = a * out + b * L x (every map, circular)."""
+        self._check(self.lib.surfh_laplacian_axpby(self.h, x.data_ptr(), out.data_ptr(), float(a), float(b),
+                                                   self._stream()))
+        return out
+
     def hessp(self, v, out):
-        """out = mu_s H^T H v + mu_r (D_r^T D_r + D_c^T D_c) v ; s[1] = <v, out>."""
+        """out = mu_s H^T H v + mu_r R v ; s[1] = <v, out>, with R = L ('separated': D_r^T D_r + D_c^T D_c)
+        or R = L L ('joint')."""
         self.model.fwadj_into(v, out)
-        self._check(self.lib.surfh_cg_regularise_dot(self.h, v.data_ptr(), out.data_ptr(), self.mu_s, self.mu_r,
-                                                     self.s.data_ptr(), self._stream()))
+        if self.gradient == "separated":
+            self._check(self.lib.surfh_cg_regularise_dot(self.h, v.data_ptr(), out.data_ptr(), self.mu_s, self.mu_r,
+                                                         self.s.data_ptr(), self._stream()))
+            return
+        if self._lap is None:
+            self._lap = _torch().empty_like(out)
+        self.laplacian(v, self._lap)
+        self.laplacian(self._lap, out, a=self.mu_s, b=self.mu_r)      # out = mu_s H^T H v + mu_r L L v
+        self._check(self.lib.surfh_cg_regularise_dot(self.h, v.data_ptr(), out.data_ptr(), 1.0, 0.0,
+                                                     self.s.data_ptr(), self._stream()))  # s[1] = <v, out>
 
     def start(self, x0, max_iter: int):
         torch = _torch()
@@ -149,17 +173,20 @@ class DeviceCG:
         self._check(self.lib.surfh_criterion_terms(self.h, self.y.data_ptr(), hx.data_ptr(), n, x.data_ptr(),
                                                    out.data_ptr(), self._stream()))
         total += out
+        if self.gradient == "joint":  # ||L x||^2 instead of ||D_r x||^2 + ||D_c x||^2
+            lx = self.laplacian(x, torch.empty_like(x))
+            total[1] = torch.dot(lx.double(), lx.double())
         t = total.cpu().numpy()
         return float((self.mu_s * t[0] + self.mu_r * t[1]) / 2)
 
 
 def lcg(model, y, mu_spectro=1.0, mu_reg=1.0, x0=None, tol=1e-4, max_iter=500, min_iter=0,
         callback: Optional[Callable] = None, refresh: int = REFRESH_PERIOD, check_every: int = 10, comm=None,
-        numpy_result: bool = True) -> OptimizeResult:
+        numpy_result: bool = True, gradient: str = "separated") -> OptimizeResult:
     """Linear CG on the device.  `res.x` is a flat device tensor while iterating (callbacks may
     `.reshape` it) and, at return, a numpy array of the model's input shape (`numpy_result`)."""
     torch = _torch()
-    cg = DeviceCG(model, y, mu_spectro, mu_reg, comm=comm)
+    cg = DeviceCG(model, y, mu_spectro, mu_reg, comm=comm, gradient=gradient)
     if x0 is None:
         x0 = np.zeros(model.ishape)
     cg.start(x0, max_iter)
@@ -187,9 +214,75 @@ def lcg(model, y, mu_spectro=1.0, mu_reg=1.0, x0=None, tol=1e-4, max_iter=500, m
     return res
 
 
+def mmmg(model, y, mu_spectro=1.0, mu_reg=1.0, x0=None, tol=1e-4, max_iter=500, min_iter=0,
+         callback: Optional[Callable] = None, comm=None, numpy_result: bool = True,
+         gradient: str = "separated") -> OptimizeResult:
+    """qmm.mmmg (3MG: majorize-minimize memory gradient) for the quadratic objectives of
+    `QuadCriterion_MRS.run_method(method != 'lcg')` (fusion_CT.py:194-197), on the device.
+
+    Every iteration minimises J exactly over the plane spanned by -grad and the previous move (for
+    quadratic objectives the quadratic majorant is J itself):
+        g = Q x - b;  D = [-g, m];  M = sum_i hyper_i (V_i D)^T (V_i D) (2x2);  step = -lstsq(M, D^T g);
+        m = D step;  x += m;  V_i m is carried by linearity (V_i D) step, as qmm does.
+    One H^T H application (gradient) and one H application (H g) per iteration; the 2x2 system is solved
+    on the host (five scalars cross PCIe per iteration).  Stops when |g|^2 < x.size * tol (qmm's rule).
+    """
+    torch = _torch()
+    cg = DeviceCG(model, y, mu_spectro, mu_reg, comm=comm, gradient=gradient)
+    if x0 is None:
+        x0 = np.zeros(model.ishape)
+    cg.start(x0, 1)                       # b = mu_s H^T y; x, q = Q x, r = b - Q x
+    x, b = cg.x, cg.b
+    n = x.numel()
+    move = torch.zeros_like(x)
+    h_move = torch.zeros(model.osize, dtype=x.dtype, device=x.device)   # H m
+    q = torch.empty_like(x)
+    lap_g, lap_m = torch.empty_like(x), torch.empty_like(x)
+    res = OptimizeResult(x=x, success=False, status=99, nit=max_iter, grad_norm=[], time=[time.time()],
+                         message="maximum number of iterations reached")
+
+    def reg_gram(u, lu, v, lv):
+        """<u, R v> with R = L (separated) or L L (joint), given lu = L u and lv = L v."""
+        return torch.dot(u, lv) if gradient == "separated" else torch.dot(lu, lv)
+
+    for iteration in range(max_iter):
+        cg.hessp(x, q)                                   # q = Q x
+        g = q.sub_(b)                                    # gradient, in place
+        gn = float(torch.dot(g, g))
+        res["grad_norm"].append(gn)
+        if gn < n * tol and iteration >= min_iter:
+            res["success"], res["status"], res["nit"] = True, 1, iteration
+            res["message"] = "gradient norm below tolerance"
+            break
+        h_g = model.forward(g.reshape(model.ishape))     # H g  (the direction is -g: signs handled below)
+        cg.laplacian(g, lap_g)
+        cg.laplacian(move, lap_m)
+        # M = mu_s [H d_i . H d_j] + mu_r [d_i . R d_j]  for d_0 = -g, d_1 = m
+        m00 = cg.mu_s * torch.dot(h_g, h_g) + cg.mu_r * reg_gram(g, lap_g, g, lap_g)
+        m01 = -(cg.mu_s * torch.dot(h_g, h_move) + cg.mu_r * reg_gram(g, lap_g, move, lap_m))
+        m11 = cg.mu_s * torch.dot(h_move, h_move) + cg.mu_r * reg_gram(move, lap_m, move, lap_m)
+        rhs = torch.stack([-torch.dot(g, g), torch.dot(move, g)])
+        vals = torch.stack([m00, m01, m11]).double().cpu().numpy()
+        rhs = rhs.double().cpu().numpy()
+        mat = np.array([[vals[0], vals[1]], [vals[1], vals[2]]])
+        step = -np.linalg.lstsq(mat, rhs, rcond=None)[0]
+        # m = D step ; H m = (H D) step
+        move.mul_(float(step[1])).add_(g, alpha=-float(step[0]))
+        h_move.mul_(float(step[1])).add_(h_g, alpha=-float(step[0]))
+        x.add_(move)
+        res["time"].append(time.time())
+        if callback is not None:
+            callback(res)
+    torch.cuda.current_stream().synchronize()
+    res["x"] = x.reshape(model.ishape).cpu().numpy().astype(np.float64) if numpy_result else x.reshape(model.ishape)
+    res["solver"] = cg
+    return res
+
+
 class QuadCriterion_MRS:
-    """Same constructor and `run_method` as the reference class; 'separated' gradients and the
-    'lcg' method run on the device.  ('joint' gradients and qmm.mmmg are SURVEY section 8f items.)"""
+    """Same constructor and `run_method` as the reference class, run on the device: gradient =
+    'separated' (NpDiff_r / NpDiff_c) or 'joint' (Difference_Operator_Joint), method = 'lcg' or anything
+    else -> mmmg, exactly like the reference's dispatch (fusion_CT.py:194-197)."""
 
     def __init__(self, mu_spectro, y_spectro, model_spectro, mu_reg, printing=False, gradient="separated",
                  comm=None):
@@ -204,10 +297,11 @@ class QuadCriterion_MRS:
             assert len(mu_reg) == self.n_spec
         shape_target = model_spectro.ishape[1:]
         self.shape_of_output = (self.n_spec, shape_target[0], shape_target[1])
-        if gradient != "separated":
-            raise NotImplementedError("only gradient='separated' is implemented on the device")
-        self.npdiff_r = NpDiff_r(self.shape_of_output)
-        self.npdiff_c = NpDiff_c(self.shape_of_output)
+        if gradient not in ("separated", "joint"):
+            raise ValueError("gradient must be 'separated' or 'joint'")
+        if gradient == "separated":
+            self.npdiff_r = NpDiff_r(self.shape_of_output)
+            self.npdiff_c = NpDiff_c(self.shape_of_output)
         self.L_mu = np.copy(mu_reg) if isinstance(mu_reg, (list, np.ndarray)) else np.ones(self.n_spec) * mu_reg
         self.printing = printing
         self.gradient = gradient
@@ -217,14 +311,13 @@ class QuadCriterion_MRS:
 
     def _solver(self) -> DeviceCG:
         if self._cg is None:
-            self._cg = DeviceCG(self.model_spectro, self.y_spectro, self.mu_spectro, self.mu_reg, comm=self.comm)
+            self._cg = DeviceCG(self.model_spectro, self.y_spectro, self.mu_spectro, self.mu_reg, comm=self.comm,
+                                gradient=self.gradient)
         return self._cg
 
     def run_method(self, method="lcg", maximum_iterations=10, tolerance=1e-12, calc_crit=False, perf_crit=None,
                    value_init=0.5):
         assert isinstance(self.mu_reg, (int, float))
-        if method != "lcg":
-            raise NotImplementedError("only method='lcg' is implemented on the device")
         if isinstance(value_init, (float, int)):
             init = np.ones(self.shape_of_output) * value_init
         else:
@@ -257,8 +350,9 @@ class QuadCriterion_MRS:
         else:
             callback = None
         t1 = time.time()
-        res = lcg(self.model_spectro, self.y_spectro, self.mu_spectro, self.mu_reg, init, tol=tolerance,
-                  max_iter=maximum_iterations, callback=callback, comm=self.comm)
+        function = lcg if method == "lcg" else mmmg
+        res = function(self.model_spectro, self.y_spectro, self.mu_spectro, self.mu_reg, init, tol=tolerance,
+                       max_iter=maximum_iterations, callback=callback, comm=self.comm, gradient=self.gradient)
         if self.printing:
             print(f"Total time needed for {method} :", round(time.time() - t1, 3))
         return res

@@ -107,3 +107,27 @@ def test_jansky_scaling_matches_reference_rule(torch_cuda):
             block[:, s] = block[:, s] * np.sum(w[0, 0, :]) * oracle.srfs[c]
         expect[oracle._idx[c]: oracle._idx[c + 1]] = block.ravel()
     assert rel(out, expect) < 1e-15
+
+
+@pytest.mark.parametrize("gradient", ["separated", "joint"])
+@pytest.mark.parametrize("method", ["lcg", "mmmg"])
+def test_run_method_variants_match_oracle(torch_cuda, method, gradient):
+    """QuadCriterion_MRS.run_method dispatches like the reference (fusion_CT.py:139-162, 194-197):
+    'lcg' or mmmg, 'separated' or 'joint' gradients; iterates and criterion vs the oracle."""
+    from surfh_b200 import fusion_CT
+    from surfh_b200.model import spectroSigRLSCT
+    from surfh_oracle import model as om
+    cfg = CASES["mini_2band_4p"]()
+    args = cfg.model_args()
+    oracle = om.SpectroLMM(**args, adjoint_mode="exact")
+    gpu = spectroSigRLSCT(**args, adjoint_mode="exact")
+    y = noisy_data(oracle, cfg)
+    mu, n_it = 3.0, 8
+    ref = om.solve(oracle, y, 1.0, mu, n_it, method=method, gradient=gradient, value_init=0.0)
+    quad = fusion_CT.QuadCriterion_MRS(mu_spectro=1, y_spectro=y, model_spectro=gpu, mu_reg=mu, gradient=gradient)
+    res = quad.run_method(method, n_it, tolerance=1e-12, value_init=0)
+    assert res.x.shape == gpu.ishape
+    assert rel(res.x, ref.x) <= 1e-9
+    assert np.allclose(res.grad_norm[: len(ref.grad_norm)], ref.grad_norm, rtol=1e-7)
+    j_cpu = (om.criterion_joint if gradient == "joint" else om.criterion)(oracle, y, ref.x, 1, mu)
+    assert abs(quad.get_crit_val(res.x) - j_cpu) <= 1e-10 * abs(j_cpu)
