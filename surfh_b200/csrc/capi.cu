@@ -626,9 +626,9 @@ template <typename T> struct ModelImpl : surfh_model {
             const int lo = std::max(c0, b.l0), hi = std::min(c1, b.l0 + b.nl);
             if (lo >= hi) continue;
             const int nl = hi - lo;
-            dim3 grid(ceil_div(b.ncol, 128), ceil_div(nl, kLB));
             const double bytes = sizeof(T) * ((double)nl * b.A * b.B * b.P + (double)nl * b.ncol);
             Scope sc(this, ST_SLIT_GATHER, st, bytes, 8.0 * nl * b.ncol * b.srf, 1, true);
+            dim3 grid(ceil_div(b.ncol, 128), ceil_div(nl, kLB));
             slit_gather_kernel<T, kLB><<<grid, 128, 0, st>>>(cubebuf.as<T>() + (size_t)(lo - c0) * plane, plane, Nb, nl,
                                                              b.slit_tables(),
                                                              b.G.template as<T>() + (size_t)(lo - b.l0) * b.ncol);
@@ -637,7 +637,14 @@ template <typename T> struct ModelImpl : surfh_model {
     }
 
     void scatter_chunk(int c0, int c1, int mode, cudaStream_t st) {
-        {
+        if (use_own_fft && prune_rows) {
+            double rows = 0;
+            for (int l = c0; l < c1; ++l) rows += 2.0 * plane_pair_cnt[l];
+            Scope sc(this, ST_MEMSET, st, rows * Nb * sizeof(T), 0, 1, true);
+            dim3 grid(32, c1 - c0);
+            zero_row_hull_kernel<T><<<grid, 256, 0, st>>>(cubebuf.as<T>(), plane, Na, Nb, plane_pairs.as<int2>() + c0);
+            SURFH_CUDA(cudaGetLastError());
+        } else {
             Scope sc(this, ST_MEMSET, st, (double)(c1 - c0) * plane * sizeof(T), 0, 1, false);
             SURFH_CUDA(cudaMemsetAsync(cubebuf.p, 0, (size_t)(c1 - c0) * plane * sizeof(T), st));
         }

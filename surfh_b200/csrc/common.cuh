@@ -72,6 +72,15 @@ __device__ __forceinline__ double block_sum(double v, double* smem /* >= 32 doub
     return r;
 }
 
+// Ampere-style asynchronous global -> shared copies (LDGSTS): no register staging, many in flight.
+template <int BYTES> __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async moves 4, 8 or 16 bytes");
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace surfh

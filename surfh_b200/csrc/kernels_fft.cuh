@@ -21,8 +21,8 @@
 //   * The inputs of item i+1 are copied global -> shared by cp.async into thread-private slots while
 //     item i is transformed: HBM latency is off the critical path at 12 warps per SM.
 //   * A transform is spread over TT = M/16 threads that hold 16 points each; a CTA runs G transforms
-//     side by side, split into two independent halves that synchronise with their own named barrier
-//     so that one half's shared-memory phases overlap the other half's FP64 phases.
+//     side by side, split into independent groups that synchronise with their own named barrier
+//     so that one group's shared-memory phases overlap the others' FP64 phases.
 //   * Of the 4 register<->register exchanges of one chirp-z, 2 go through shared memory (one barrier
 //     each), 2 are transposes among R3 adjacent lanes done with warp shuffles.
 //
@@ -49,14 +49,32 @@ template <typename T, int M> struct FftK {
     // 16 complex doubles per thread need ~168 registers to stay out of local memory: 384 threads per SM
     // in fp64 (256 for M = 2048, whose tables are twice as large); fp32 runs 512 threads at 128 registers
     static constexpr int NT = sizeof(T) == 8 ? (M == 2048 ? 256 : 384) : 512;
-    static constexpr int NH = 2;                // independent halves of the CTA
-    static constexpr int HT = NT / NH;          // threads per half
     static constexpr int G = NT / TT;           // transforms per CTA step
-    static constexpr int GH = G / NH;           // transforms per half
-    static_assert(GH * NH * TT == NT && HT % 32 == 0, "CTA shape");
-    // per-transform exchange buffer: M elements + a pad that staggers the buffers of the transforms whose
-    // lanes share a 128-byte wavefront (R3 consecutive t of 8/R3 or 16/R3 transforms)
-    static constexpr int BUF = M + R3;
+    // independently synchronised groups (named barriers 1..NH): one group's shared-memory phases overlap
+    // the others' FP64 phases.  Measured at N = 501 fp64 (ms per 512 planes, R2C / C2R): 2 groups 2.39 / 2.40,
+    // 3 groups 2.17 / 2.36, 6 groups (one transform each) 2.96 / 3.08 -- the transforms interleaved lane-wise
+    // inside a group keep the column accesses in contiguous runs, so fewer, fatter groups win.
+#ifndef SURFH_FFT_GROUPS
+#define SURFH_FFT_GROUPS 3
+#endif
+    static constexpr int pick_groups() {
+        int best = 1;
+        for (int nh = 1; nh <= SURFH_FFT_GROUPS && nh <= G; ++nh)
+            if (G % nh == 0 && (NT / nh) % 32 == 0) best = nh;
+        return best;
+    }
+    static constexpr int NH = pick_groups();
+    static constexpr int HT = NT / NH;          // threads per group
+    static constexpr int GH = G / NH;           // transforms per group
+    static_assert(GH * NH * TT == NT && HT % 32 == 0 && NH <= 15, "CTA shape");
+    // Exchange buffer of one transform: 16 blocks of TT elements (block q = the q-th sub-sequence) at pitch
+    // TP, buffers at pitch BUF.  A 128-byte wavefront serves 8/R3 (or 16/R3 in fp32) consecutive
+    // (block, transform) pairs of R3 elements each: with several transforms per group the pad of BUF
+    // staggers them over the banks, with one transform per group the pad of TP staggers the blocks.
+    static constexpr int TP = TT + (GH == 1 ? R3 : 0);
+    static constexpr int BUF = 16 * TP + R3;
+    // natural index n of the transform <-> its slot in the buffer (block n / TT, element n % TT)
+    __host__ __device__ static constexpr int slot(int n) { return n + (n / TT) * (TP - TT); }
     static constexpr int N_TW = M + 16 * R3;    // tw1[q*TT + t] then tw2[q2*R3 + n2]
     static constexpr int HALF = M / 2;          // the transform length N must be <= HALF
     static constexpr int SLOTS = 8;             // staged complex-sized elements per thread
@@ -298,7 +316,7 @@ __device__ __forceinline__ void fft_fwd(cplx_t<T>* v, cplx_t<T>* buf, const FftT
         buf[th.t] = v[0];
 #pragma unroll
         for (int q = 1; q < 16; ++q) {
-            buf[q * TT + th.t] = cmul(v[q], pw);
+            buf[q * K::TP + th.t] = cmul(v[q], pw);
             if (q < 15) pw = cmul(pw, w);
         }
     } else {
@@ -306,11 +324,11 @@ __device__ __forceinline__ void fft_fwd(cplx_t<T>* v, cplx_t<T>* buf, const FftT
         for (int q = 0; q < 16; ++q) {
             C x = v[q];
             if (q) x = cmul(x, tw[q * TT + th.t]);
-            buf[q * TT + th.t] = x;
+            buf[q * K::TP + th.t] = x;
         }
     }
     th.sync();
-    C* blk = buf + th.q * TT;
+    C* blk = buf + th.q * K::TP;
 #pragma unroll
     for (int m = 0; m < 16; ++m) v[m] = blk[th.n2 + R3 * m];
     dft16<false>(v);
@@ -358,7 +376,7 @@ __device__ __forceinline__ void fft_inv(cplx_t<T>* v, cplx_t<T>* buf, const FftT
     }
     dft16<true>(v);
     // these are the very locations this thread read in fft_fwd: no barrier needed before the writes
-    C* blk = buf + th.q * TT;
+    C* blk = buf + th.q * K::TP;
 #pragma unroll
     for (int m = 0; m < 16; ++m) blk[th.n2 + R3 * m] = v[m];
     th.sync();
@@ -368,13 +386,13 @@ __device__ __forceinline__ void fft_inv(cplx_t<T>* v, cplx_t<T>* buf, const FftT
         v[0] = buf[th.t];
 #pragma unroll
         for (int qq = 1; qq < 16; ++qq) {
-            v[qq] = cmul_conj(pw, buf[qq * TT + th.t]);
+            v[qq] = cmul_conj(pw, buf[qq * K::TP + th.t]);
             if (qq < 15) pw = cmul(pw, w);
         }
     } else {
 #pragma unroll
         for (int qq = 0; qq < 16; ++qq) {
-            C x = buf[qq * TT + th.t];
+            C x = buf[qq * K::TP + th.t];
             if (qq) x = cmul_conj(tw[qq * TT + th.t], x);
             v[qq] = x;
         }
@@ -513,14 +531,6 @@ __device__ __forceinline__ FftRanges fft_build_ranges(int* smem_i, const int2* p
 // ---- asynchronous staging of the next item's inputs -------------------------------------------
 // Every thread copies exactly the elements it will itself consume into thread-private shared-memory
 // slots, so a cp.async.wait_group is all the synchronisation the staging needs.
-template <int BYTES> __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
-    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async moves 4, 8 or 16 bytes");
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 // A work item of a CTA step, seen from one thread: which plane and which row pair / column.
 struct FftItem {
     bool live;
@@ -592,7 +602,7 @@ template <typename T, int M> struct RowsR2C {
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int n = t + K::TT * m;
-            if (n < s.nb) buf[n] = cmul(v[m], chirp[n]);
+            if (n < s.nb) buf[K::slot(n)] = cmul(v[m], chirp[n]);
         }
         th.sync();
         if (!it.live) return;
@@ -602,7 +612,7 @@ template <typename T, int M> struct RowsR2C {
         for (int m = 0; m < 5; ++m) {
             const int j = t + K::TT * m;
             if (j < s.nh) {
-                const C a = buf[j], b = buf[j == 0 ? 0 : s.nb - j];
+                const C a = buf[K::slot(j)], b = buf[K::slot(j == 0 ? 0 : s.nb - j)];
                 ya[j] = make_c<T>(T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y));
                 if (has_b) ya[s.nh + j] = make_c<T>(T(0.5) * (a.y + b.y), T(0.5) * (b.x - a.x));
             }
@@ -689,7 +699,7 @@ template <typename T, int M, bool INVERSE> struct ColsPass {
             if (i < s.na) {
                 C r = cmul(v[m], chirp[i]);
                 r.y = self_mirror ? T(0) : -r.y;
-                buf[i] = r;
+                buf[K::slot(i)] = r;
             }
         }
         th.sync();
@@ -701,8 +711,8 @@ template <typename T, int M, bool INVERSE> struct ColsPass {
         for (int m = 0; m < 4; ++m) {
             const int p = t + K::TT * m;
             if (p >= p0 && p < p1) {
-                const C a = buf[2 * p];
-                const C b = 2 * p + 1 < s.na ? buf[2 * p + 1] : make_c<T>(T(0), T(0));
+                const C a = buf[K::slot(2 * p)];
+                const C b = 2 * p + 1 < s.na ? buf[K::slot(2 * p + 1)] : make_c<T>(T(0), T(0));
                 C* row = zp + (size_t)p * s.nb;
                 row[j] = make_c<T>(a.x - b.y, a.y + b.x);
                 if (!self_mirror) row[s.nb - j] = make_c<T>(a.x + b.y, b.x - a.y);

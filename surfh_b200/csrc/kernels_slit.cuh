@@ -81,6 +81,11 @@ slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube
         if (l0 + u < n_l) G[(size_t)(l0 + u) * t.ncol + c] = w * acc[u];
 }
 
+// (A shared-memory-tiled variant -- per-tile footprint analysis, parallelogram-shaped staging area filled by
+// double-buffered cp.async, taps read from shared memory -- was built and measured in round 1: bitwise-equal
+// results, 152 us against this kernel's 137 us on config C2: the 4 taps per sample cost as many LSU
+// wavefronts from shared memory (bank conflicts across the rotated rows) as they do from L1.  Removed.)
+
 template <typename T> struct CsrTable {
     const int32_t* row_pixel;  // [n_rows]
     const int64_t* row_ptr;    // [n_rows + 1]
@@ -113,6 +118,19 @@ slit_scatter_kernel(const T* __restrict__ Gt, int ncol, int n_l, CsrTable<T> t, 
 #pragma unroll
     for (int u = 0; u < LB; ++u)
         if (l0 + u < n_l) dst[(size_t)u * plane] += acc[u];
+}
+
+// Zero, in every plane of a chunk, only the row pairs [lo, lo + cnt) that the pruned R2C transform will read
+// (the rows outside are never looked at): replaces a memset of the whole working cube.
+template <typename T>
+__global__ void __launch_bounds__(256)
+zero_row_hull_kernel(T* __restrict__ cube, size_t plane, int n_alpha, int n_beta, const int2* __restrict__ pair_range) {
+    const int2 pr = pair_range[blockIdx.y];
+    const int r0 = 2 * pr.x, r1 = min(n_alpha, r0 + 2 * pr.y);
+    const size_t n = (size_t)(r1 - r0) * n_beta;
+    T* dst = cube + (size_t)blockIdx.y * plane + (size_t)r0 * n_beta;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = T(0);
 }
 
 // No spectral response (MRSBlurred, surfh/Models/spectro_blind.py:191-235): the detector value is the
