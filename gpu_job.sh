@@ -1,3 +1,5 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --config c4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/v6_c4.json 2> gpurun_out/v6_c4.err; tail -2 gpurun_out/v6_c4.err
+python -m pytest tests/test_gpu_fft.py -x -q 2>&1 | tail -1
+python tools/fft_bench.py 501 512 float64 5
+python tools/fft_bench.py 251 512 float64 5
+python tools/fft_bench.py 501 512 float32 5

@@ -628,7 +628,10 @@ template <typename T, int M> struct RowsR2C {
 template <typename T, int M, bool INVERSE> struct ColsPass {
     using C = cplx_t<T>;
     using K = FftK<T, M>;
-    static constexpr bool POST = INVERSE;
+    // The C2R pairing is a lane-pair shuffle when the transform's adjacent threads are adjacent lanes
+    // (R3 >= 2), else a round trip through the shared buffer (which then needs the PRE_SYNC of fft_fwd).
+    static constexpr bool PAIR_BY_SHUFFLE = INVERSE && K::R3 >= 2;
+    static constexpr bool POST = INVERSE && !PAIR_BY_SHUFFLE;
     const C* src;
     C* dst;
     FftShape s;
@@ -693,6 +696,32 @@ template <typename T, int M, bool INVERSE> struct ColsPass {
         const int j = it.idx;
         const int nyq = (s.nb & 1) ? -1 : s.nb / 2;
         const bool self_mirror = j == 0 || j == nyq;  // numpy's irfft ignores the imaginary part there
+        const int p0 = rg.start ? rg.lo[it.plane] : 0;
+        const int p1 = rg.start ? p0 + rg.cnt(it.plane) : s.npair;
+        C* zp = dst + (size_t)it.plane * s.z_plane;
+        if (PAIR_BY_SHUFFLE) {
+            // rows 2p and 2p+1 sit in the adjacent lanes t and t^1 (t = ... + n2, n2 the fastest lane index):
+            // the even lane assembles Z[p][j], the odd lane its Hermitian mirror Z[p][nb-j]
+            const bool odd = (t & 1) != 0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int i = t + K::TT * m;
+                C mine = make_c<T>(T(0), T(0));
+                if (i < s.na) {
+                    mine = cmul(v[m], chirp[i]);
+                    mine.y = self_mirror ? T(0) : -mine.y;
+                }
+                const C other = shfl_xor_c(mine, 1);
+                const C a = odd ? other : mine, b = odd ? mine : other;
+                const int p = i >> 1;
+                if (it.live && p >= p0 && p < p1) {
+                    C* row = zp + (size_t)p * s.nb;
+                    if (!odd) row[j] = make_c<T>(a.x - b.y, a.y + b.x);
+                    else if (!self_mirror) row[s.nb - j] = make_c<T>(a.x + b.y, b.x - a.y);
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const int i = t + K::TT * m;
@@ -704,9 +733,6 @@ template <typename T, int M, bool INVERSE> struct ColsPass {
         }
         th.sync();
         if (!it.live) return;
-        C* zp = dst + (size_t)it.plane * s.z_plane;
-        const int p0 = rg.start ? rg.lo[it.plane] : 0;
-        const int p1 = rg.start ? p0 + rg.cnt(it.plane) : s.npair;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int p = t + K::TT * m;
