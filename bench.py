@@ -160,7 +160,7 @@ def band_summaries(cfg):
         hull_rows = len(la) * abs(np.cos(ang)) + len(lb) * abs(np.sin(ang)) + 6  # rotated local grid + dithers
         out.append(dict(wave_start=wsl.start, n_wave=wsl.stop - wsl.start, n_det=band.n_wavel, nb=nbw,
                         n_pointing=len(pts), n_slit=band.n_slit, na=na, local_a=len(la), local_b=len(lb),
-                        hull_rows=float(hull_rows)))
+                        hull_rows=float(hull_rows), srf=int(srf)))
     return out
 
 
@@ -243,7 +243,8 @@ def workload_description(cfg, dtype, args):
             "adjoint_mode": args.adjoint, "compute_dtype": dtype,
             "l2_policy": "inputs larger than L2: every step streams the OTF and cube chunks (GBs) through HBM",
             "parallelism": f"cube wavelength axis sharded over {args.gpus} GPU(s) (contiguous, cost-balanced); per "
-                           f"application: all-reduce of the detector vector (partial sums) and of the [K,N,N] maps"}
+                           f"application: the detector blocks of bands shared by several ranks are summed among those "
+                           f"ranks (NCCL sub-communicators), then one all-reduce of the [K,N,N] maps"}
 
 
 # ------------------------------------------------------------------------- GPU arm

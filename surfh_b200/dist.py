@@ -1,11 +1,14 @@
-"""Band sharding across GPUs: one process per GPU (torch.distributed, NCCL over NVLink).
+"""Wavelength sharding across GPUs: one process per GPU (torch.distributed, NCCL over NVLink).
 
-The forward is independent per band (each band needs only the K maps, its wavelength window of the
-OTF / templates and its own tables, and produces its own slice of y), so bands are dealt to ranks
-with no data-path collective.  The adjoint's T^T C^T is linear and wavelength-local, so every rank
-finishes its partial [K, N, N] map gradient locally and the only exchange per CG iteration is one
-all-reduce(sum) of that array (12 MB at K=6, N=501 fp64); the CG scalars are then computed
-redundantly on identical data, so they need no collective.  
+The cube wavelength axis is cut into contiguous, cost-balanced ranges (`partition_lambda`).  The FFT,
+OTF and slit stages are wavelength-local; a band whose window straddles a cut is computed as partial
+sums (its spectral contraction is split along K = (lambda, beta)).  Exchanges per application:
+  * between forward and adjoint, the detector blocks of the bands that are SHARED by several ranks are
+    summed among exactly those ranks (`BandExchange`: one small all-reduce per shared band on a
+    sub-communicator; 2-3 ranks and 6-22 MB each instead of 144 MB across all 8);
+  * at the end, one all-reduce(sum) of the [K, N, N] map gradient (12 MB at K=6, N=501 fp64).
+The CG scalars are then computed redundantly on identical data, so they need no collective.
+
 """
 from __future__ import annotations
 
@@ -63,7 +66,7 @@ def lambda_costs(n_lambda: int, bands: Sequence[dict], n_pix: int, bytes_per_rea
     """Per-wavelength cost model in seconds, calibrated on a B200 with the C4 workload in fp64
     (profiles/r01_app_kernels.md); only the ratios matter for the partition.  `bands`: dicts with
     wave_start, n_wave, n_det, nb, n_pointing, n_slit, na, local_a, local_b and, optionally, hull_rows
-    (cube rows the band's field of view touches; default: every row).  A covered wavelength costs
+    (cube rows the band's field of view touches; default: every row) and srf (default 7).  A covered wavelength costs
       * the two column passes of its 2-D FFT pair, the two template x OTF streams and the memset,
       * the two row passes, proportional to the row pairs in the hull of the bands covering it,
     plus, per band covering it, its share of the gather / scatter index streams (2.2 TB/s effective)
@@ -78,6 +81,9 @@ def lambda_costs(n_lambda: int, bands: Sequence[dict], n_pix: int, bytes_per_rea
         hull[sl] = np.maximum(hull[sl], min(n_pix, b.get("hull_rows", n_pix)))
         flops = 4.0 * b["n_det"] * b["nb"] * b["n_pointing"] * b["n_slit"] * b["na"]
         stream = 2.0 * b["n_pointing"] * (b["local_a"] * b["local_b"] + b["n_slit"] * b["na"] * b["nb"]) * bytes_per_real
+        # the index streams are bound by LSU wavefronts, which grow with the taps per output (srf rows of 4)
+        # faster than with the bytes: empirical exponent from the per-rank kernel times at 8 GPUs
+        stream *= (b.get("srf", 7) / 7.0) ** 0.5
         cost[sl] += flops / gemm_rate + stream / 2.2e12
     covered = hull > 0
     cost[covered] += col_passes + streams + per_pair * (hull[covered] / 2.0 + 1.0)
@@ -107,6 +113,58 @@ class Comm:
     def barrier(self):
         if self.world_size > 1:
             self.dist.barrier(group=self.group)
+
+
+def band_rank_sets(band_windows: Sequence[tuple], ranges: Sequence[tuple]) -> List[List[int]]:
+    """For every band (wavelength window [start, stop)), the ranks whose wavelength range overlaps it."""
+    out = []
+    for w0, w1 in band_windows:
+        out.append([r for r, (l0, l1) in enumerate(ranges) if min(w1, l1) > max(w0, l0)])
+    return out
+
+
+class BandExchange:
+    """Sums the detector block of every band among the ranks that computed a share of it.
+
+    Built collectively (every rank of `comm` must construct it with the same arguments, in the same
+    order: torch.distributed.new_group is a collective).  `blocks[b]` = (offset, size) of band b in the
+    detector vector.  A rank only ends up with complete blocks for the bands it touches -- which is all
+    its own adjoint reads."""
+
+    def __init__(self, comm: Comm, band_windows: Sequence[tuple], blocks: Sequence[tuple],
+                 my_range: Optional[tuple]):
+        import torch
+        self.comm = comm
+        dist = comm.dist
+        mine = torch.tensor(list(my_range) if my_range is not None else [0, 1 << 30], dtype=torch.int64)
+        if torch.cuda.is_available() and dist.get_backend(comm.group) == "nccl":
+            mine = mine.cuda()
+        gathered = [torch.zeros_like(mine) for _ in range(comm.world_size)]
+        dist.all_gather(gathered, mine, group=comm.group)
+        self.ranges = [tuple(int(v) for v in g.cpu()) for g in gathered]
+        self.rank_sets = band_rank_sets(band_windows, self.ranges)
+        self.blocks = list(blocks)
+        groups = {}
+        self.plan = []  # (offset, size, group) for the shared bands this rank takes part in, band order
+        for b, ranks in enumerate(self.rank_sets):
+            if len(ranks) < 2:
+                continue
+            key = tuple(ranks)
+            if key not in groups:  # every rank creates every group, in band order (collective call)
+                groups[key] = None if len(ranks) == comm.world_size else dist.new_group(ranks=list(ranks))
+            if comm.rank in ranks:
+                self.plan.append((int(blocks[b][0]), int(blocks[b][1]), groups[key] if groups[key] is not None
+                                  else comm.group))
+
+    def reduce_shared(self, y):
+        """In place: y[block of b] = sum over the ranks sharing band b, for the bands of this rank."""
+        dist = self.comm.dist
+        for off, size, group in self.plan:
+            dist.all_reduce(y[off: off + size], op=dist.ReduceOp.SUM, group=group)
+        return y
+
+    def bytes_per_application(self, itemsize: int) -> int:
+        return sum(size for _, size, _ in self.plan) * itemsize
 
 
 def init_from_env(backend: Optional[str] = None) -> Optional[Comm]:

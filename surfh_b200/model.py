@@ -343,11 +343,25 @@ class spectroSigRLSCT(LinOp):
         if len(self.local_bands) < len(self.band_tables):
             y.zero_()  # slices of bands this shard does not touch must not carry the previous sum
         _capi.check(self._h, self._lib.surfh_forward(self._h, x.data_ptr(), y.data_ptr(), self._stream()))
-        self.comm.allreduce_sum(y)
+        # the adjoint of this shard reads only the detector blocks of the bands it touches: sum each shared
+        # band among the ranks that hold a share of it (sub-communicators) instead of all-reducing all of y
+        if self.lambda_range is not None and len(self.local_bands) > 0:
+            self._band_exchange().reduce_shared(y)
+        else:
+            self.comm.allreduce_sum(y)
         _capi.check(self._h, self._lib.surfh_adjoint(self._h, y.data_ptr(), out.data_ptr(), self.mode_code,
                                                      self._stream()))
         self.comm.allreduce_sum(out)
         return out
+
+    def _band_exchange(self):
+        """Collective on first use: every rank of the communicator must reach it (fwadj does)."""
+        if getattr(self, "_exchange", None) is None:
+            from .dist import BandExchange
+            windows = [(t.wslice.start, t.wslice.stop) for t in self.band_tables]
+            blocks = [(int(self._idx[c]), int(self._idx[c + 1] - self._idx[c])) for c in range(len(self.band_tables))]
+            self._exchange = BandExchange(self.comm, windows, blocks, self.lambda_range)
+        return self._exchange
 
     fwback = fwadj
 

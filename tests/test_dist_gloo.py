@@ -90,3 +90,56 @@ def test_partition_helpers():
     assert dist.partition_lambda(np.ones(8), 8) == [(i, i + 1) for i in range(8)]
     with pytest.raises(ValueError):
         dist.partition_lambda(np.zeros(4), 2)
+
+
+def _exchange_worker(rank, world, port, ret):
+    for p in (ROOT,):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as tdist
+    from surfh_b200 import dist
+
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = dist.Comm()
+    ranges = [(0, 10), (10, 20), (20, 30)]
+    windows = [(0, 15), (12, 25), (26, 30), (0, 30)]      # shared by {0,1}, {1,2}, {2}, everyone
+    blocks = [(0, 5), (5, 7), (12, 3), (15, 4)]
+    ex = dist.BandExchange(comm, windows, blocks, ranges[rank])
+    y = torch.zeros(19, dtype=torch.float64)
+    for b, (off, size) in enumerate(blocks):                # partial sums: rank r contributes (r + 1) * (b + 1)
+        if rank in ex.rank_sets[b]:
+            y[off: off + size] = (rank + 1) * (b + 1)
+    ex.reduce_shared(y)
+    ret[rank] = (ex.ranges, ex.rank_sets, y.numpy().copy(), ex.bytes_per_application(8))
+    tdist.destroy_process_group()
+
+
+def test_band_exchange_sums_each_band_among_its_ranks_only():
+    """3 gloo ranks: every shared band is summed on a sub-communicator of exactly the ranks that hold a
+    share of it; a rank ends up with complete blocks for the bands it touches."""
+    import torch.multiprocessing as mp
+    world = 3
+    port = 31500 + (os.getpid() % 2000)
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_exchange_worker, args=(world, port, ret), nprocs=world, join=True)
+    blocks = [(0, 5), (5, 7), (12, 3), (15, 4)]
+    sets = [[0, 1], [1, 2], [2], [0, 1, 2]]
+    for rank in range(world):
+        ranges, rank_sets, y, nbytes = ret[rank]
+        assert ranges == [(0, 10), (10, 20), (20, 30)] and rank_sets == sets
+        for b, (off, size) in enumerate(blocks):
+            if rank in sets[b]:
+                want = (b + 1) * sum(r + 1 for r in sets[b])
+                assert np.all(y[off: off + size] == want), (rank, b, y)
+            else:
+                assert np.all(y[off: off + size] == 0)
+        assert nbytes == 8 * sum(size for b, (off, size) in enumerate(blocks) if rank in sets[b] and len(sets[b]) > 1)
+
+
+def test_band_rank_sets():
+    from surfh_b200 import dist
+    assert dist.band_rank_sets([(0, 10), (8, 20), (25, 30)], [(0, 9), (9, 18), (18, 40)]) == [[0, 1], [0, 1, 2], [2]]
+    assert dist.band_rank_sets([(5, 6)], [(0, 5), (5, 6), (6, 9)]) == [[1]]
