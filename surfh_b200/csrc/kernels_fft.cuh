@@ -30,12 +30,17 @@
 //   R2C:  rows_r2c  real [Na][Nb] -> A/B-separated half spectra Y [Na][Nh]   (separation through the
 //                   transform's own shared buffer)            ->  cols  (-> spec [Na][Nh])
 //   C2R:  cols_c2r  spec [Na][Nh] -> Z [ceil(Na/2)][Nb], Z[p] = W[2p] + i W[2p+1] Hermitian-extended
-//                   (pairing through the shared buffer)       ->  rows_c2r (-> real [Na][Nb])
+//                   (rows 2p, 2p+1 sit in adjacent lanes: pairing by shuffle) ->  rows_c2r (-> real [Na][Nb])
+// In the operator the rows passes only visit the row pairs some band's field of view touches (FftRanges).
 #pragma once
 #include "common.cuh"
 
+// build-time switches for A/B measurements (python -c "build.build(out=..., defines=[...])")
 #ifndef SURFH_FFT_TWIDDLE_CHAIN
 #define SURFH_FFT_TWIDDLE_CHAIN 1
+#endif
+#ifndef SURFH_FFT_GROUPS
+#define SURFH_FFT_GROUPS 3
 #endif
 
 namespace surfh {
@@ -54,9 +59,6 @@ template <typename T, int M> struct FftK {
     // the others' FP64 phases.  Measured at N = 501 fp64 (ms per 512 planes, R2C / C2R): 2 groups 2.39 / 2.40,
     // 3 groups 2.17 / 2.36, 6 groups (one transform each) 2.96 / 3.08 -- the transforms interleaved lane-wise
     // inside a group keep the column accesses in contiguous runs, so fewer, fatter groups win.
-#ifndef SURFH_FFT_GROUPS
-#define SURFH_FFT_GROUPS 3
-#endif
     static constexpr int pick_groups() {
         int best = 1;
         for (int nh = 1; nh <= SURFH_FFT_GROUPS && nh <= G; ++nh)
@@ -98,8 +100,8 @@ template <typename T, int M> struct FftK {
 };
 
 // Who am I: transform g (of G), thread t (of TT) = q*R3 + n2.  The R3 threads that exchange registers
-// in the last radix stage are adjacent lanes; the GH transforms of a half are interleaved next, so that a
-// warp reads few distinct table entries (broadcast) and touches GH adjacent columns in a column pass.
+// in the last radix stage are adjacent lanes; the GH transforms of a group are interleaved next, so that a
+// warp touches GH adjacent columns in a column pass.  `half` = index of the barrier group.
 template <typename T, int M> struct FftThread {
     using K = FftK<T, M>;
     int half, g, t, q, n2;
@@ -112,7 +114,7 @@ template <typename T, int M> struct FftThread {
         q = c / K::GH;
         t = q * K::R3 + n2;
     }
-    // barrier among the threads of this half only
+    // barrier among the threads of this group only
     __device__ __forceinline__ void sync() const {
         asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(K::HT) : "memory");
     }
