@@ -618,7 +618,14 @@ template <typename T> struct ModelImpl : surfh_model {
         }
     }
 
-    static constexpr int kLB = 4;  // wavelengths per thread in the slit kernels
+#ifndef SURFH_GATHER_LB
+#define SURFH_GATHER_LB 4
+#endif
+#ifndef SURFH_SCATTER_LB
+#define SURFH_SCATTER_LB 4
+#endif
+    static constexpr int kLB = SURFH_GATHER_LB;    // wavelengths per thread in the gather ...
+    static constexpr int kLBs = SURFH_SCATTER_LB;  // ... and in the scatter
 
     void gather_chunk(int c0, int c1, cudaStream_t st) {
         for (auto& bp : bands) {
@@ -653,10 +660,10 @@ template <typename T> struct ModelImpl : surfh_model {
             const int lo = std::max(c0, b.l0), hi = std::min(c1, b.l0 + b.nl);
             if (lo >= hi || b.csr_rows[mode] == 0) continue;
             const int nl = hi - lo;
-            dim3 grid(ceil_div(b.csr_rows[mode], 128), ceil_div(nl, kLB));
+            dim3 grid(ceil_div(b.csr_rows[mode], 128), ceil_div(nl, kLBs));
             const double bytes = sizeof(T) * ((double)nl * b.ncol + 2.0 * nl * b.csr_rows[mode]);
             Scope sc(this, ST_SLIT_SCATTER, st, bytes, 2.0 * nl * (double)b.csr_nnz[mode], 1, true);
-            slit_scatter_kernel<T, kLB><<<grid, 128, 0, st>>>(b.G.template as<T>() + (size_t)(lo - b.l0) * b.ncol, b.ncol,
+            slit_scatter_kernel<T, kLBs><<<grid, 128, 0, st>>>(b.G.template as<T>() + (size_t)(lo - b.l0) * b.ncol, b.ncol,
                                                               nl, b.csr(mode),
                                                               cubebuf.as<T>() + (size_t)(lo - c0) * plane, plane);
             SURFH_CUDA(cudaGetLastError());

@@ -249,32 +249,26 @@ dgemm_mma_kernel(const __grid_constant__ GemmBatch batch) {
     const int gq = lane >> 2, tq = lane & 3;
 
     // ---- loader mapping (see otgemm_kernel) ----------------------------------------------
-    int32_t a_fix[A_KFAST ? EA : 1], b_fix[B_KFAST ? EB : 1];
-    bool a_ok[A_KFAST ? EA : 1], b_ok[B_KFAST ? EB : 1];
+    // K-fast operands: a thread loads EA (EB) rows at one k per slab; the row offsets live in shared memory
+    // (one table per CTA) instead of EA + EB registers per thread, which kept the forward variant spilling.
+    __shared__ int32_t s_afix[A_KFAST ? kDBM : 1], s_bfix[B_KFAST ? kDBN : 1];
+    int32_t a_fix0 = 0, b_fix0 = 0;
+    bool a_ok0 = false, b_ok0 = false;
     if (A_KFAST) {
-#pragma unroll
-        for (int i = 0; i < EA; ++i) {
-            const int m = m0 + tid / kDBK + i * (NT / kDBK);
-            a_ok[i] = m < g.M;
-            a_fix[i] = a_ok[i] ? __ldg(g.aM + m) : 0;
-        }
+        for (int r = tid; r < kDBM; r += NT) s_afix[r] = m0 + r < g.M ? __ldg(g.aM + m0 + r) : -1;
     } else {
         const int m = m0 + tid % kDBM;
-        a_ok[0] = m < g.M;
-        a_fix[0] = a_ok[0] ? __ldg(g.aM + m) : 0;
+        a_ok0 = m < g.M;
+        a_fix0 = a_ok0 ? __ldg(g.aM + m) : 0;
     }
     if (B_KFAST) {
-#pragma unroll
-        for (int i = 0; i < EB; ++i) {
-            const int n = n0 + tid / kDBK + i * (NT / kDBK);
-            b_ok[i] = n < g.N;
-            b_fix[i] = b_ok[i] ? __ldg(g.bN + n) : 0;
-        }
+        for (int r = tid; r < kDBN; r += NT) s_bfix[r] = n0 + r < g.N ? __ldg(g.bN + n0 + r) : -1;
     } else {
         const int n = n0 + tid % kDBN;
-        b_ok[0] = n < g.N;
-        b_fix[0] = b_ok[0] ? __ldg(g.bN + n) : 0;
+        b_ok0 = n < g.N;
+        b_fix0 = b_ok0 ? __ldg(g.bN + n) : 0;
     }
+    __syncthreads();
     double ra[EA], rb[EB];
     auto load_slab = [&](int k0) {
         if (A_KFAST) {
@@ -282,12 +276,15 @@ dgemm_mma_kernel(const __grid_constant__ GemmBatch batch) {
             const bool kok = k < g.K;
             const int32_t ko = kok ? __ldg(g.aK + k) : 0;
 #pragma unroll
-            for (int i = 0; i < EA; ++i) ra[i] = (kok && a_ok[i]) ? __ldg(g.A + a_fix[i] + ko) : 0.0;
+            for (int i = 0; i < EA; ++i) {
+                const int32_t fix = s_afix[tid / kDBK + i * (NT / kDBK)];
+                ra[i] = (kok && fix >= 0) ? __ldg(g.A + fix + ko) : 0.0;
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < EA; ++i) {
                 const int k = k0 + tid / kDBM + i * (NT / kDBM);
-                ra[i] = (k < g.K && a_ok[0]) ? __ldg(g.A + a_fix[0] + __ldg(g.aK + k)) : 0.0;
+                ra[i] = (k < g.K && a_ok0) ? __ldg(g.A + a_fix0 + __ldg(g.aK + k)) : 0.0;
             }
         }
         if (B_KFAST) {
@@ -295,12 +292,15 @@ dgemm_mma_kernel(const __grid_constant__ GemmBatch batch) {
             const bool kok = k < g.K;
             const int32_t ko = kok ? __ldg(g.bK + k) : 0;
 #pragma unroll
-            for (int i = 0; i < EB; ++i) rb[i] = (kok && b_ok[i]) ? __ldg(g.B + b_fix[i] + ko) : 0.0;
+            for (int i = 0; i < EB; ++i) {
+                const int32_t fix = s_bfix[tid / kDBK + i * (NT / kDBK)];
+                rb[i] = (kok && fix >= 0) ? __ldg(g.B + fix + ko) : 0.0;
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < EB; ++i) {
                 const int k = k0 + tid / kDBN + i * (NT / kDBN);
-                rb[i] = (k < g.K && b_ok[0]) ? __ldg(g.B + b_fix[0] + __ldg(g.bK + k)) : 0.0;
+                rb[i] = (k < g.K && b_ok0) ? __ldg(g.B + b_fix0 + __ldg(g.bK + k)) : 0.0;
             }
         }
     };
