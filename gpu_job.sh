@@ -1,3 +1,6 @@
+# the round's standard check: GPU parity suite, smoke, default bench line, CPU reference arm
 set -x
-python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -2
-python bench.py --config c4 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/t_c4.json 2> gpurun_out/t_c4.err; tail -2 gpurun_out/t_c4.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
+python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -2 gpurun_out/bench_default.err
+python bench.py --impl reference --steps 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; tail -2 gpurun_out/bench_reference.err
