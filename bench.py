@@ -181,6 +181,8 @@ def cpu_sample(cfg, n_pointings: int, repeats: int, warmup: int):
     from surfh_b200 import synthetic
     from surfh_oracle import model as om  # executed here only as the timed CPU baseline
 
+    if cfg.templates is None:
+        return cpu_sample_blind(cfg, repeats, warmup)
     band = cfg.band_names[0]
     k = cfg.templates.shape[0]
     sub = synthetic.mrs_config([band], len(cfg.alpha_axis), k, n_pointings, seed=0, name=f"{cfg.name}-sample")
@@ -200,6 +202,32 @@ def cpu_sample(cfg, n_pointings: int, repeats: int, warmup: int):
               f"wavelengths), {n_pointings} pointing(s), K={k}, N={len(cfg.alpha_axis)}, fp64: "
               f"{model.osize} of {full_out} detector samples = {frac:.4f} of one application in {t:.2f} s "
               f"(median of {repeats}); value = fraction / seconds")
+    return {"value": frac / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample,
+            "seconds_per_sample": t, "sample_fraction": frac}
+
+
+def cpu_sample_blind(cfg, repeats: int, warmup: int, n_wave: int = 16):
+    """Config 5: the oracle's MRSBlurred on the first `n_wave` wavelengths, one after the other like the
+    reference's per-wavelength script (deconvolution_mrs_single_wavelength.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from surfh_b200 import synthetic
+    from surfh_oracle import blind as ob  # executed here only as the timed CPU baseline
+    sotf = synthetic.ir2fr(cfg.psf[:n_wave], cfg.imshape)
+    models = [ob.MRSBlurred(sotf[l], cfg.alpha_axis, cfg.beta_axis, cfg.instrs[0], cfg.step_degree, cfg.pointings[0])
+              for l in range(n_wave)]
+    times = []
+    for it in range(warmup + repeats):
+        t0 = time.perf_counter()
+        for l, m in enumerate(models):
+            m.adjoint(m.forward(cfg.maps[l]))
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = float(np.median(times))
+    frac = n_wave / len(cfg.wavelength_axis)
+    sample = (f"{n_wave} of {len(cfg.wavelength_axis)} wavelengths of {cfg.name} (band {cfg.band_names[0]}, "
+              f"N={len(cfg.alpha_axis)}, {len(cfg.pointings[0])} pointings, fp64) = {frac:.4f} of one application in "
+              f"{t:.2f} s (median of {repeats}); value = fraction / seconds")
     return {"value": frac / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample,
             "seconds_per_sample": t, "sample_fraction": frac}
 
@@ -236,6 +264,14 @@ def run_reference(args):
 
 
 def workload_description(cfg, dtype, args):
+    if cfg.templates is None:
+        return {"workload": f"{cfg.name}: MRSBlurred (non-LMM, per-wavelength C-S-Sum-L-beta-sum chain of "
+                            f"spectro_blind.py) batched over {len(cfg.wavelength_axis)} cube wavelengths, band "
+                            f"{cfg.band_names[0]}, {len(cfg.alpha_axis)}x{len(cfg.beta_axis)} planes, "
+                            f"{len(cfg.pointings[0])} pointings; one step = one forward + one adjoint of the batch",
+                "adjoint_mode": args.adjoint, "compute_dtype": dtype,
+                "l2_policy": "inputs larger than L2: every step streams the cube, the OTF and the FFT intermediates",
+                "parallelism": "single GPU"}
     return {"workload": f"{cfg.name}: {len(cfg.instrs)} MRS band(s) {','.join(cfg.band_names)}, "
                         f"K={cfg.templates.shape[0]} templates, {len(cfg.alpha_axis)}x{len(cfg.beta_axis)} maps, "
                         f"{len(cfg.wavelength_axis)} cube wavelengths, {len(cfg.pointings[0])} pointings; "
@@ -266,13 +302,21 @@ def run_b200(args):
     esz = 8 if args.dtype == "float64" else 4
 
     cfg = build_config(args.config)
-    lam_range = shard_for_rank(cfg, comm, esz)
+    lam_range = shard_for_rank(cfg, comm, esz) if cfg.templates is not None else None
     shape = cfg.imshape
     t_setup = time.time()
     sotf = lambda lo, hi: synthetic.ir2fr_device(cfg.psf[lo:hi], shape, dev, torch.float64)  # noqa: E731
-    model = spectroSigRLSCT(sotf, cfg.templates, cfg.alpha_axis, cfg.beta_axis, cfg.wavelength_axis, cfg.instrs,
-                            cfg.step_degree, cfg.pointings, dtype=args.dtype, adjoint_mode=args.adjoint,
-                            lambda_range=lam_range, comm=comm, chunk=args.chunk, device=local_rank)
+    if cfg.templates is None:  # configuration 5: the batched non-LMM operator, one GPU
+        if comm is not None:
+            raise SystemExit("bench.py: config c5 is a single-GPU stress of the FFT + slit path")
+        from surfh_b200.spectro_blind import MRSBlurred
+        model = MRSBlurred(sotf, cfg.alpha_axis, cfg.beta_axis, cfg.instrs[0], cfg.step_degree, cfg.pointings[0],
+                           n_lambda=len(cfg.wavelength_axis), dtype=args.dtype, adjoint_mode=args.adjoint,
+                           chunk=args.chunk, device=local_rank)
+    else:
+        model = spectroSigRLSCT(sotf, cfg.templates, cfg.alpha_axis, cfg.beta_axis, cfg.wavelength_axis, cfg.instrs,
+                                cfg.step_degree, cfg.pointings, dtype=args.dtype, adjoint_mode=args.adjoint,
+                                lambda_range=lam_range, comm=comm, chunk=args.chunk, device=local_rank)
     setup_s = time.time() - t_setup
 
     x = torch.as_tensor(cfg.maps, device=dev, dtype=tdtype)
@@ -330,6 +374,7 @@ def run_b200(args):
     cg.start(np.zeros(model.ishape), args.steps + args.warmup + 8)
     ms_cg, _, _, _ = timed(lambda: cg.step(False), args.steps, args.warmup)
     cg_iters = 1e3 * args.steps / ms_cg
+    del cg, y
 
     # ---- end to end through the LinOp API with host buffers: numpy maps in pinned memory ->
     # spectroSigRLSCT.fwadj (H2D, forward, [all-reduce], adjoint, [all-reduce], D2H) -> numpy maps

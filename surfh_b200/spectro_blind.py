@@ -55,8 +55,9 @@ class MRSBlurred(spectroSigRLSCT):
         out = super().adjoint(data)
         return out.reshape(self.ishape)
 
-    def fwadj(self, x):
-        return super().fwadj(self._shape_in(x)).reshape(self.ishape)
+    def fwadj(self, x, out=None):
+        res = super().fwadj(self._shape_in(x), out=None if out is None else out.reshape(self.cube_shape))
+        return out if out is not None else res.reshape(self.ishape)
 
     fwback = fwadj
 

@@ -203,5 +203,6 @@ def baseline_config(which: str, seed: int = 0) -> Config:
     if which == "c4":
         return mrs_config(ALL_BANDS, 501, 6, 4, seed, "c4", wavel=cube_wavelength_axis(4.75, 28.9))
     if which == "c5":
-        return mrs_config(["1c"], 301, 0, 4, seed, "c5", lmm=False)
+        # the per-wavelength (non-LMM) MRSBlurred operator batched over a full-size cube: ~3000 wavelengths
+        return mrs_config(["1c"], 301, 0, 4, seed, "c5", lmm=False, wavel=cube_wavelength_axis(4.75, 21.3))
     raise ValueError(f"unknown baseline configuration {which!r}")
