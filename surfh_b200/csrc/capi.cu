@@ -453,6 +453,13 @@ template <typename T> struct ModelImpl : surfh_model {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         SURFH_CUDA(cudaFuncSetAttribute(otgemm_kernel<T, G::BM, G::BN, G::BK, G::TM, G::TN, false, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (const char* e = std::getenv("SURFH_F32_GEMM")) f32_tensor_gemm = std::strcmp(e, "simt") != 0;
+        if (std::is_same<T, float>::value) {
+            SURFH_CUDA(cudaFuncSetAttribute(sgemm_tf32x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sgemm_smem_bytes<true, true>()));
+            SURFH_CUDA(cudaFuncSetAttribute(sgemm_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sgemm_smem_bytes<false, false>()));
+        }
         if (std::is_same<T, double>::value) {
             SURFH_CUDA(cudaFuncSetAttribute(dgemm_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)dgemm_smem_bytes<true, true>()));
@@ -589,6 +596,9 @@ template <typename T> struct ModelImpl : surfh_model {
 
     // FP64 tensor path: all bands in one grouped launch (per group of kMaxGemmGroup bands)
     void gemm_grouped_f64(double* y, bool adjoint, cudaStream_t st);
+    // FP32 tensor path (3xTF32 split), same grouping; SURFH_F32_GEMM=simt selects the FFMA kernel
+    void gemm_grouped_f32(float* y, bool adjoint, cudaStream_t st);
+    bool f32_tensor_gemm = true;
 
     void beta_sum(BandT<T>& b, T* y, bool adjoint, cudaStream_t st) {
         const size_t n = (size_t)b.nl * b.Nn * (adjoint ? b.nb : 1);
@@ -612,6 +622,8 @@ template <typename T> struct ModelImpl : surfh_model {
         if (!any_lsf) return;
         if (std::is_same<T, double>::value) {
             gemm_grouped_f64(reinterpret_cast<double*>(y), adjoint, st);
+        } else if (f32_tensor_gemm) {
+            gemm_grouped_f32(reinterpret_cast<float*>(y), adjoint, st);
         } else {
             for (auto& bp : bands)
                 if (bp->mode == SURFH_SPECTRAL_LSF) gemm_simt(*bp, y, adjoint, st);
@@ -895,6 +907,38 @@ template <typename T> struct ModelImpl : surfh_model {
 
 template <> void ModelImpl<float>::gemm_grouped_f64(double*, bool, cudaStream_t) {
     throw Error(SURFH_ESTATE, "internal: fp64 GEMM on an fp32 model");
+}
+template <> void ModelImpl<double>::gemm_grouped_f32(float*, bool, cudaStream_t) {
+    throw Error(SURFH_ESTATE, "internal: fp32 GEMM on an fp64 model");
+}
+
+template <> void ModelImpl<float>::gemm_grouped_f32(float* y, bool adjoint, cudaStream_t st) {
+    std::vector<size_t> lsf_bands;
+    for (size_t i = 0; i < bands.size(); ++i)
+        if (bands[i]->mode == SURFH_SPECTRAL_LSF) lsf_bands.push_back(i);
+    for (size_t first = 0; first < lsf_bands.size(); first += kMaxGemmGroup) {
+        GemmBatchF batch;
+        batch.count = 0;
+        batch.tile_start[0] = 0;
+        double bytes = 0, flops = 0;
+        for (size_t j = first; j < std::min(lsf_bands.size(), first + (size_t)kMaxGemmGroup); ++j) {
+            BandT<float>& b = *bands[lsf_bands[j]];
+            GemmArgs<float> g = gemm_args(b, y, adjoint);
+            batch.p[batch.count] = g;
+            batch.tile_start[batch.count + 1] =
+                batch.tile_start[batch.count] + ceil_div(g.M, kFBM) * ceil_div(g.N, kFBN);
+            batch.count++;
+            bytes += sizeof(float) * ((double)b.nd * b.KB + (double)b.nl * b.ncol + (double)b.out_size);
+            flops += 2.0 * g.M * g.N * g.K;
+        }
+        Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, flops, 1, true);
+        const int tiles = batch.tile_start[batch.count];
+        if (!adjoint)
+            sgemm_tf32x3_kernel<true, true><<<tiles, 256, sgemm_smem_bytes<true, true>(), st>>>(batch);
+        else
+            sgemm_tf32x3_kernel<false, false><<<tiles, 256, sgemm_smem_bytes<false, false>(), st>>>(batch);
+        SURFH_CUDA(cudaGetLastError());
+    }
 }
 
 template <> void ModelImpl<double>::gemm_grouped_f64(double* y, bool adjoint, cudaStream_t st) {

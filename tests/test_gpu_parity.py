@@ -65,6 +65,22 @@ def test_full_size_vs_reference_golden(built, golden_dir, name):
     assert abs(np.linalg.norm(x) - float(gold["adj_norm"])) <= 1e-10 * float(gold["adj_norm"])
 
 
+@pytest.mark.parametrize("gemm", ["tensor", "simt"])
+def test_fp32_full_size_vs_reference_golden(built, golden_dir, gemm, monkeypatch):
+    """fp32 mode at full size (contraction length 3144) against the reference's golden vectors, 1e-5 budget,
+    for both spectral-response kernels: 3xTF32 on the tensor cores (slab-wise accumulation, without which
+    the truncating tensor-core adds bias the sum by 2e-5) and the FFMA kernel."""
+    monkeypatch.setenv("SURFH_F32_GEMM", gemm)
+    cfg = CASES["c1_band1a"]()
+    gold = np.load(os.path.join(golden_dir, "c1_band1a.npz"))
+    gpu = built(**cfg.model_args(), dtype="float32", adjoint_mode="reference")
+    y = gpu.forward(cfg.maps)
+    assert rel(y[::int(gold["fwd_stride"])], gold["fwd_sample"]) <= 1e-5
+    v = np.random.default_rng(1234).standard_normal(gpu.osize)
+    x = gpu.adjoint(v)
+    assert rel(x[:, ::7, ::7], gold["adj_sample"]) <= 1e-5
+
+
 @pytest.mark.parametrize("name", ["mini_2band_4p", "c1_band1a"])
 def test_dot_test_exact_adjoint(built, name):
     """<Hx, y> = <x, H^T y> to 1e-6 (BASELINE.json) in exact mode; it holds to ~1e-13 in fp64."""
