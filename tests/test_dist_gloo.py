@@ -143,3 +143,25 @@ def test_band_rank_sets():
     from surfh_b200 import dist
     assert dist.band_rank_sets([(0, 10), (8, 20), (25, 30)], [(0, 9), (9, 18), (18, 40)]) == [[0, 1], [0, 1, 2], [2]]
     assert dist.band_rank_sets([(5, 6)], [(0, 5), (5, 6), (6, 9)]) == [[1]]
+
+
+def test_c4_partition_is_contiguous_complete_and_balanced():
+    """The wavelength partition bench.py uses for the full 12-band workload at 2, 4 and 8 ranks."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from surfh_b200 import dist, synthetic
+    cfg = synthetic.baseline_config("c4")
+    bands = bench.band_summaries(cfg)
+    assert len(bands) == 12 and all(b["hull_rows"] <= 501 and b["srf"] in (7, 9, 10) for b in bands)
+    costs = dist.lambda_costs(len(cfg.wavelength_axis), bands, len(cfg.alpha_axis), 8)
+    assert costs.min() > 0  # every cube wavelength of C4 is inside some band's window
+    for world in (2, 4, 8):
+        parts = dist.partition_lambda(costs, world)
+        assert parts[0][0] == 0 and parts[-1][1] == len(costs)
+        assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(parts, parts[1:]))
+        loads = [costs[a:b].sum() for a, b in parts]
+        assert max(loads) / min(loads) < 1.02
+        # every band is shared by a contiguous set of ranks, and no rank is left without a band
+        sets = dist.band_rank_sets([(b["wave_start"], b["wave_start"] + b["n_wave"]) for b in bands], parts)
+        assert all(s == list(range(s[0], s[-1] + 1)) for s in sets)
+        assert set(r for s in sets for r in s) == set(range(world))
