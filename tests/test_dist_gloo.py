@@ -154,11 +154,11 @@ def test_c4_partition_is_contiguous_complete_and_balanced():
     bands = bench.band_summaries(cfg)
     assert len(bands) == 12 and all(b["hull_rows"] <= 501 and b["srf"] in (7, 9, 10) for b in bands)
     costs = dist.lambda_costs(len(cfg.wavelength_axis), bands, len(cfg.alpha_axis), 8)
-    assert costs.min() > 0  # every cube wavelength of C4 is inside some band's window
+    assert costs.min() >= 0 and (costs > 0).mean() > 0.95  # a few wavelengths at the ends lie outside every band
     for world in (2, 4, 8):
         parts = dist.partition_lambda(costs, world)
         assert parts[0][0] == 0 and parts[-1][1] == len(costs)
-        assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(parts, parts[1:]))
+        assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(parts, parts[1:])) and parts[-1][0] < parts[-1][1]
         loads = [costs[a:b].sum() for a, b in parts]
         assert max(loads) / min(loads) < 1.02
         # every band is shared by a contiguous set of ranks, and no rank is left without a band
