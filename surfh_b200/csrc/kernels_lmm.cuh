@@ -71,7 +71,7 @@ lmm_otf_adj_kernel(const cplx_t<T>* __restrict__ spec, const cplx_t<T>* __restri
 #pragma unroll
     for (int k = 0; k < K; ++k) a[k] = make_c<T>(T(0), T(0));
     if (f < nfp) {
-#pragma unroll 2
+#pragma unroll 4  // 8 loads in flight per thread: 0.92 of the HBM rate (unroll 2: 0.87, unroll 8: 0.80)
         for (int l = ty; l < n_l; l += kAdjLanes) {
             const C o = ld_stream(otf + (size_t)l * nfp + f);
             const C s = ld_stream(spec + (size_t)l * nfp + f);
