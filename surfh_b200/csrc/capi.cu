@@ -647,7 +647,8 @@ template <typename T> struct ModelImpl : surfh_model {
             const int nl = hi - lo;
             const double bytes = sizeof(T) * ((double)nl * b.A * b.B * b.P + (double)nl * b.ncol);
             Scope sc(this, ST_SLIT_GATHER, st, bytes, 8.0 * nl * b.ncol * b.srf, 1, true);
-            dim3 grid(ceil_div(b.ncol, 128), ceil_div(nl, kLB));
+            const int pp = std::min(b.P, 4), chunks = 4 / pp;  // see the kernel: 4 warps = pp pointings x chunks
+            dim3 grid(ceil_div(b.S * b.na * b.nb, 32 * chunks), ceil_div(nl, kLB));
             slit_gather_kernel<T, kLB><<<grid, 128, 0, st>>>(cubebuf.as<T>() + (size_t)(lo - c0) * plane, plane, Nb, nl,
                                                              b.slit_tables(),
                                                              b.G.template as<T>() + (size_t)(lo - b.l0) * b.ncol);

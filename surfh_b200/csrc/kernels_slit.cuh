@@ -38,15 +38,24 @@ template <typename T, int LB>
 __global__ void __launch_bounds__(128)
 slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube plane */, int n_beta,
                    int n_l, SlitTables<T> t, T* __restrict__ G) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= t.ncol) return;
+    // Thread -> output mapping: the warps of a CTA take the SAME 32 outputs (s, a, b) of DIFFERENT pointings.
+    // The dithers shift the field of view by a couple of pixels only, so the warps of a CTA read almost the
+    // same cube sectors at almost the same time and share them in L1 (the kernel is bound by the L2 -> L1
+    // sector stream of its scattered taps, not by HBM).
+    const int n_per_p = t.S * t.na * t.nb;         // outputs per pointing
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const int pp = t.P < n_warps ? t.P : n_warps;  // pointings side by side in a CTA
+    const int chunks = n_warps / pp;               // 32-output chunks per CTA
+    if (warp >= pp * chunks) return;
+    const int o = (blockIdx.x * chunks + warp / pp) * 32 + lane;
+    if (o >= n_per_p) return;
     const int l0 = blockIdx.y * LB;
-    int b = c % t.nb;
-    int r = c / t.nb;
+    const int b = o % t.nb;
+    int r = o / t.nb;
     const int a = r % t.na;
-    r /= t.na;
-    const int s = r % t.S;
-    const int p = r / t.S;
+    const int s = r / t.na;
+  for (int p = warp % pp; p < t.P; p += pp) {
+    const int c = p * n_per_p + o;
     const int j = t.slit_b0[s] + b;
     const int i_first = t.slit_a0[s] + a * t.srf;
     const int32_t* gb = t.grid_base + (size_t)p * t.A * t.B;
@@ -79,6 +88,7 @@ slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube
 #pragma unroll
     for (int u = 0; u < LB; ++u)
         if (l0 + u < n_l) G[(size_t)(l0 + u) * t.ncol + c] = w * acc[u];
+  }
 }
 
 // (A shared-memory-tiled variant -- per-tile footprint analysis, parallelogram-shaped staging area filled by
