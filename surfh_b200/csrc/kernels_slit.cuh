@@ -50,12 +50,14 @@ slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube
     const int o = (blockIdx.x * chunks + warp / pp) * 32 + lane;
     if (o >= n_per_p) return;
     const int l0 = blockIdx.y * LB;
+    // o enumerates (a, s, b) with (s, b) fastest: a warp's 32 lanes walk ~32 consecutive local columns of ONE
+    // local row, i.e. ~5 runs of ~7 cube pixels, instead of 4 local rows of 8 columns
     const int b = o % t.nb;
     int r = o / t.nb;
-    const int a = r % t.na;
-    const int s = r / t.na;
+    const int s = r % t.S;
+    const int a = r / t.S;
   for (int p = warp % pp; p < t.P; p += pp) {
-    const int c = p * n_per_p + o;
+    const int c = ((p * t.S + s) * t.na + a) * t.nb + b;
     const int j = t.slit_b0[s] + b;
     const int i_first = t.slit_a0[s] + a * t.srf;
     const int32_t* gb = t.grid_base + (size_t)p * t.A * t.B;
