@@ -122,7 +122,19 @@ template <typename T> struct BandT {
     int csr_rows[2] = {0, 0};
     int64_t csr_nnz[2] = {0, 0};
     DevBuf t_ident, t_wrow, t_gK, t_gN, t_yM, t_yN;
-    DevBuf G;  // [nl][ncol] slit-space vector (forward G / adjoint Gt)
+    DevBuf G;  // [nl][ncol] slit-space vector (forward G / adjoint Gt), columns in INTERNAL order
+    // The ABI (and the detector) order slit-space columns as ((p*S + s)*na + a)*nb + b; internally they are
+    // stored as ((p*na + a)*S + s)*nb + b, so that the 32 consecutive cube pixels a warp of the scatter owns
+    // (and the 32 outputs a warp of the gather produces) touch one contiguous run of G instead of one run of
+    // nb per slit.
+    int internal_col(int c) const {
+        const int bb = c % nb;
+        int r = c / nb;
+        const int aa = r % na;
+        r /= na;
+        const int ss = r % S, pp = r / S;
+        return ((pp * na + aa) * S + ss) * nb + bb;
+    }
 
     SlitTables<T> slit_tables() const {
         SlitTables<T> t;
@@ -331,7 +343,11 @@ template <typename T> struct ModelImpl : surfh_model {
             if (cs[m]->n_rows == 0) continue;
             upload_converted<int32_t>(b->csr_pix[m], cs[m]->row_pixel, cs[m]->n_rows);
             upload_converted<int64_t>(b->csr_ptr[m], cs[m]->row_ptr, (size_t)cs[m]->n_rows + 1);
-            upload_converted<int32_t>(b->csr_col[m], cs[m]->col, cs[m]->nnz);
+            {
+                std::vector<int32_t> col((size_t)cs[m]->nnz);
+                for (int64_t e = 0; e < cs[m]->nnz; ++e) col[(size_t)e] = b->internal_col(cs[m]->col[e]);
+                upload_converted<int32_t>(b->csr_col[m], col.data(), col.size());
+            }
             upload_converted<T>(b->csr_val[m], cs[m]->val, cs[m]->nnz);
         }
         // GEMM offset tables
@@ -347,7 +363,7 @@ template <typename T> struct ModelImpl : surfh_model {
             for (int k = 0; k < b->KB; ++k) v[k] = (k / b->nb) * b->ncol + k % b->nb;
             upload_converted<int32_t>(b->t_gK, v.data(), b->KB);
             v.assign(b->Nn, 0);
-            for (int n = 0; n < b->Nn; ++n) v[n] = n * b->nb;
+            for (int n = 0; n < b->Nn; ++n) v[n] = b->internal_col(n * b->nb);  // n = (p*S + s)*na + a
             upload_converted<int32_t>(b->t_gN, v.data(), b->Nn);
             v.assign(b->nd, 0);
             for (int m = 0; m < b->nd; ++m) v[m] = m * b->na;
@@ -605,11 +621,11 @@ template <typename T> struct ModelImpl : surfh_model {
         const double bytes = sizeof(T) * ((double)b.nl * b.ncol + (double)b.nl * b.Nn);
         Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, (double)b.nl * b.ncol, 1, true);
         if (!adjoint)
-            beta_sum_fwd_kernel<T><<<ceil_div(n, 256), 256, 0, st>>>(b.G.template as<T>(), b.nl, b.Nn, b.nb, b.det_start,
-                                                                   y + b.out_offset);
+            beta_sum_fwd_kernel<T><<<ceil_div(n, 256), 256, 0, st>>>(b.G.template as<T>(), b.nl, b.Nn, b.nb, b.S, b.na,
+                                                                   b.det_start, y + b.out_offset);
         else
-            beta_sum_adj_kernel<T><<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.nl, b.Nn, b.nb, b.det_start,
-                                                                   b.G.template as<T>());
+            beta_sum_adj_kernel<T><<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.nl, b.Nn, b.nb, b.S, b.na,
+                                                                   b.det_start, b.G.template as<T>());
         SURFH_CUDA(cudaGetLastError());
     }
 

@@ -1,7 +1,7 @@
 // k3 / k3^T: IFU slit sampling and its two "adjoints".
 //
 // Forward (gather), fused S . Sum . L . alpha-decimation for all pointings of a band:
-//   G[l, (p,s,a,b)] = w[s,b] * sum_{m<srf} bilinear(cube[l]; grid[p][(a0[s] + a*srf + m) mod A, b0[s] + b])
+//   G[l, (p,a,s,b)] = w[s,b] * sum_{m<srf} bilinear(cube[l]; grid[p][(a0[s] + a*srf + m) mod A, b0[s] + b])
 // Replaces (paths relative to the reference tree)
 //   Channel.gridding            surfh/Models/spectroModelChannel.py:158-177
 //     -> cythons_files.find_indices / solve_2D_hypercube   surfh/ToolsDir/cythons_files.pyx:109-193
@@ -57,7 +57,7 @@ slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube
     const int s = r % t.S;
     const int a = r / t.S;
   for (int p = warp % pp; p < t.P; p += pp) {
-    const int c = ((p * t.S + s) * t.na + a) * t.nb + b;
+    const int c = ((p * t.na + a) * t.S + s) * t.nb + b;  // internal slit-space order: contiguous in (s, b)
     const int j = t.slit_b0[s] + b;
     const int i_first = t.slit_a0[s] + a * t.srf;
     const int32_t* gb = t.grid_base + (size_t)p * t.A * t.B;
@@ -148,12 +148,19 @@ zero_row_hull_kernel(T* __restrict__ cube, size_t plane, int n_alpha, int n_beta
 // No spectral response (MRSBlurred, surfh/Models/spectro_blind.py:191-235): the detector value is the
 // beta-sum of the weighted slit, one output row per cube wavelength; the transpose replicates.
 //   y[(row0 + l) * Nn + n] = sum_b G[l, n*nb + b]          Gt[l, n*nb + b] = y[(row0 + l) * Nn + n]
+// Detector sample n = (p*S + s)*na + a lives at slit-space column ((p*na + a)*S + s)*nb (+ b).
+__device__ __forceinline__ size_t slit_col_of_sample(size_t n, int S, int na, int nb) {
+    const size_t a = n % na, ps = n / na, s = ps % S, p = ps / S;
+    return ((p * na + a) * S + s) * nb;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
-beta_sum_fwd_kernel(const T* __restrict__ G, int n_l, int Nn, int nb, int row0, T* __restrict__ y) {
+beta_sum_fwd_kernel(const T* __restrict__ G, int n_l, int Nn, int nb, int S, int na, int row0, T* __restrict__ y) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n_l * Nn) return;
-    const T* g = G + idx * nb;
+    const size_t l = idx / Nn, n = idx % Nn;
+    const T* g = G + l * ((size_t)Nn * nb) + slit_col_of_sample(n, S, na, nb);
     T s = T(0);
     for (int b = 0; b < nb; ++b) s += g[b];
     y[(size_t)row0 * Nn + idx] = s;
@@ -161,10 +168,11 @@ beta_sum_fwd_kernel(const T* __restrict__ G, int n_l, int Nn, int nb, int row0, 
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-beta_sum_adj_kernel(const T* __restrict__ y, int n_l, int Nn, int nb, int row0, T* __restrict__ Gt) {
+beta_sum_adj_kernel(const T* __restrict__ y, int n_l, int Nn, int nb, int S, int na, int row0, T* __restrict__ Gt) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n_l * Nn * nb) return;
-    Gt[idx] = y[(size_t)row0 * Nn + idx / nb];
+    const size_t b = idx % nb, ln = idx / nb, l = ln / Nn, n = ln % Nn;
+    Gt[l * ((size_t)Nn * nb) + slit_col_of_sample(n, S, na, nb) + b] = y[(size_t)row0 * Nn + ln];
 }
 
 }  // namespace surfh
