@@ -149,7 +149,7 @@ template <typename T> struct BandT {
     CsrTable<T> csr(int mode) const {
         CsrTable<T> c;
         c.row_pixel = csr_pix[mode].as<int32_t>();
-        c.row_ptr = csr_ptr[mode].as<int64_t>();
+        c.slice_ptr = csr_ptr[mode].as<int64_t>();
         c.col = csr_col[mode].as<int32_t>();
         c.val = csr_val[mode].as<T>();
         c.n_rows = csr_rows[mode];
@@ -342,13 +342,27 @@ template <typename T> struct ModelImpl : surfh_model {
             b->csr_nnz[m] = cs[m]->nnz;
             if (cs[m]->n_rows == 0) continue;
             upload_converted<int32_t>(b->csr_pix[m], cs[m]->row_pixel, cs[m]->n_rows);
-            upload_converted<int64_t>(b->csr_ptr[m], cs[m]->row_ptr, (size_t)cs[m]->n_rows + 1);
-            {
-                std::vector<int32_t> col((size_t)cs[m]->nnz);
-                for (int64_t e = 0; e < cs[m]->nnz; ++e) col[(size_t)e] = b->internal_col(cs[m]->col[e]);
-                upload_converted<int32_t>(b->csr_col[m], col.data(), col.size());
+            // CSR -> sliced ELL (see kernels_slit.cuh), columns in the internal slit-space order
+            const int n_rows = cs[m]->n_rows, n_slices = (n_rows + 31) / 32;
+            std::vector<int64_t> slice_ptr((size_t)n_slices + 1, 0);
+            for (int sl = 0; sl < n_slices; ++sl) {
+                int64_t width = 0;
+                for (int r = sl * 32; r < std::min(n_rows, sl * 32 + 32); ++r)
+                    width = std::max<int64_t>(width, cs[m]->row_ptr[r + 1] - cs[m]->row_ptr[r]);
+                slice_ptr[(size_t)sl + 1] = slice_ptr[(size_t)sl] + 32 * width;
             }
-            upload_converted<T>(b->csr_val[m], cs[m]->val, cs[m]->nnz);
+            std::vector<int32_t> col((size_t)slice_ptr.back(), 0);
+            std::vector<double> val((size_t)slice_ptr.back(), 0.0);
+            for (int r = 0; r < n_rows; ++r) {
+                const int64_t at = slice_ptr[(size_t)(r / 32)] + r % 32;
+                for (int64_t e = cs[m]->row_ptr[r], k = 0; e < cs[m]->row_ptr[r + 1]; ++e, ++k) {
+                    col[(size_t)(at + 32 * k)] = b->internal_col(cs[m]->col[e]);
+                    val[(size_t)(at + 32 * k)] = cs[m]->val[e];
+                }
+            }
+            upload_converted<int64_t>(b->csr_ptr[m], slice_ptr.data(), slice_ptr.size());
+            upload_converted<int32_t>(b->csr_col[m], col.data(), col.size());
+            upload_converted<T>(b->csr_val[m], val.data(), val.size());
         }
         // GEMM offset tables
         if (b->mode == SURFH_SPECTRAL_LSF) {

@@ -98,34 +98,44 @@ slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube
 // results, 152 us against this kernel's 137 us on config C2: the 4 taps per sample cost as many LSU
 // wavefronts from shared memory (bank conflicts across the rotated rows) as they do from L1.  Removed.)
 
+// The host hands the adjoint tables over as CSR (include/surfh_b200.h); on the device they are stored
+// "sliced ELL": rows in slices of 32 (one warp), the k-th entries of a slice's 32 rows adjacent in memory,
+// every slice padded to its longest row with (column 0, weight 0).  A warp then reads its k-th entries as one
+// contiguous 128 / 256-byte run; in row-major CSR the same read touched 32 different sectors (rows hold
+// 16-32 entries), and those two table reads per entry were the bulk of the kernel's LSU wavefronts.
 template <typename T> struct CsrTable {
-    const int32_t* row_pixel;  // [n_rows]
-    const int64_t* row_ptr;    // [n_rows + 1]
-    const int32_t* col;        // [nnz]
-    const T* val;              // [nnz]
+    const int32_t* row_pixel;   // [n_rows]
+    const int64_t* slice_ptr;   // [n_slices + 1] entry offset of every slice (multiples of 32)
+    const int32_t* col;         // [slice_ptr[n_slices]]  entry k of row r at slice_ptr[r/32] + 32 k + r % 32
+    const T* val;               // same layout
     int32_t n_rows;
 };
 
-// cube[l, pixel] += sum_e val[e] * Gt[l, col[e]]     (cube is zeroed by the caller)
+// cube[l, pixel] += sum_e val[e] * Gt[l, col[e]]     (the rows of the cube are zeroed by the caller)
 template <typename T, int LB>
 __global__ void __launch_bounds__(128)
 slit_scatter_kernel(const T* __restrict__ Gt, int ncol, int n_l, CsrTable<T> t, T* __restrict__ cube,
                     size_t plane) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= t.n_rows) return;
+    const int slice = r >> 5, lane = r & 31;             // warp-uniform slice: no divergence on the loop bound
+    if ((slice << 5) >= t.n_rows) return;
     const int l0 = blockIdx.y * LB;
-    const int64_t e0 = t.row_ptr[r], e1 = t.row_ptr[r + 1];
+    const int64_t base = t.slice_ptr[slice];
+    const int width = (int)((t.slice_ptr[slice + 1] - base) >> 5);
     T acc[LB];
 #pragma unroll
     for (int u = 0; u < LB; ++u) acc[u] = T(0);
     const T* g = Gt + (size_t)l0 * ncol;
-    for (int64_t e = e0; e < e1; ++e) {
-        const int c = __ldg(t.col + e);
-        const T v = __ldg(t.val + e);
+    const int32_t* col = t.col + base + lane;
+    const T* val = t.val + base + lane;
+    for (int k = 0; k < width; ++k) {
+        const int c = __ldg(col + 32 * k);
+        const T v = __ldg(val + 32 * k);
 #pragma unroll
         for (int u = 0; u < LB; ++u)
             if (l0 + u < n_l) acc[u] = fma(v, __ldg(g + (size_t)u * ncol + c), acc[u]);
     }
+    if (r >= t.n_rows) return;
     T* dst = cube + (size_t)l0 * plane + t.row_pixel[r];
 #pragma unroll
     for (int u = 0; u < LB; ++u)
