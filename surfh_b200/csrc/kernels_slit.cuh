@@ -128,6 +128,7 @@ slit_scatter_kernel(const T* __restrict__ Gt, int ncol, int n_l, CsrTable<T> t, 
     const T* g = Gt + (size_t)l0 * ncol;
     const int32_t* col = t.col + base + lane;
     const T* val = t.val + base + lane;
+#pragma unroll 4  // 4 entries = 16 dependent G loads in flight (unroll 1: 3.28 ms, 4: 2.59 ms, 8: 2.79 ms on C4)
     for (int k = 0; k < width; ++k) {
         const int c = __ldg(col + 32 * k);
         const T v = __ldg(val + 32 * k);
