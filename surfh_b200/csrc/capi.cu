@@ -947,6 +947,12 @@ template <> void ModelImpl<float>::gemm_grouped_f32(float* y, bool adjoint, cuda
     std::vector<size_t> lsf_bands;
     for (size_t i = 0; i < bands.size(); ++i)
         if (bands[i]->mode == SURFH_SPECTRAL_LSF) lsf_bands.push_back(i);
+    // longest tiles first (a tile's cost is its contraction length): the block scheduler hands tiles out in
+    // blockIdx order, so the tail of the grouped launch is made of the short ones
+    std::stable_sort(lsf_bands.begin(), lsf_bands.end(), [&](size_t x, size_t y) {
+        const int kx = adjoint ? bands[x]->nd : bands[x]->KB, ky = adjoint ? bands[y]->nd : bands[y]->KB;
+        return kx > ky;
+    });
     for (size_t first = 0; first < lsf_bands.size(); first += kMaxGemmGroup) {
         GemmBatchF batch;
         batch.count = 0;
@@ -976,6 +982,12 @@ template <> void ModelImpl<double>::gemm_grouped_f64(double* y, bool adjoint, cu
     std::vector<size_t> lsf_bands;
     for (size_t i = 0; i < bands.size(); ++i)
         if (bands[i]->mode == SURFH_SPECTRAL_LSF) lsf_bands.push_back(i);
+    // longest tiles first (a tile's cost is its contraction length): the block scheduler hands tiles out in
+    // blockIdx order, so the tail of the grouped launch is made of the short ones
+    std::stable_sort(lsf_bands.begin(), lsf_bands.end(), [&](size_t x, size_t y) {
+        const int kx = adjoint ? bands[x]->nd : bands[x]->KB, ky = adjoint ? bands[y]->nd : bands[y]->KB;
+        return kx > ky;
+    });
     for (size_t first = 0; first < lsf_bands.size(); first += kMaxGemmGroup) {
         GemmBatch batch;
         batch.count = 0;
