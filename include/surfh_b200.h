@@ -9,7 +9,8 @@
  * Conventions
  *   - every function returns 0 on success, a negative SURFH_E* code otherwise; the message is
  *     available from surfh_last_error(); no exception crosses the boundary;
- *   - one handle per GPU (the device current at surfh_create); a handle is not thread-safe;
+ *   - one handle per GPU (the device current at surfh_create; every entry point makes that device
+ *     current for the duration of the call and restores the caller's); a handle is not thread-safe;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
  *     enqueued on it, nothing synchronises unless stated;
  *   - "real" means the handle's dtype: SURFH_F64 -> double, SURFH_F32 -> float; complex means
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SURFH_ABI_VERSION 3
+#define SURFH_ABI_VERSION 4
 
 enum { SURFH_F32 = 0, SURFH_F64 = 1 };
 
@@ -183,6 +184,11 @@ int surfh_cg_refresh(surfh_handle h, int32_t phase, void* x, void* r, void* d, c
  * fusion_CT.py:242-265).  hx/y may be NULL to skip the data term, x may be NULL to skip the prior. */
 int surfh_criterion_terms(surfh_handle h, const void* y, const void* hx, int64_t n, const void* x, double* s_out,
                           void* stream);
+
+/* s_out[0] = <x, b + r> on n_maps*[n_alpha,n_beta] vectors.  With r = b - Q x (the CG residual) the
+ * quadratic criterion is J(x) = mu_s |y|^2 / 2 - <x, b + r> / 2: `get_crit_val` on the current iterate
+ * (fusion_CT.py:242-265 as called from the lcg callback, :164-192) without the extra forward pass. */
+int surfh_cg_dot_x_b_plus_r(surfh_handle h, const void* x, const void* b, const void* r, double* s_out, void* stream);
 
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* number of kernels (own + cuFFT exec calls) this handle has launched since creation */

@@ -178,6 +178,37 @@ def geometry_record(model):
     return rec
 
 
+def run_cg_case(model_mod, ref_instru, cfg, n_iter: int, mu_reg: float):
+    """BASELINE.json's configs[1]: the reference's own QuadCriterion_MRS.run_method('lcg', n_iter,
+    perf_crit=1, calc_crit=True, value_init=0) (scripts/main_fusion.py:179-190) on the reference operator,
+    driven by the restated qmm.lcg.  Stores the gradient-norm history, the criterion trace and a strided
+    sample of the final maps."""
+    import contextlib
+    import io
+    from surfh.Simulation import fusion_CT
+    model = build_reference_model(model_mod, ref_instru, cfg)
+    fwd = np.asarray(model.forward(cfg.maps))
+    y = fwd + 0.01 * np.sqrt(np.mean(fwd ** 2)) * np.random.default_rng(99).standard_normal(fwd.shape)
+    crit = fusion_CT.QuadCriterion_MRS(1, np.copy(y), model, mu_reg, printing=False, gradient="separated")
+    rec = {"idx": np.asarray(model._idx), "mu_reg": np.array(mu_reg), "n_iter": np.array(n_iter),
+           "fwd_norm": np.array(np.linalg.norm(fwd)), "crit_at_zero": np.array(crit.get_crit_val(np.zeros(model.ishape)))}
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = crit.run_method("lcg", n_iter, perf_crit=1, calc_crit=True, value_init=0)
+    x = np.asarray(res.x).reshape(model.ishape)
+    rec["cg_x_sample"] = x[:, ::3, ::3].copy()
+    rec["cg_x_norm"] = np.array(np.linalg.norm(x))
+    rec["cg_grad_norm"] = np.asarray(res.grad_norm)
+    rec["cg_crit"] = np.asarray(crit.L_crit_val)
+    rec["crit_final"] = np.array(crit.get_crit_val(x))
+    return rec
+
+
+CG_CASES = {
+    # name: (config factory, iterations, mu_reg)
+    "c2_cg50": (lambda: synthetic.baseline_config("c2"), 50, 5e3),
+}
+
+
 def run_case(model_mod, ref_instru, cfg, full: bool, with_cg: bool = False):
     model = build_reference_model(model_mod, ref_instru, cfg)
     rng = np.random.default_rng(1234)
@@ -226,6 +257,11 @@ CASES = {
     "mini_2band_2p_cube": (lambda: synthetic.mini_config(2, 2, lmm=False, n_pix=96), True, False),
     "c1_band1a": (lambda: synthetic.baseline_config("c1"), False, False),
     "band2a_4p": (lambda: synthetic.mrs_config(["2a"], 251, 4, 4, seed=3, name="band2a_4p"), False, False),
+    # channels 3 and 4 at the north-star map size (srf 9 / 10, nb 16 / 26; the 275x319 local grid of
+    # channel 4 is what forces N = 501), 4 dithers, and BASELINE.json's configs[2] (C3) as a whole
+    "band3a_n501_4p": (lambda: synthetic.mrs_config(["3a"], 501, 4, 4, seed=11, name="band3a_n501_4p"), False, False),
+    "band4a_n501_4p": (lambda: synthetic.mrs_config(["4a"], 501, 4, 4, seed=12, name="band4a_n501_4p"), False, False),
+    "c3": (lambda: synthetic.baseline_config("c3"), False, False),
 }
 
 
@@ -265,6 +301,14 @@ def main(names=None):
         if names and name not in names:
             continue
         run_blind(ref_instru, name, cfg, l_idx)
+    for name, (factory, n_iter, mu_reg) in CG_CASES.items():
+        if names and name not in names:
+            continue
+        rec = run_cg_case(model_mod, ref_instru, factory(), n_iter, mu_reg)
+        path = os.path.join(GOLDEN, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print(f"{name}: {n_iter} iterations, J0={float(rec['crit_at_zero']):.6e} J={float(rec['crit_final']):.6e} "
+              f"-> {os.path.getsize(path) / 1e3:.0f} kB")
     for name, (factory, full, with_cg) in CASES.items():
         if names and name not in names:
             continue

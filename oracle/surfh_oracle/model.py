@@ -92,15 +92,18 @@ def interpn_cube2local(alpha_axis, beta_axis, cube, pts_a, pts_b):
 
 def interpn_local2cube(local_alpha, local_beta, local_cube, pts_a, pts_b):
     """Bilinear sample of the LOCAL cube at the points; points outside the local grid give 0
-    (cython_utils.py:33-58; cython_2D_interpolation.py:316-323, 369-376)."""
-    i0, i1, w = bilinear_tables(local_alpha, local_beta, pts_a, pts_b)
-    out = local_cube[:, i0, i1] * w[0]
-    out = out + local_cube[:, i0, i1 + 1] * w[1]
-    out = out + local_cube[:, i0 + 1, i1] * w[2]
-    out = out + local_cube[:, i0 + 1, i1 + 1] * w[3]
+    (cython_utils.py:33-58; cython_2D_interpolation.py:316-323, 369-376).  The reference evaluates the
+    extrapolated value everywhere and then overwrites the out-of-bounds points with 0; only the in-bounds
+    points are evaluated here (same values, a third of the work at N = 501)."""
     pa, pb = pts_a.ravel(), pts_b.ravel()
-    oob = (pa < local_alpha[0]) | (pa > local_alpha[-1]) | (pb < local_beta[0]) | (pb > local_beta[-1])
-    out[:, oob] = 0
+    inb = ~((pa < local_alpha[0]) | (pa > local_alpha[-1]) | (pb < local_beta[0]) | (pb > local_beta[-1]))
+    i0, i1, w = bilinear_tables(local_alpha, local_beta, pa[inb], pb[inb])
+    val = local_cube[:, i0, i1] * w[0]
+    val = val + local_cube[:, i0, i1 + 1] * w[1]
+    val = val + local_cube[:, i0 + 1, i1] * w[2]
+    val = val + local_cube[:, i0 + 1, i1 + 1] * w[3]
+    out = np.zeros((local_cube.shape[0], pa.size))
+    out[:, inb] = val
     return out.reshape((local_cube.shape[0],) + pts_a.shape)
 
 

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
+#include <tuple>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -86,6 +88,7 @@ struct surfh_model {
                             cudaStream_t st) = 0;
     virtual void criterion_terms(const void* y, const void* hx, int64_t n, const void* x, double* out,
                                  cudaStream_t st) = 0;
+    virtual void cg_dot_x_b_plus_r(const void* x, const void* b, const void* r, double* out, cudaStream_t st) = 0;
 
     struct Scope {
         surfh_model* m; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
@@ -116,6 +119,7 @@ namespace surfh {
 template <typename T> struct BandT {
     int P, S, na, nb, srf, A, B, l0, nl, nd, ncol, Nn, KB, mode, det_start;
     int row_lo = 0, row_hi = 0;  // cube rows this band reads (gather) or writes (either adjoint table)
+    int64_t footprint = 0;       // distinct cube pixels the bilinear taps of ALL pointings read (union)
     int64_t out_offset, out_size;
     DevBuf slit_a0, slit_b0, slit_w, lsf, grid_base, grid_frac;
     DevBuf csr_pix[2], csr_ptr[2], csr_col[2], csr_val[2];
@@ -323,6 +327,14 @@ template <typename T> struct ModelImpl : surfh_model {
             const int i = d->grid_base[q] / Nb;
             b->row_lo = std::min(b->row_lo, i);
             b->row_hi = std::max(b->row_hi, i + 1);
+        }
+        {   // union footprint of the four taps over every pointing: what one gather launch reads per plane
+            std::vector<uint8_t> seen(plane, 0);
+            for (int64_t q = 0; q < (int64_t)b->P * AB; ++q) {
+                const int32_t off = d->grid_base[q];
+                seen[off] = seen[off + 1] = seen[off + Nb] = seen[off + Nb + 1] = 1;
+            }
+            for (uint8_t v : seen) b->footprint += v;
         }
         for (const surfh_csr* c : {&d->adj_exact, &d->adj_reference})
             if (c->n_rows > 0) {
@@ -675,7 +687,8 @@ template <typename T> struct ModelImpl : surfh_model {
             const int lo = std::max(c0, b.l0), hi = std::min(c1, b.l0 + b.nl);
             if (lo >= hi) continue;
             const int nl = hi - lo;
-            const double bytes = sizeof(T) * ((double)nl * b.A * b.B * b.P + (double)nl * b.ncol);
+            // one launch serves every pointing of the band and reads the union of their footprints once
+            const double bytes = sizeof(T) * ((double)nl * b.footprint + (double)nl * b.ncol);
             Scope sc(this, ST_SLIT_GATHER, st, bytes, 8.0 * nl * b.ncol * b.srf, 1, true);
             const int pp = std::min(b.P, 4), chunks = 4 / pp;  // see the kernel: 4 warps = pp pointings x chunks
             dim3 grid(ceil_div(b.S * b.na * b.nb, 32 * chunks), ceil_div(nl, kLB));
@@ -849,7 +862,10 @@ template <typename T> struct ModelImpl : surfh_model {
         cudaStream_t st = 0;
         const size_t ni = (size_t)input_size(), no = (size_t)output_size();
         to_device(x, x_stage, ni, st);
-        y_stage.ensure_zeroed(no * sizeof(T));  // slices of bands this handle does not own stay zero
+        // the output staging is shared with adjoint_host's input and a partial handle (band / wavelength
+        // shard) does not write every element: zero it at every call so non-owned slices are zeros
+        y_stage.ensure(no * sizeof(T));
+        SURFH_CUDA(cudaMemsetAsync(y_stage.p, 0, no * sizeof(T), st));
         forward(x_stage.p, y_stage.p, st);
         to_host(y_stage, y, no, st);
     }
@@ -925,6 +941,7 @@ template <typename T> struct ModelImpl : surfh_model {
         }
         SURFH_CUDA(cudaGetLastError());
     }
+    void cg_dot_x_b_plus_r(const void* x, const void* b, const void* r, double* out, cudaStream_t st) override;
     void criterion_terms(const void* y, const void* hx, int64_t n, const void* x, double* out, cudaStream_t st) override {
         SURFH_REQUIRE(out, "NULL buffer");
         const size_t nmax = std::max<size_t>((size_t)std::max<int64_t>(n, 0), x ? (size_t)input_size() : 0);
@@ -935,6 +952,16 @@ template <typename T> struct ModelImpl : surfh_model {
         SURFH_CUDA(cudaGetLastError());
     }
 };
+
+template <typename T>
+void ModelImpl<T>::cg_dot_x_b_plus_r(const void* x, const void* b, const void* r, double* out, cudaStream_t st) {
+    SURFH_REQUIRE(x && b && r && out, "NULL buffer");
+    const size_t n = (size_t)input_size();
+    Scope sc(this, ST_CG, st, 3.0 * n * sizeof(T), 2.0 * n, 1, true);
+    cg_dot_x_b_plus_r_kernel<T><<<cg_grid(n), kCgThreads, 0, st>>>(reinterpret_cast<const T*>(x), reinterpret_cast<const T*>(b),
+                                                                   reinterpret_cast<const T*>(r), n, out, scratch());
+    SURFH_CUDA(cudaGetLastError());
+}
 
 template <> void ModelImpl<float>::gemm_grouped_f64(double*, bool, cudaStream_t) {
     throw Error(SURFH_ESTATE, "internal: fp64 GEMM on an fp32 model");
@@ -1016,9 +1043,28 @@ template <> void ModelImpl<double>::gemm_grouped_f64(double* y, bool adjoint, cu
 }  // namespace surfh
 
 // ------------------------------------------------------------------------------------------------
+// A handle belongs to the device that was current at surfh_create: every entry point runs with that device
+// current (and restores the caller's on exit), so a multi-GPU process cannot launch on the wrong GPU.
+namespace {
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceScope(int want) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != want) {
+            if (cudaSetDevice(want) != cudaSuccess) throw Error(SURFH_ECUDA, "cudaSetDevice(handle's device) failed");
+            switched = true;
+        }
+    }
+    ~DeviceScope() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+}  // namespace
+
 #define SURFH_API_BEGIN(h)                                   \
     if (!(h)) return SURFH_EINVAL;                           \
-    try {
+    try {                                                    \
+        DeviceScope surfh_device_scope_((h)->device);
 #define SURFH_API_END(h)                                     \
     }                                                        \
     catch (const surfh::Error& e) {                          \
@@ -1043,10 +1089,16 @@ template <typename T> struct FftCacheEntry {
 };
 template <typename T> int rfft2_impl(int na, int nb, int batch, int inverse, const void* in, void* out, cudaStream_t st) {
     using Cx = surfh::cplx_t<T>;
-    static std::map<std::pair<int, int>, std::unique_ptr<FftCacheEntry<T>>> cache;
+    // plans (device tables + scratch) are per (device, shape); the cache is process-wide, so calls are
+    // serialised: concurrent callers would otherwise share one scratch buffer
+    static std::map<std::tuple<int, int, int>, std::unique_ptr<FftCacheEntry<T>>> cache;
+    static std::mutex cache_mutex;
     if (!surfh::OwnFft2d<T>::supported(na, nb)) throw Error(SURFH_EINVAL, "surfh_rfft2: axes must be in [2, 1024]");
     if (batch <= 0 || !in || !out) throw Error(SURFH_EINVAL, "surfh_rfft2: bad batch or NULL buffer");
-    auto& e = cache[std::make_pair(na, nb)];
+    int device = 0;
+    SURFH_CUDA(cudaGetDevice(&device));
+    std::lock_guard<std::mutex> lock(cache_mutex);
+    auto& e = cache[std::make_tuple(device, na, nb)];
     if (!e) {
         e = std::make_unique<FftCacheEntry<T>>();
         e->fft.init(na, nb);
@@ -1168,6 +1220,11 @@ int surfh_cg_refresh(surfh_handle h, int32_t phase, void* x, void* r, void* d, c
 int surfh_criterion_terms(surfh_handle h, const void* y, const void* hx, int64_t n, const void* x, double* s_out,
                           void* stream) {
     SURFH_API_BEGIN(h) h->criterion_terms(y, hx, n, x, s_out, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+
+int surfh_cg_dot_x_b_plus_r(surfh_handle h, const void* x, const void* b, const void* r, double* s_out, void* stream) {
+    SURFH_API_BEGIN(h) h->cg_dot_x_b_plus_r(x, b, r, s_out, (cudaStream_t)stream);
     SURFH_API_END(h)
 }
 

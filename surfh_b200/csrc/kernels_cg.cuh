@@ -46,6 +46,14 @@ __device__ __forceinline__ bool finish_reduction(double block_value, double* par
     return threadIdx.x == 0;
 }
 
+// Step length rho / <d,Qd>.  A zero curvature (x0 already the solution: r = d = 0) or a zero residual would
+// give 0/0: the step is then 0, x stays put and the gradient-norm history records 0, which the host's
+// stopping test sees.
+__device__ __forceinline__ double cg_alpha(const double* s) {
+    const double rho = s[0], curv = s[1];
+    return (curv > 0.0 && rho > 0.0) ? rho / curv : 0.0;
+}
+
 // q = mu_s * q + mu_r * stencil(d);  s[1] = <d, q>
 template <typename T>
 __global__ void __launch_bounds__(kCgThreads)
@@ -121,7 +129,7 @@ cg_step_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ d, co
                const T* __restrict__ b, size_t n, double* __restrict__ s, int nscal, CgScratch sc) {
     __shared__ double smem[32];
     const double rho = s[0];
-    const double alpha = rho / s[1];
+    const double alpha = cg_alpha(s);
     double part = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         T rv;
@@ -139,7 +147,7 @@ cg_step_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ d, co
     if (finish_reduction(bs, sc.partial, sc.ticket, smem, total)) {
         const int it = (int)s[4] + 1;
         if (!REFRESH) s[2] = alpha;
-        s[3] = total / rho;
+        s[3] = rho > 0.0 ? total / rho : 0.0;
         s[0] = total;
         s[4] = (double)it;
         s[nscal + it] = total;
@@ -150,7 +158,7 @@ cg_step_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ d, co
 template <typename T>
 __global__ void __launch_bounds__(kCgThreads)
 cg_axpy_alpha_kernel(T* __restrict__ x, const T* __restrict__ d, size_t n, double* __restrict__ s) {
-    const double alpha = s[0] / s[1];
+    const double alpha = cg_alpha(s);
     if (blockIdx.x == 0 && threadIdx.x == 0) s[2] = alpha;  // nobody reads s[2] in this kernel
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         x[i] = (T)((double)x[i] + alpha * (double)d[i]);
@@ -163,6 +171,21 @@ cg_direction_kernel(const T* __restrict__ r, T* __restrict__ d, size_t n, const 
     const double beta = s[3];
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         d[i] = (T)((double)r[i] + beta * (double)d[i]);
+}
+
+// out[0] = <x, b + r>: with r = b - Q x the quadratic criterion is J(x) = c - <x, b + r> / 2,
+// c = mu_s |y|^2 / 2, so the CG state gives J(x_k) without another forward pass.
+template <typename T>
+__global__ void __launch_bounds__(kCgThreads)
+cg_dot_x_b_plus_r_kernel(const T* __restrict__ x, const T* __restrict__ b, const T* __restrict__ r, size_t n,
+                         double* __restrict__ out, CgScratch sc) {
+    __shared__ double smem[32];
+    double part = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        part += (double)x[i] * ((double)b[i] + (double)r[i]);
+    const double bs = block_sum(part, smem);
+    double total;
+    if (finish_reduction(bs, sc.partial, sc.ticket, smem, total)) out[0] = total;
 }
 
 // out[0] = sum (y - hx)^2 ; out[1] = sum (D_r x)^2 + (D_c x)^2

@@ -76,6 +76,24 @@ class ChannelView:
     def name(self):
         return self.instr.name
 
+    def sliceToCube(self, *args, **kwargs):
+        """`Channel.sliceToCube` (spectroModelChannel.py:266) re-projects detector slices onto the cube for
+        plots: a visualisation helper outside the operator path, not provided."""
+        raise NotImplementedError(
+            "surfh_b200: Channel.sliceToCube is a visualisation helper of the reference "
+            "(surfh/Models/spectroModelChannel.py:266) and is outside the forward/adjoint/CG path this "
+            "library replaces; use surfh.Models.spectroModelChannel.Channel for plots")
+
+
+def _viz_stub(name: str, where: str):
+    def method(self, *args, **kwargs):
+        raise NotImplementedError(
+            f"surfh_b200: spectroSigRLSCT.{name} is a host-side visualisation helper of the reference ({where}) "
+            f"and is outside the forward/adjoint/CG path this library replaces; call it on the reference class")
+    method.__name__ = name
+    method.__doc__ = f"Not provided: visualisation helper of the reference ({where})."
+    return method
+
 
 class spectroSigRLSCT(LinOp):
     """Drop-in for `surfh.Models.spectroModel.spectroSigRLSCT`.
@@ -275,11 +293,12 @@ class spectroSigRLSCT(LinOp):
         if _is_torch(maps):
             import torch
             x = self._dev_in(maps, self.isize)
-            alloc = torch.empty if len(self.local_bands) == len(self.band_tables) else torch.zeros
+            # a partial model (band / wavelength shard) does not write every element of y: bands it does not
+            # own, and the detector rows of beta-sum bands outside its wavelength window, must read as zeros
+            alloc = torch.zeros if self.partial else torch.empty
             y = alloc(self.osize, dtype=x.dtype, device=x.device)
             _capi.check(self._h, self._lib.surfh_forward(self._h, x.data_ptr(), y.data_ptr(), self._stream()))
-            if self.comm is not None:
-                self.comm.allreduce_sum(y)
+            self._reduce(y)
             return y
         x = np.ascontiguousarray(np.asarray(maps, dtype=np.float64).reshape(self.ishape))
         y = np.zeros(self.oshape, dtype=np.float64)
@@ -294,8 +313,7 @@ class spectroSigRLSCT(LinOp):
             x = torch.empty(self.ishape, dtype=y.dtype, device=y.device)
             _capi.check(self._h, self._lib.surfh_adjoint(self._h, y.data_ptr(), x.data_ptr(), self.mode_code,
                                                          self._stream()))
-            if self.comm is not None:
-                self.comm.allreduce_sum(x)
+            self._reduce(x)
             return x
         y = np.ascontiguousarray(np.asarray(inarray, dtype=np.float64).reshape(-1))
         if y.size != self.osize:
@@ -330,18 +348,23 @@ class spectroSigRLSCT(LinOp):
         """out = H^T H x on device tensors.  Sharded (partial) models exchange the detector vector
         (all-reduce of the partial sums over wavelength shards) between the two halves and the
         [K, N, N] result at the end; unsharded models run the fused library call."""
-        if self.comm is None or not self.partial:
+        if not self.partial:
+            # every rank holds the whole operator: nothing to sum (a comm on an unsharded model is ignored --
+            # summing W identical copies would scale H^T H by W)
             _capi.check(self._h, self._lib.surfh_fwadj(self._h, x.data_ptr(), out.data_ptr(), self.mode_code, None,
                                                        self._stream()))
-            if self.comm is not None:
-                self.comm.allreduce_sum(out)
             return out
+        if self.comm is None:
+            raise ValueError("a sharded model (lambda_range / local_bands) needs comm= to apply H^T H: "
+                             "the detector vector has to be summed over the shards between H and H^T")
         import torch
         if getattr(self, "_y_shard", None) is None or self._y_shard.dtype != x.dtype:
             self._y_shard = torch.zeros(self.osize, dtype=x.dtype, device=x.device)
         y = self._y_shard
-        if len(self.local_bands) < len(self.band_tables):
-            y.zero_()  # slices of bands this shard does not touch must not carry the previous sum
+        if self._y_needs_zeroing:
+            # elements this shard does not write (bands it does not touch, detector rows of beta-sum bands
+            # outside its wavelength window) still hold the previous application's exchanged SUM
+            y.zero_()
         _capi.check(self._h, self._lib.surfh_forward(self._h, x.data_ptr(), y.data_ptr(), self._stream()))
         # the adjoint of this shard reads only the detector blocks of the bands it touches: sum each shared
         # band among the ranks that hold a share of it (sub-communicators) instead of all-reducing all of y
@@ -354,6 +377,18 @@ class spectroSigRLSCT(LinOp):
         self.comm.allreduce_sum(out)
         return out
 
+    def _reduce(self, tensor):
+        """Sum partial results over the shards.  Only a partial model has anything to sum."""
+        if self.partial and self.comm is not None:
+            self.comm.allreduce_sum(tensor)
+        return tensor
+
+    @property
+    def _y_needs_zeroing(self) -> bool:
+        if len(self.local_bands) < len(self.band_tables):
+            return True
+        return any(self.band_tables[it].lsf is None for it in self.local_bands)
+
     def _band_exchange(self):
         """Collective on first use: every rank of the communicator must reach it (fwadj does)."""
         if getattr(self, "_exchange", None) is None:
@@ -364,6 +399,9 @@ class spectroSigRLSCT(LinOp):
         return self._exchange
 
     fwback = fwadj
+    project_FOV = _viz_stub("project_FOV", "surfh/Models/spectroModel.py:201")
+    plot_slice = _viz_stub("plot_slice", "surfh/Models/spectroModel.py:242")
+    make_mask = _viz_stub("make_mask", "surfh/Models/spectroModel.py:289")
 
     def matvec(self, point):
         return self.forward(point.reshape(self.ishape)).reshape(-1)

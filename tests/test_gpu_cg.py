@@ -77,6 +77,46 @@ def test_run_method_like_main_fusion_and_golden(torch_cuda, golden_dir):
     assert rel(gpu.cubeTomaps(cube.astype(np.float64)), om.lmm_cube2maps(cube.astype(np.float64), cfg.templates)) < 1e-13
 
 
+def test_c2_50_iteration_solve_vs_reference_golden(torch_cuda, golden_dir):
+    """BASELINE.json configs[1] (C2: band 1A, 4 dithers, N = 251, K = 4, 50 CG iterations, mu = 5e3) against the
+    trace of the reference's own QuadCriterion_MRS.run_method('lcg', 50, perf_crit=1, calc_crit=True,
+    value_init=0) on the reference operator (oracle/make_golden.py::run_cg_case; qmm.lcg itself restated, so
+    CG parity stays 'unpinned' in the sense of SURVEY section 8c).  The refresh at iteration 0 is exercised,
+    the iterate after 50 iterations is compared to 1e-8 (50 iterations amplify rounding), the gradient-norm
+    history and the criterion trace to 1e-7 / 1e-10."""
+    from surfh_b200 import fusion_CT
+    from surfh_b200.model import spectroSigRLSCT
+    from surfh_b200 import synthetic
+    gold = np.load(os.path.join(golden_dir, "c2_cg50.npz"))
+    cfg = synthetic.baseline_config("c2")
+    gpu = spectroSigRLSCT(**cfg.model_args())  # reference adjoint, fp64
+    fwd = gpu.forward(cfg.maps)
+    assert abs(np.linalg.norm(fwd) - float(gold["fwd_norm"])) <= 1e-10 * float(gold["fwd_norm"])
+    y = fwd + 0.01 * np.sqrt(np.mean(fwd ** 2)) * np.random.default_rng(99).standard_normal(fwd.shape)
+    quad = fusion_CT.QuadCriterion_MRS(mu_spectro=1, y_spectro=np.copy(y), model_spectro=gpu, mu_reg=float(gold["mu_reg"]))
+    j0 = quad.get_crit_val(np.zeros(gpu.ishape))
+    assert abs(j0 - float(gold["crit_at_zero"])) <= 1e-9 * float(gold["crit_at_zero"])
+    res = quad.run_method("lcg", int(gold["n_iter"]), perf_crit=1, calc_crit=True, value_init=0)
+    assert len(res.grad_norm) == len(gold["cg_grad_norm"])
+    assert np.allclose(res.grad_norm, gold["cg_grad_norm"], rtol=1e-7)
+    assert np.allclose(quad.L_crit_val, gold["cg_crit"], rtol=1e-9)
+    assert rel(res.x[:, ::3, ::3], gold["cg_x_sample"]) <= 1e-8
+    assert abs(np.linalg.norm(res.x) - float(gold["cg_x_norm"])) <= 1e-9 * float(gold["cg_x_norm"])
+    assert abs(quad.get_crit_val(res.x) - float(gold["crit_final"])) <= 1e-10 * float(gold["crit_final"])
+
+
+def test_cg_degenerate_start_does_not_produce_nan(torch_cuda):
+    """x0 already the solution of Q x = b (here: y = 0, x0 = 0): rho = <d,Qd> = 0.  The step must be 0, not
+    0/0 (qmm would divide; the device kernel guards it) and the loop stops on the gradient norm."""
+    from surfh_b200 import fusion_CT
+    from surfh_b200.model import spectroSigRLSCT
+    cfg = CASES["mini_1band_1p"]()
+    gpu = spectroSigRLSCT(**cfg.model_args())
+    res = fusion_CT.lcg(gpu, np.zeros(gpu.osize), 1.0, 5.0, np.zeros(gpu.ishape), tol=1e-12, max_iter=5)
+    assert np.all(np.isfinite(res.x)) and np.all(res.x == 0)
+    assert res.nit == 1 and res.status == 1
+
+
 def test_fp32_cg_tracks_fp64(torch_cuda):
     from surfh_b200 import fusion_CT
     from surfh_b200.model import spectroSigRLSCT

@@ -1,6 +1,6 @@
 """BASELINE.json's full-size workload (C4: 12 MRS bands, K=6, 501x501 maps, 3612 cube wavelengths,
-4 dithers, 18 M detector samples) through size-independent properties -- the CPU oracle needs minutes
-per band at this size, so parity is pinned on the small and single-band cases and carried here by:
+4 dithers, 18 M detector samples): every one of the 12 bands against the CPU oracle (one dither at a time,
+seconds per band), a 100-iteration CG solve, and the size-independent properties:
   * dot-test <Hx, y> = <x, H^T y> in exact mode (1e-6 asked by BASELINE.json; holds to ~1e-12),
   * linearity of forward and of fwadj, symmetry of the normal operator <H^T H x, z> = <x, H^T H z>,
   * band independence: the band-1A block of the 12-band output equals the output of the stand-alone
@@ -86,6 +86,94 @@ def test_c4_fft_backends_agree(c4):
     assert rel(y0, y1) <= 1e-12
     assert rel(model.adjoint(y0), lib.adjoint(y0)) <= 1e-12
     del lib
+
+
+def _oracle_band(cfg, band, pointing, mode):
+    from cases import band_subconfig
+    from surfh_oracle import model as om
+    return om.SpectroLMM(**band_subconfig(cfg, band, pointing), adjoint_mode=mode)
+
+
+def test_c4_every_band_vs_oracle(c4):
+    """Each of the 12 bands of the full-size model against the CPU oracle at that band's real geometry
+    (N = 501, K = 6, the band's own srf / nb / slit layout / LSF), one dither per band (band b uses dither
+    b mod 4, so all four are exercised): the band's [p] block of `forward`, and `adjoint` of a vector that
+    is non-zero only in that block -- both adjoint flavours.  Tolerance: BASELINE.json's 1e-10."""
+    import torch
+    from surfh_b200.model import spectroSigRLSCT
+    cfg, exact, sotf = c4
+    x = torch.as_tensor(cfg.maps, device="cuda")
+    y = exact.forward(x).cpu().numpy()
+    rng = np.random.default_rng(77)
+    probes = {}
+    worst = {"fwd": 0.0, "adj_exact": 0.0, "adj_reference": 0.0}
+    for b in range(len(cfg.instrs)):
+        p = b % 4
+        oracle = _oracle_band(cfg, b, p, "exact")
+        lo, hi = int(exact._idx[b]), int(exact._idx[b + 1])
+        block = y[lo:hi].reshape(exact.instrs_oshape[b])[p]
+        e = rel(block.ravel(), oracle.forward(cfg.maps))
+        worst["fwd"] = max(worst["fwd"], e)
+        assert e <= 1e-10, f"forward, band {cfg.band_names[b]}: {e:.2e}"
+        v = rng.standard_normal(oracle.osize)
+        probes[b] = v
+        full = np.zeros(exact.osize)
+        full[lo:hi].reshape(exact.instrs_oshape[b])[p] = v.reshape(exact.instrs_oshape[b][1:])
+        e = rel(exact.adjoint(full), oracle.adjoint(v))
+        worst["adj_exact"] = max(worst["adj_exact"], e)
+        assert e <= 1e-10, f"exact adjoint, band {cfg.band_names[b]}: {e:.2e}"
+    reference = spectroSigRLSCT(sotf, cfg.templates, cfg.alpha_axis, cfg.beta_axis, cfg.wavelength_axis, cfg.instrs,
+                                cfg.step_degree, cfg.pointings, adjoint_mode="reference")
+    for b in range(len(cfg.instrs)):
+        p = b % 4
+        oracle = _oracle_band(cfg, b, p, "reference")
+        lo, hi = int(reference._idx[b]), int(reference._idx[b + 1])
+        full = np.zeros(reference.osize)
+        full[lo:hi].reshape(reference.instrs_oshape[b])[p] = probes[b].reshape(reference.instrs_oshape[b][1:])
+        e = rel(reference.adjoint(full), oracle.adjoint(probes[b]))
+        worst["adj_reference"] = max(worst["adj_reference"], e)
+        assert e <= 1e-10, f"reference adjoint, band {cfg.band_names[b]}: {e:.2e}"
+    print("C4 per-band worst rel-L2 vs oracle:", worst)
+    del reference
+
+
+def test_c4_100_iteration_solve(c4):
+    """The north-star solve: 100 CG iterations on C4 (fusion_CT.py:194-232 as called by
+    scripts/main_fusion.py:179-190: mu = 5e3, value_init = 0, perf_crit = 1, calc_crit = True).
+      * the criterion trace (every 5th iteration) decreases monotonically and comes from the CG state,
+        i.e. costs no forward pass; its last value equals the explicit evaluation through H to 1e-10;
+      * the exact residual recomputation at iteration 50 (qmm.lcg's refresh) agrees with the recurrence:
+        a run without refresh has the same gradient-norm history to 1e-8 up to and beyond iteration 50;
+      * the solution reproduces the data to the noise level."""
+    import torch
+    from surfh_b200 import fusion_CT
+    cfg, model, _ = c4
+    x_true = torch.as_tensor(cfg.maps, device="cuda")
+    y = model.forward(x_true)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    sigma = 0.01 * float(y.pow(2).mean().sqrt())
+    y = (y + sigma * torch.randn(y.shape, dtype=y.dtype, device="cuda", generator=g)).cpu().numpy()
+    quad = fusion_CT.QuadCriterion_MRS(mu_spectro=1, y_spectro=np.copy(y), model_spectro=model, mu_reg=5e3)
+    launches0 = model.own_launch_count()
+    res = quad.run_method("lcg", 100, perf_crit=1, calc_crit=True, value_init=0)
+    crit = np.asarray(quad.L_crit_val)
+    assert len(res.grad_norm) == 101 and len(crit) == 20
+    assert np.all(np.diff(crit) < 0), crit
+    assert quad._solver()._state_evals == 20
+    explicit = quad._solver().criterion(res.x)
+    j_state = quad._solver().criterion_from_state()
+    assert abs(j_state - explicit) <= 1e-10 * abs(explicit), (j_state, explicit)
+    assert crit[-1] >= explicit * (1 - 1e-9)   # the trace's last entry is from an earlier iterate
+    no_refresh = fusion_CT.lcg(model, y, 1.0, 5e3, np.zeros(model.ishape), tol=1e-12, max_iter=60, refresh=0,
+                               check_every=60)
+    assert np.allclose(no_refresh.grad_norm[:61], res.grad_norm[:61], rtol=1e-8), \
+        np.max(np.abs(np.asarray(no_refresh.grad_norm[:61]) / np.asarray(res.grad_norm[:61]) - 1))
+    hx = model.forward(torch.as_tensor(res.x, device="cuda")).cpu().numpy()
+    misfit = np.sqrt(np.mean((hx - y) ** 2))
+    assert 0.5 * sigma < misfit < 1.5 * sigma, (misfit, sigma)
+    print(f"C4 100-iteration solve: J {crit[0]:.6e} -> {explicit:.6e}, grad_norm {res.grad_norm[0]:.3e} -> "
+          f"{res.grad_norm[-1]:.3e}, misfit/sigma {misfit / sigma:.3f}, "
+          f"{model.own_launch_count() - launches0} own kernel launches")
 
 
 def test_c4_cg_decreases_criterion(c4):

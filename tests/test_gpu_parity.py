@@ -65,6 +65,33 @@ def test_full_size_vs_reference_golden(built, golden_dir, name):
     assert abs(np.linalg.norm(x) - float(gold["adj_norm"])) <= 1e-10 * float(gold["adj_norm"])
 
 
+def test_c3_vs_reference_golden(built, golden_dir):
+    """BASELINE.json configs[2] (C3: bands 1A, 2A, 3A, 4A, K = 4, N = 501, 3612 cube wavelengths, 4 dithers)
+    against the vector the reference's own code produced for the same inputs (oracle/make_golden.py)."""
+    import torch
+    from surfh_b200 import synthetic
+    cfg = CASES["c3"]()
+    gold = np.load(os.path.join(golden_dir, "c3.npz"))
+    dev = torch.device("cuda")
+    sotf = lambda lo, hi: synthetic.ir2fr_device(cfg.psf[lo:hi], cfg.imshape, dev, torch.float64)  # noqa: E731
+    gpu = built(sotf, cfg.templates, cfg.alpha_axis, cfg.beta_axis, cfg.wavelength_axis, cfg.instrs, cfg.step_degree,
+                cfg.pointings, dtype="float64", adjoint_mode="reference")
+    assert np.array_equal(gpu._idx, gold["idx"]) and gpu.ishape == tuple(gold["ishape"])
+    y = gpu.forward(cfg.maps)
+    stride = int(gold["fwd_stride"])
+    assert rel(y[::stride], gold["fwd_sample"]) <= 1e-10
+    assert abs(np.linalg.norm(y) - float(gold["fwd_norm"])) <= 1e-10 * float(gold["fwd_norm"])
+    # every band's block on its own (a band-local error cannot hide behind the others' norm)
+    for c in range(4):
+        lo, hi = int(gold["idx"][c]), int(gold["idx"][c + 1])
+        first = -(-lo // stride) * stride
+        assert rel(y[first:hi:stride], gold["fwd_sample"][first // stride: (hi - 1) // stride + 1]) <= 1e-10
+    v = np.random.default_rng(1234).standard_normal(gpu.osize)
+    x = gpu.adjoint(v)
+    assert rel(x[:, ::7, ::7], gold["adj_sample"]) <= 1e-10
+    assert abs(np.linalg.norm(x) - float(gold["adj_norm"])) <= 1e-10 * float(gold["adj_norm"])
+
+
 @pytest.mark.parametrize("gemm", ["tensor", "simt"])
 def test_fp32_full_size_vs_reference_golden(built, golden_dir, gemm, monkeypatch):
     """fp32 mode at full size (contraction length 3144) against the reference's golden vectors, 1e-5 budget,

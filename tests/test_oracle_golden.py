@@ -55,9 +55,12 @@ def test_oracle_matches_reference_mini(golden_dir, name):
     assert rel(ch0.gridding(blurred[ch0.wslice], ch0.pointings[0])[::4], gold["gridded0"]) < 1e-13
 
 
-def test_oracle_matches_reference_full_size_c1(golden_dir):
-    cfg = CASES["c1_band1a"]()
-    gold = load(golden_dir, "c1_band1a")
+@pytest.mark.parametrize("name", ["c1_band1a", "band3a_n501_4p", "band4a_n501_4p"])
+def test_oracle_matches_reference_full_size(golden_dir, name):
+    """Full-size single bands run by the reference's own code: 1A (C1, N = 251) and, at the north-star
+    map size N = 501 with 4 dithers, one band of channel 3 (srf 9, nb 16) and one of channel 4 (srf 10, nb 26)."""
+    cfg = CASES[name]()
+    gold = load(golden_dir, name)
     model = om.SpectroLMM(**cfg.model_args(), adjoint_mode="reference")
     check_geometry(model, gold)
     y = model.forward(cfg.maps)
@@ -66,6 +69,34 @@ def test_oracle_matches_reference_full_size_c1(golden_dir):
     v = np.random.default_rng(1234).standard_normal(model.osize)
     x = model.adjoint(v)
     assert rel(x[:, ::7, ::7], gold["adj_sample"]) < 1e-13
+
+
+def test_oracle_matches_reference_c3_blocks(golden_dir):
+    """BASELINE.json configs[2] (C3: 1A, 2A, 3A, 4A on the 3612-plane axis, N = 501, 4 dithers) as run by the
+    reference's own code: block offsets and geometry of the 4-band model (tables only, no cube is built), and
+    band 2A's block of the reference output -- the band no single-band N = 501 fixture covers -- from a
+    one-band oracle on that band's window of the same axis."""
+    from cases import band_subconfig
+    from surfh_b200 import geometry, instru
+    cfg = CASES["c3"]()
+    gold = load(golden_dir, "c3")
+    idx = [0]
+    srfs = instru.get_srf([i.det_pix_size for i in cfg.instrs], cfg.step_degree * 3600)
+    for c, (ifu, srf) in enumerate(zip(cfg.instrs, srfs)):
+        ws = ifu.wslice(cfg.wavelength_axis, 0.1)
+        assert tuple(gold[f"b{c}_wslice"]) == (ws.start, ws.stop)
+        assert int(gold[f"b{c}_srf"]) == srf
+        idx.append(idx[-1] + int(np.prod(gold[f"b{c}_oshape"])))
+    assert np.array_equal(idx, gold["idx"])
+    band = 1
+    model = om.SpectroLMM(**band_subconfig(cfg, band), adjoint_mode="reference")
+    assert tuple(gold[f"b{band}_oshape"]) == model.channels[0].oshape
+    y = model.forward(cfg.maps)
+    stride = int(gold["fwd_stride"])
+    lo, hi = int(gold["idx"][band]), int(gold["idx"][band + 1])
+    first = -(-lo // stride) * stride          # first multiple of the stride inside the block
+    want = gold["fwd_sample"][first // stride: (hi - 1) // stride + 1]
+    assert rel(y[first - lo:: stride], want) < 1e-13
 
 
 def test_geometry_all_twelve_bands_match_survey_table():
