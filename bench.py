@@ -27,6 +27,12 @@ import subprocess
 import sys
 import time
 
+if "reference" in sys.argv[1:]:
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must see every host core like a plain
+    # `python bench.py --impl reference` does (all host cores) -- before numpy loads
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ.pop(_v, None)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -48,7 +54,7 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample-pointings", type=int, default=1)
+    ap.add_argument("--solve-iters", type=int, default=100, help="iterations of the timed CG solve (0 = skip)")
     return ap.parse_args()
 
 
@@ -174,36 +180,74 @@ def shard_for_rank(cfg, comm, dtype_bytes):
 
 
 # ------------------------------------------------------------------- CPU reference legs
-def cpu_sample(cfg, n_pointings: int, repeats: int, warmup: int):
-    """Time the CPU oracle on a bounded sample of the workload: the first band of the configuration
-    on its own wavelength window, `n_pointings` pointings, same N, K, dtype fp64, all host threads."""
+def _channel_representatives(cfg):
+    """One band per MRS channel present in the configuration (bands of a channel share S, srf, the local
+    grid, na and nb -- SURVEY section 8d -- so they cost the same per wavelength): [(band index, bands in
+    that channel)]."""
+    groups = {}
+    for i, name in enumerate(cfg.band_names):
+        groups.setdefault(name[0], []).append(i)
+    return [(idx[0], len(idx)) for _, idx in sorted(groups.items())]
+
+
+def cpu_sample(cfg, repeats: int, warmup: int):
+    """Time the CPU oracle (numpy/scipy fp64 restatement of the reference path, all host threads) on a bounded
+    sample of the workload and extrapolate one full application from the sample's OWN stage times.
+
+    Sample = one band per MRS channel, ONE dither, on that band's wavelength window, same N and K.  For each
+    sampled band the global stages (templates T and spatial blur C of the forward, C^T and T^T of the adjoint:
+    per cube plane, independent of the dithers) and the per-dither stages (gridding, box-sum FFTs, slit
+    slicing, spectral response and their adjoints) are timed separately; then
+        t_application = sum_channels bands_in_channel * ( planes_scale * t_global + P * t_per_dither )
+    where planes_scale = (planes of the configuration's union of windows) / (sum of the bands' windows)
+    accounts for the reference transforming every cube plane once however many bands read it."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    from surfh_b200 import synthetic
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cases import band_subconfig
     from surfh_oracle import model as om  # executed here only as the timed CPU baseline
 
     if cfg.templates is None:
         return cpu_sample_blind(cfg, repeats, warmup)
-    band = cfg.band_names[0]
-    k = cfg.templates.shape[0]
-    sub = synthetic.mrs_config([band], len(cfg.alpha_axis), k, n_pointings, seed=0, name=f"{cfg.name}-sample")
-    model = om.SpectroLMM(**sub.model_args(), adjoint_mode="reference")
-    times = []
+    reps = _channel_representatives(cfg)
+    n_point = len(cfg.pointings[0])
+    windows = [i.wslice(cfg.wavelength_axis, 0.1) for i in cfg.instrs]
+    covered = np.zeros(len(cfg.wavelength_axis), dtype=bool)
+    for w in windows:
+        covered[w] = True
+    planes_scale = float(covered.sum()) / float(sum(w.stop - w.start for w in windows))
+    models = [(om.SpectroLMM(**band_subconfig(cfg, b, pointing=0), adjoint_mode="reference"), nb) for b, nb in reps]
+    rng = np.random.default_rng(0)
+    probes = [rng.standard_normal(m.osize) for m, _ in models]
+    samples, estimates = [], []
     for it in range(warmup + repeats):
-        t0 = time.perf_counter()
-        y = model.forward(sub.maps)
-        model.adjoint(y)
-        dt = time.perf_counter() - t0
+        t_sample, t_app = 0.0, 0.0
+        for (m, n_bands), v in zip(models, probes):
+            ch = m.channels[0]
+            t0 = time.perf_counter()
+            blurred = m.blurred_cube(cfg.maps)                     # T, C (global)
+            t1 = time.perf_counter()
+            ch.forward(blurred)                                    # S, Sum, L, Sig R (one dither)
+            t2 = time.perf_counter()
+            cube = m.adjoint_cube(v)                               # R^T Sig^T, L^T, Sum^T, gridding_t (one dither)
+            t3 = time.perf_counter()
+            om.lmm_cube2maps(om.idft(om.dft(cube) * m.sotf.conj(), m.imshape), m.templates)  # C^T, T^T (global)
+            t4 = time.perf_counter()
+            t_global, t_dither = (t1 - t0) + (t4 - t3), (t2 - t1) + (t3 - t2)
+            t_sample += t4 - t0
+            t_app += n_bands * (planes_scale * t_global + n_point * t_dither)
         if it >= warmup:
-            times.append(dt)
-    full_out = full_output_size(cfg)
-    frac = model.osize / full_out
-    t = float(np.median(times))
-    sample = (f"band {band.upper()} of {cfg.name} only (cube axis = that band's window, {len(sub.wavelength_axis)} "
-              f"wavelengths), {n_pointings} pointing(s), K={k}, N={len(cfg.alpha_axis)}, fp64: "
-              f"{model.osize} of {full_out} detector samples = {frac:.4f} of one application in {t:.2f} s "
-              f"(median of {repeats}); value = fraction / seconds")
-    return {"value": frac / t, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample,
-            "seconds_per_sample": t, "sample_fraction": frac}
+            samples.append(t_sample)
+            estimates.append(t_app)
+    t_sample, t_app = float(np.median(samples)), float(np.median(estimates))
+    names = ",".join(cfg.band_names[b].upper() for b, _ in reps)
+    sample = (f"bands {names} of {cfg.name} (one per MRS channel), one of the {n_point} dithers each, on each band's "
+              f"own wavelength window, K={cfg.templates.shape[0]}, N={len(cfg.alpha_axis)}, fp64, forward + adjoint "
+              f"(reference gridding_t): {t_sample:.2f} s per sample (median of {repeats}, {warmup} warm-up); one "
+              f"application extrapolated from the sample's own stage times as sum_channels n_bands * "
+              f"({planes_scale:.3f} * t_global + {n_point} * t_per_dither) = {t_app:.1f} s")
+    return {"value": 1.0 / t_app, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample,
+            "seconds_per_sample": t_sample, "sample_fraction": t_sample / t_app, "extrapolated_application_s": t_app,
+            "repeats": repeats, "warmup": warmup}
 
 
 def cpu_sample_blind(cfg, repeats: int, warmup: int, n_wave: int = 16):
@@ -245,20 +289,25 @@ def full_output_size(cfg) -> int:
 
 
 def run_reference(args):
+    """The CPU arm: one step = one bounded sample (see cpu_sample); `ms_per_step` is the measured sample time,
+    `value` the applications/s extrapolated from it (= sample_fraction / seconds_per_sample)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = build_config(args.config)
-    steps, warm = max(1, min(args.steps, 3)), 1
-    base = cpu_sample(cfg, args.cpu_sample_pointings, steps, warm)
+    steps, warm = max(1, min(args.steps, 3)), min(max(args.warmup, 0), 1)
+    base = cpu_sample(cfg, steps, warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": 1e3 / base["value"], "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * base["seconds_per_sample"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_description(cfg, "float64", args),
+        "step_definition": "one step = one bounded CPU sample of the workload (cpu_baseline.sample); value = "
+                           "sample_fraction / seconds_per_sample, i.e. whole applications per second",
+        "sample_fraction": base["sample_fraction"],
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
     }
     emit(line)
 
@@ -368,13 +417,41 @@ def run_b200(args):
         comm.allreduce_sum(rank_ms)
     rank_ms = [float(v) for v in rank_ms.cpu()]
 
-    # ---- CG iterations
+    # ---- CG iterations (stage events on: the fused vector kernels show up as the `cg_fused` stage row)
     y = model.forward(x)
+    g = torch.Generator(device=dev).manual_seed(1)
+    y = y + 0.01 * y.pow(2).mean().sqrt() * torch.randn(y.shape, dtype=y.dtype, device=dev, generator=g)
     cg = fusion_CT.DeviceCG(model, y, 1.0, 5e3, comm=comm)
     cg.start(np.zeros(model.ishape), args.steps + args.warmup + 8)
-    ms_cg, _, _, _ = timed(lambda: cg.step(False), args.steps, args.warmup)
+    ms_cg, _, _, cg_stages = timed(lambda: cg.step(False), args.steps, args.warmup, profile=True)
     cg_iters = 1e3 * args.steps / ms_cg
-    del cg, y
+    cg_row = next((st for st in cg_stages if st["stage"] == "cg_fused"), None)
+    del cg
+
+    # ---- the north-star solve: `--solve-iters` CG iterations from x0 = 0 (mu_reg = 5e3, refresh every 50,
+    # criterion every 5th iteration from the CG state), wall clock around the whole call, result on the host
+    solve = None
+    if args.solve_iters > 0:
+        quad = fusion_CT.QuadCriterion_MRS(1.0, y, model, 5e3, comm=comm)
+        torch.cuda.synchronize()
+        if comm:
+            comm.barrier()
+        t0 = time.perf_counter()
+        res = quad.run_method("lcg", args.solve_iters, tolerance=1e-12, perf_crit=1, calc_crit=True, value_init=0)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if comm:
+            comm.allreduce_max(dt)
+        solve = {"iterations": int(res.nit), "seconds": float(dt.item()),
+                 "iters_per_s": int(res.nit) / float(dt.item()),
+                 "criterion_first": float(quad.L_crit_val[0]), "criterion_last": float(quad.L_crit_val[-1]),
+                 "criterion_evaluations": len(quad.L_crit_val),
+                 "criterion_forward_passes": len(quad.L_crit_val) - quad._solver()._state_evals,
+                 "grad_norm_first": float(res.grad_norm[0]), "grad_norm_last": float(res.grad_norm[-1]),
+                 "mu_reg": 5e3, "what": "QuadCriterion_MRS.run_method('lcg', n, perf_crit=1, calc_crit=True, "
+                                        "value_init=0) as scripts/main_fusion.py:179-190 calls it; data = H x_true + 1 % noise"}
+        del quad, res
+    del y
 
     # ---- end to end through the LinOp API with host buffers: numpy maps in pinned memory ->
     # spectroSigRLSCT.fwadj (H2D, forward, [all-reduce], adjoint, [all-reduce], D2H) -> numpy maps
@@ -403,6 +480,7 @@ def run_b200(args):
         assert np.isfinite(out_np).all()
         e2e = {"value": rate, "unit": UNIT, "h2d_bytes_per_step": int(8 * model.isize),
                "d2h_bytes_per_step": int(8 * model.isize), "steps": steps_h,
+               "cg_iters_per_s": cg_iters, "cg_solve": solve,
                "path": "spectroSigRLSCT.fwadj (aljabr LinOp.fwadj): float64 numpy maps in pinned host memory -> "
                        "H2D -> forward -> adjoint -> D2H -> numpy maps; wall clock around the calls, max over ranks"}
         if world == 1:
@@ -457,7 +535,16 @@ def run_b200(args):
         if name in traffic:
             row["traffic"] = traffic[name]
         stage_rows.append(row)
-    own_rows = [r for r in stage_rows if r["own"] and r.get("achieved")]
+    if cg_row is not None and cg_row["ms"] > 0:
+        sec = cg_row["ms"] * 1e-3
+        stage_rows.append({"stage": "cg_fused", "ms_per_step": cg_row["ms"] / args.steps, "share": None, "own": True,
+                           "launches_per_step": cg_row["launches"] / args.steps, "bound": "hbm", "unit": "GB/s",
+                           "achieved": cg_row["bytes"] / sec / 1e9, "peak": hbm_peak,
+                           "frac": cg_row["bytes"] / sec / 1e9 / hbm_peak,
+                           "algorithmic_bytes_per_launch": cg_row["bytes"] / max(1, cg_row["launches"]),
+                           "note": "per CG iteration, outside the application's timed region; the vectors "
+                                   "(K*N^2 reals) are L2-resident, the cost is launch latency"})
+    own_rows = [r for r in stage_rows if r["own"] and r.get("achieved") and r.get("share") is not None]
     top = max(own_rows, key=lambda r: r["ms_per_step"]) if own_rows else None
     roofline = None
     if top:
@@ -465,21 +552,23 @@ def run_b200(args):
                     "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top.get("frac"),
                     "traffic": top.get("traffic"),
                     "peak_source": peak_src if top["unit"] == "GB/s" else fp_peak["source"],
-                    "share_of_step": top["share"]}
+                    "share_of_step": top["share"],
+                    "fp_peak": {"tflops": fp_peak["tflops"], "source": fp_peak["source"]},
+                    "hbm_peak": {"gbs": hbm_peak, "source": peak_src}}
         for k in ("tflops", "frac_of_fp_peak", "limiter", "algorithmic_bytes_per_launch"):
             if k in top:
                 roofline[k] = top[k]
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cpu = cpu_sample(cfg, args.cpu_sample_pointings, 1, 0)
+        cpu = cpu_sample(cfg, 1, 0)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64" if esz == 8 else "f32", "data": "synthetic", "config": workload_description(cfg, args.dtype, args),
-        "cg_iters_per_s": cg_iters, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "cg_iters_per_s": cg_iters, "cg_solve": solve, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "stages": stage_rows, "cpu_baseline": cpu,
         "per_rank_kernel_ms": rank_ms, "exchange_and_idle_ms": ms_step - max(rank_ms),
         "setup_s": setup_s, "lambda_range_rank0": lam_range, "workspace_gb": model.workspace_bytes() / 1e9,

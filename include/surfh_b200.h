@@ -190,6 +190,31 @@ int surfh_criterion_terms(surfh_handle h, const void* y, const void* hx, int64_t
  * (fusion_CT.py:242-265 as called from the lcg callback, :164-192) without the extra forward pass. */
 int surfh_cg_dot_x_b_plus_r(surfh_handle h, const void* x, const void* b, const void* r, double* s_out, void* stream);
 
+/* y += s[idx] * x on n reals, the scalar read on the device (e.g. idx = 2: the step length alpha of the last
+ * surfh_cg_update).  Keeps H x_k = H x_{k-1} + alpha H d alongside the iterate, so the criterion of
+ * fusion_CT.py:242-265 is evaluated on the running iterate from (y, H x_k, x_k) without applying H again
+ * (H d is the y_scratch of surfh_fwadj). */
+int surfh_axpy_device_scalar(surfh_handle h, void* y, const void* x, int64_t n, const double* s, int32_t idx,
+                             void* stream);
+
+/* ---- Fourier-domain block preconditioner ------------------------------ */
+/* Builds, per spatial frequency f, P(f) = ( mu_s * sum_l w_l |OTF_l(f)|^2 T_l T_l^T + mu_r * d(f)^p I )^-1
+ * (K x K, p = 1: separated gradients, p = 2: joint), d = eigenvalue of the circular 5-point Laplacian.
+ * Replaces the per-frequency Hessian of `Model_WCT` (surfh/Models/mixing.py:131-207, `hess_spec_freq`) and its
+ * bin-wise inverse `Inv_Regul_Fusion_Model3` (surfh/ToolsDir/fusion_mixing.py:401-438,
+ * algorithms.make_iHtH_spectro), used here as the `precond` of qmm.lcg.  w_lambda: [host] [n_lambda] mean gain
+ * of the detector sampling at each cube wavelength (0 where no band observes).  Synchronises. */
+int surfh_precond_build(surfh_handle h, const double* w_lambda, double mu_s, double mu_r, int32_t joint);
+/* z = P r on n_maps*[n_alpha,n_beta] device vectors: K-map FFT, per-bin K x K product, K-map inverse FFT */
+int surfh_precond_apply(surfh_handle h, const void* r, void* z, void* stream);
+/* Preconditioned lcg iteration, scalars as for surfh_cg_*: s[0] holds rho_z = <r, z> between calls, s[5] too.
+ * phase 0: alpha = s[0]/s[1]; x += alpha d; r -= alpha q; <r,r> appended to the history.
+ * phase 1: r = b - q with q = Q x (exact residual refresh), <r,r> appended. */
+int surfh_pcg_update(surfh_handle h, int32_t phase, void* x, void* r, const void* d, const void* q, const void* b, double* s,
+                     void* stream);
+/* rho_z' = <r, z>; beta = rho_z'/rho_z (0 when first != 0); d = z + beta d */
+int surfh_pcg_direction(surfh_handle h, const void* r, const void* z, void* d, double* s, int32_t first, void* stream);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* number of kernels (own + cuFFT exec calls) this handle has launched since creation */
 int64_t surfh_launch_count(surfh_handle h);

@@ -24,6 +24,7 @@
 #include "kernels_cg.cuh"
 #include "kernels_gemm.cuh"
 #include "kernels_lmm.cuh"
+#include "kernels_precond.cuh"
 #include "kernels_slit.cuh"
 
 namespace surfh {
@@ -89,6 +90,12 @@ struct surfh_model {
     virtual void criterion_terms(const void* y, const void* hx, int64_t n, const void* x, double* out,
                                  cudaStream_t st) = 0;
     virtual void cg_dot_x_b_plus_r(const void* x, const void* b, const void* r, double* out, cudaStream_t st) = 0;
+    virtual void axpy_device_scalar(void* y, const void* x, int64_t n, const double* s, int idx, cudaStream_t st) = 0;
+    virtual void precond_build(const double* w, double mu_s, double mu_r, int joint) = 0;
+    virtual void precond_apply(const void* r, void* z, cudaStream_t st) = 0;
+    virtual void pcg_update(int phase, void* x, void* r, const void* d, const void* q, const void* b, double* s,
+                            cudaStream_t st) = 0;
+    virtual void pcg_direction(const void* r, const void* z, void* d, double* s, int first, cudaStream_t st) = 0;
 
     struct Scope {
         surfh_model* m; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
@@ -225,7 +232,7 @@ template <typename T> struct ModelImpl : surfh_model {
         SURFH_REQUIRE(fft_backend == SURFH_FFT_AUTO || fft_backend == SURFH_FFT_CUFFT || fft_backend == SURFH_FFT_OWN,
                       "unknown fft_backend");
         SURFH_REQUIRE(fft_backend != SURFH_FFT_OWN || OwnFft2d<T>::supported(Na, Nb),
-                      "fft_backend = own needs both map axes <= 1024 pixels");
+                      "fft_backend = own needs both map axes <= 512 pixels");
         if (const char* e = std::getenv("SURFH_FFT_PRUNE")) prune_rows = std::strcmp(e, "0") != 0;
         use_own_fft = fft_backend == SURFH_FFT_OWN || (fft_backend == SURFH_FFT_AUTO && OwnFft2d<T>::supported(Na, Nb));
         own_fft_names = use_own_fft;
@@ -262,7 +269,9 @@ template <typename T> struct ModelImpl : surfh_model {
             dsrc = tmp.as<double2>();
         }
         dim3 grid(ceil_div(nfp, 256), l_count);
-        otf_convert_kernel<T><<<grid, 256>>>(dsrc, otf.as<C>() + (size_t)l_start * nfp, nf, nfp, l_count);
+        // the hand-written FFT keeps every half spectrum transposed ([Nh][Na]: contiguous columns); cuFFT's is [Na][Nh]
+        otf_convert_kernel<T><<<grid, 256>>>(dsrc, otf.as<C>() + (size_t)l_start * nfp, nf, nfp, l_count, Na, Nh,
+                                             use_own_fft ? 1 : 0);
         SURFH_CUDA(cudaGetLastError());
         SURFH_CUDA(cudaDeviceSynchronize());
         for (int l = l_start; l < l_start + l_count; ++l) otf_set[l] = 1;
@@ -590,10 +599,10 @@ template <typename T> struct ModelImpl : surfh_model {
             }
             if (kind == 0)
                 ownfft.r2c(reinterpret_cast<const T*>(in), plane, reinterpret_cast<C*>(out), nfp, zbuf.as<C>(), batch, st,
-                           pr, n_pairs);
+                           true, pr, n_pairs);
             else
                 ownfft.c2r(reinterpret_cast<const C*>(in), nfp, reinterpret_cast<T*>(out), plane, zbuf.as<C>(), batch, st,
-                           pr, n_pairs);
+                           true, pr, n_pairs);
             return;
         }
         cufftHandle p = plan(kind, batch);
@@ -942,6 +951,100 @@ template <typename T> struct ModelImpl : surfh_model {
         SURFH_CUDA(cudaGetLastError());
     }
     void cg_dot_x_b_plus_r(const void* x, const void* b, const void* r, double* out, cudaStream_t st) override;
+
+    // ---- Fourier-domain block preconditioner (kernels_precond.cuh) ------------------------------
+    DevBuf precond_inv;   // [K*K][nfp] real
+    bool precond_ready = false;
+    template <int KK> void launch_precond_gram(const double* w, double* gram) {
+        dim3 grid(ceil_div(nfp, 32)), block(32, kGramLanes);
+        precond_gram_kernel<T, KK><<<grid, block>>>(otf.as<C>(), tpl_raw.as<T>(), Nl, w, Nl, nfp, gram);
+    }
+    template <int KK> void launch_precond_factor(const double* gram, double mu_s, double mu_r, int power) {
+        precond_factor_kernel<T, KK><<<ceil_div(nfp, 128), 128>>>(gram, nf, nfp, Na, Nb, Nh, use_own_fft ? 1 : 0, mu_s, mu_r,
+                                                                  power, precond_inv.as<T>());
+    }
+    template <int KK> void launch_precond_apply(cudaStream_t st) {
+        precond_apply_kernel<T, KK><<<ceil_div(nfp, 256), 256, 0, st>>>(precond_inv.as<T>(), xhat.as<C>(), nfp,
+                                                                        (T)(1.0 / ((double)Na * (double)Nb)));
+    }
+    void precond_build(const double* w, double mu_s, double mu_r, int joint) override {
+        require_ready();
+        SURFH_REQUIRE(K > 0, "the Fourier-domain preconditioner needs templates (LMM model)");
+        SURFH_REQUIRE(w != nullptr, "NULL wavelength weights");
+        SURFH_REQUIRE(mu_s >= 0.0 && mu_r >= 0.0 && mu_s + mu_r > 0.0, "bad hyper-parameters");
+        for (int l = 0; l < Nl; ++l)
+            SURFH_REQUIRE(w[l] >= 0.0 && (w[l] == 0.0 || otf_set[l]), "weight on a wavelength whose OTF was never uploaded");
+        DevBuf dw, gram;
+        dw.alloc((size_t)Nl * sizeof(double));
+        SURFH_CUDA(cudaMemcpy(dw.p, w, (size_t)Nl * sizeof(double), cudaMemcpyHostToDevice));
+        gram.alloc((size_t)(K * (K + 1) / 2) * nfp * sizeof(double));
+        precond_inv.alloc((size_t)K * K * nfp * sizeof(T));
+        SURFH_DISPATCH_K(launch_precond_gram, dw.as<double>(), gram.as<double>());
+        SURFH_CUDA(cudaGetLastError());
+        SURFH_DISPATCH_K(launch_precond_factor, gram.as<double>(), mu_s, mu_r, joint ? 2 : 1);
+        SURFH_CUDA(cudaGetLastError());
+        SURFH_CUDA(cudaDeviceSynchronize());
+        own_launches += 2; launches += 2;
+        precond_ready = true;
+    }
+    // z = P r : K-map R2C, per-bin K x K product, K-map C2R (xhat is the scratch spectrum)
+    void precond_apply(const void* r, void* z, cudaStream_t st) override {
+        require_ready();
+        SURFH_REQUIRE(precond_ready, "surfh_precond_build has not been called");
+        SURFH_REQUIRE(r && z, "NULL buffer");
+        {
+            Scope sc(this, ST_RFFT_MAPS, st, fft_bytes(K, -1), fft_flops(K, -1), fft_launches(), use_own_fft);
+            fft_exec(0, K, const_cast<void*>(r), xhat.p, st);
+        }
+        {
+            Scope sc(this, ST_CG, st, (double)K * nf * sizeof(C) * 2 + (double)K * K * nf * sizeof(T), 4.0 * K * K * nf, 1, true);
+            SURFH_DISPATCH_K(launch_precond_apply, st);
+            SURFH_CUDA(cudaGetLastError());
+        }
+        Scope sc(this, ST_IRFFT_MAPS, st, fft_bytes(K, -1), fft_flops(K, -1), fft_launches(), use_own_fft);
+        fft_exec(1, K, xhat.p, z, st);
+    }
+    // phase 0: x += alpha d, r -= alpha q (alpha = s[0] / s[1], s[0] = rho_z);  phase 1: r = b - q (q = Q x: refresh)
+    void pcg_update(int phase, void* x, void* r, const void* d, const void* q, const void* b, double* s,
+                    cudaStream_t st) override {
+        const size_t n = (size_t)input_size();
+        SURFH_REQUIRE(r && q && s, "NULL buffer");
+        Scope sc(this, ST_CG, st, 6.0 * n * sizeof(T), 6.0 * n, 1, true);
+        if (phase == 0) {
+            SURFH_REQUIRE(x && d, "NULL buffer");
+            cg_step_kernel<T, false><<<cg_grid(n), kCgThreads, 0, st>>>(
+                reinterpret_cast<T*>(x), reinterpret_cast<T*>(r), reinterpret_cast<const T*>(d),
+                reinterpret_cast<const T*>(q), nullptr, n, s, SURFH_CG_NSCALARS, scratch());
+        } else {
+            SURFH_REQUIRE(b, "NULL buffer");
+            cg_step_kernel<T, true><<<cg_grid(n), kCgThreads, 0, st>>>(
+                nullptr, reinterpret_cast<T*>(r), nullptr, reinterpret_cast<const T*>(q),
+                reinterpret_cast<const T*>(b), n, s, SURFH_CG_NSCALARS, scratch());
+        }
+        SURFH_CUDA(cudaGetLastError());
+    }
+    // rho_z' = <r, z>, beta = rho_z' / rho_z, d = z + beta d  (first: d = z)
+    void pcg_direction(const void* r, const void* z, void* d, double* s, int first, cudaStream_t st) override {
+        const size_t n = (size_t)input_size();
+        SURFH_REQUIRE(r && z && d && s, "NULL buffer");
+        Scope sc(this, ST_CG, st, 5.0 * n * sizeof(T), 4.0 * n, 2, true);
+        if (first)
+            pcg_dot_kernel<T, true><<<cg_grid(n), kCgThreads, 0, st>>>(reinterpret_cast<const T*>(r),
+                                                                        reinterpret_cast<const T*>(z), n, s, scratch());
+        else
+            pcg_dot_kernel<T, false><<<cg_grid(n), kCgThreads, 0, st>>>(reinterpret_cast<const T*>(r),
+                                                                         reinterpret_cast<const T*>(z), n, s, scratch());
+        cg_direction_kernel<T><<<cg_grid(n), kCgThreads, 0, st>>>(reinterpret_cast<const T*>(z), reinterpret_cast<T*>(d), n, s);
+        SURFH_CUDA(cudaGetLastError());
+    }
+    void axpy_device_scalar(void* y, const void* x, int64_t n, const double* s, int idx, cudaStream_t st) override {
+        SURFH_REQUIRE(y && x && s && n >= 0 && idx >= 0, "axpy: bad argument");
+        if (n == 0) return;
+        Scope sc(this, ST_CG, st, 3.0 * n * sizeof(T), 2.0 * n, 1, true);
+        axpy_device_scalar_kernel<T><<<cg_grid((size_t)n), kCgThreads, 0, st>>>(reinterpret_cast<T*>(y),
+                                                                                reinterpret_cast<const T*>(x), (size_t)n, s, idx);
+        SURFH_CUDA(cudaGetLastError());
+    }
     void criterion_terms(const void* y, const void* hx, int64_t n, const void* x, double* out, cudaStream_t st) override {
         SURFH_REQUIRE(out, "NULL buffer");
         const size_t nmax = std::max<size_t>((size_t)std::max<int64_t>(n, 0), x ? (size_t)input_size() : 0);
@@ -1093,7 +1196,7 @@ template <typename T> int rfft2_impl(int na, int nb, int batch, int inverse, con
     // serialised: concurrent callers would otherwise share one scratch buffer
     static std::map<std::tuple<int, int, int>, std::unique_ptr<FftCacheEntry<T>>> cache;
     static std::mutex cache_mutex;
-    if (!surfh::OwnFft2d<T>::supported(na, nb)) throw Error(SURFH_EINVAL, "surfh_rfft2: axes must be in [2, 1024]");
+    if (!surfh::OwnFft2d<T>::supported(na, nb)) throw Error(SURFH_EINVAL, "surfh_rfft2: axes must be in [2, 512]");
     if (batch <= 0 || !in || !out) throw Error(SURFH_EINVAL, "surfh_rfft2: bad batch or NULL buffer");
     int device = 0;
     SURFH_CUDA(cudaGetDevice(&device));
@@ -1105,8 +1208,8 @@ template <typename T> int rfft2_impl(int na, int nb, int batch, int inverse, con
     }
     e->z.ensure((size_t)batch * e->fft.z_plane() * sizeof(Cx));
     const size_t rp = (size_t)na * nb, sp = (size_t)na * (nb / 2 + 1);
-    if (!inverse) e->fft.r2c(reinterpret_cast<const T*>(in), rp, reinterpret_cast<Cx*>(out), sp, e->z.template as<Cx>(), batch, st);
-    else e->fft.c2r(reinterpret_cast<const Cx*>(in), sp, reinterpret_cast<T*>(out), rp, e->z.template as<Cx>(), batch, st);
+    if (!inverse) e->fft.r2c(reinterpret_cast<const T*>(in), rp, reinterpret_cast<Cx*>(out), sp, e->z.template as<Cx>(), batch, st, false);
+    else e->fft.c2r(reinterpret_cast<const Cx*>(in), sp, reinterpret_cast<T*>(out), rp, e->z.template as<Cx>(), batch, st, false);
     return SURFH_OK;
 }
 }  // namespace
@@ -1225,6 +1328,29 @@ int surfh_criterion_terms(surfh_handle h, const void* y, const void* hx, int64_t
 
 int surfh_cg_dot_x_b_plus_r(surfh_handle h, const void* x, const void* b, const void* r, double* s_out, void* stream) {
     SURFH_API_BEGIN(h) h->cg_dot_x_b_plus_r(x, b, r, s_out, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+
+int surfh_axpy_device_scalar(surfh_handle h, void* y, const void* x, int64_t n, const double* s, int32_t idx, void* stream) {
+    SURFH_API_BEGIN(h) h->axpy_device_scalar(y, x, n, s, idx, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+
+int surfh_precond_build(surfh_handle h, const double* w_lambda, double mu_s, double mu_r, int32_t joint) {
+    SURFH_API_BEGIN(h) h->precond_build(w_lambda, mu_s, mu_r, joint);
+    SURFH_API_END(h)
+}
+int surfh_precond_apply(surfh_handle h, const void* r, void* z, void* stream) {
+    SURFH_API_BEGIN(h) h->precond_apply(r, z, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+int surfh_pcg_update(surfh_handle h, int32_t phase, void* x, void* r, const void* d, const void* q, const void* b, double* s,
+                     void* stream) {
+    SURFH_API_BEGIN(h) h->pcg_update(phase, x, r, d, q, b, s, (cudaStream_t)stream);
+    SURFH_API_END(h)
+}
+int surfh_pcg_direction(surfh_handle h, const void* r, const void* z, void* d, double* s, int32_t first, void* stream) {
+    SURFH_API_BEGIN(h) h->pcg_direction(r, z, d, s, first, (cudaStream_t)stream);
     SURFH_API_END(h)
 }
 

@@ -1,8 +1,8 @@
 // Host side of the hand-written 2-D real FFT pair (kernels_fft.cuh): table construction and launches.
 //
 // Replaces the cuFFT plans for the reference's `rfftn` / `irfftn(norm="ortho")` calls
-// (surfh/ToolsDir/jax_utils.py:30-41, python_utils.py:41-71) whenever both map axes are <= 1024
-// pixels; the transforms are un-normalised like cuFFT's.
+// (surfh/ToolsDir/jax_utils.py:30-41, python_utils.py:41-71) whenever both map axes are <= 512
+// pixels (every size the reference uses: 251, 301, 501); the transforms are un-normalised like cuFFT's.
 #pragma once
 #include <cmath>
 #include <vector>
@@ -12,13 +12,12 @@
 
 namespace surfh {
 
-// Dispatch on the chirp-z length (a power of two in [256, 2048]).
+// Dispatch on the chirp-z length (a power of two in [256, 1024]).
 #define SURFH_DISPATCH_M(m, ...)                                       \
     switch (m) {                                                       \
         case 256: { constexpr int MM = 256; __VA_ARGS__; } break;      \
         case 512: { constexpr int MM = 512; __VA_ARGS__; } break;      \
         case 1024: { constexpr int MM = 1024; __VA_ARGS__; } break;    \
-        case 2048: { constexpr int MM = 2048; __VA_ARGS__; } break;    \
         default: throw Error(SURFH_EINVAL, "unsupported chirp-z length"); \
     }
 
@@ -34,9 +33,9 @@ template <typename T> struct FftAxis {
     int n = 0, m = 0;
     DevBuf chirp, filt, tw;
 
-    // smallest supported chirp-z length for n points: n <= m/2 (so 2n-1 <= m); 0 when n > 1024
+    // smallest supported chirp-z length for n points: n <= m/2 (so 2n-1 <= m); 0 when n > 512
     static int pick_m(int n) {
-        for (int m = 256; m <= 2048; m *= 2)
+        for (int m = 256; m <= 1024; m *= 2)
             if (n <= m / 2) return m;
         return 0;
     }
@@ -47,28 +46,30 @@ template <typename T> struct FftAxis {
     }
     template <int M> static void set_smem_attr() {
         set_pass_attr<M, RowsR2C<T, M>>();
-        set_pass_attr<M, ColsPass<T, M, false>>();
-        set_pass_attr<M, ColsPass<T, M, true>>();
+        set_pass_attr<M, ColsPass<T, M, false, false>>();
+        set_pass_attr<M, ColsPass<T, M, true, false>>();
+        set_pass_attr<M, ColsPass<T, M, false, true>>();
+        set_pass_attr<M, ColsPass<T, M, true, true>>();
         set_pass_attr<M, RowsC2R<T, M>>();
     }
 
     void init(int n_) {
         n = n_;
         m = pick_m(n);
-        if (m == 0) throw Error(SURFH_EINVAL, "axis too long for the hand-written FFT (max 1024)");
+        if (m == 0) throw Error(SURFH_EINVAL, "axis too long for the hand-written FFT (max 512)");
         const double pi = 3.14159265358979323846;
         // everything is evaluated in double, the filter spectrum with the double instantiation of the
         // very FFT code that consumes it, and only then rounded to T
-        const int tt = m / 16, r3 = m / 256, ntw = m + 16 * r3;
+        const int pts = m / 32, r3 = 32 / pts, ntw = m + pts * r3;
         std::vector<double2> h_tw(ntw), h_chirp(n), h_b(m);
         auto root = [&](long long e) {  // exp(-2 pi i e / m)
             const double a = -2.0 * pi * (double)(e % m) / (double)m;
             return make_double2(std::cos(a), std::sin(a));
         };
-        for (int q = 0; q < 16; ++q)
-            for (int t = 0; t < tt; ++t) h_tw[q * tt + t] = root((long long)q * t);
-        for (int q2 = 0; q2 < 16; ++q2)
-            for (int n2 = 0; n2 < r3; ++n2) h_tw[m + q2 * r3 + n2] = root(16ll * n2 * q2);
+        for (int k1 = 0; k1 < pts; ++k1)
+            for (int t = 0; t < 32; ++t) h_tw[k1 * 32 + t] = root((long long)k1 * t);
+        for (int q2 = 0; q2 < pts; ++q2)
+            for (int n2 = 0; n2 < r3; ++n2) h_tw[m + q2 * r3 + n2] = root((long long)pts * n2 * q2);  // exp(-2 pi i n2 q2 / 32)
         for (int j = 0; j < m; ++j) h_b[j] = make_double2(0.0, 0.0);
         for (int j = 0; j < n; ++j) {
             const long long q = ((long long)j * j) % (2ll * n);  // exp(-i pi j^2 / n) has period 2n in j^2
@@ -85,11 +86,12 @@ template <typename T> struct FftAxis {
         SURFH_CUDA(cudaMemcpy(d_tw.p, h_tw.data(), ntw * sizeof(double2), cudaMemcpyHostToDevice));
         SURFH_CUDA(cudaMemcpy(d_b.p, h_b.data(), m * sizeof(double2), cudaMemcpyHostToDevice));
         SURFH_DISPATCH_M(m, {
-            const int bytes = (int)FftK<double, MM>::SMEM_BYTES_FILTER;
+            using KD = FftK<double, MM>;
+            const int bytes = (int)((KD::OFF_BUF + KD::BUF) * sizeof(double2));
             SURFH_CUDA(cudaFuncSetAttribute(fft_filter_kernel<double, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
             FftPlan1d<double> pd;
             pd.chirp = nullptr; pd.filt = nullptr; pd.tw = d_tw.as<double2>(); pd.n = n;
-            fft_filter_kernel<double, MM><<<1, FftK<double, MM>::NT, bytes>>>(d_b.as<double2>(), pd, d_filt.as<double2>());
+            fft_filter_kernel<double, MM><<<1, 32, bytes>>>(d_b.as<double2>(), pd, d_filt.as<double2>());
             set_smem_attr<MM>();
         });
         SURFH_CUDA(cudaGetLastError());
@@ -150,48 +152,57 @@ template <typename T> struct OwnFft2d {
         return s;
     }
 
-    // persistent launch: one CTA per SM, each walking the steps (G transforms at a time) with a grid stride
-    template <int MM, typename Pass> void launch(const Pass& pass, long long n_steps, const FftAxis<T>& ax, cudaStream_t st) const {
-        if (n_steps >= (1ll << 31)) throw Error(SURFH_EINVAL, "FFT batch too large");
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(n_steps, n_sm));
-        fft_pass_kernel<T, MM, Pass><<<grid, FftK<T, MM>::NT, FftK<T, MM>::SMEM_BYTES, st>>>(pass, ax.plan());
+    // persistent launch: one CTA per SM, each of its G warps walking its own items with a grid stride
+    template <int MM, typename Pass> void launch(const Pass& pass, long long n_items, const FftAxis<T>& ax, cudaStream_t st) const {
+        using K = FftK<T, MM>;
+        if (n_items >= (1ll << 31)) throw Error(SURFH_EINVAL, "FFT batch too large");
+        const long long ctas = (n_items + K::G - 1) / K::G;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ctas, n_sm));
+        fft_pass_kernel<T, MM, Pass><<<grid, K::NT, K::SMEM_BYTES, st>>>(pass, ax.plan());
     }
 
-    // in: real [batch] planes (stride real_plane) -> spec: [batch][na][nh] (stride spec_plane); z: scratch
+    // in: real [batch] planes (stride real_plane) -> spec (stride spec_plane): [na][nh], or [nh][na] when
+    // `transposed`; z: scratch.
     // pair_range: [device] per-plane (first row pair, count) outside of which the input rows are zero, or NULL;
     // n_pairs: sum of the counts (host copy), ignored without pair_range
     void r2c(const T* in, size_t real_plane, C* spec, size_t spec_plane, C* z, int batch, cudaStream_t st,
-             const int2* pair_range = nullptr, long long n_pairs = 0) const {
+             bool transposed, const int2* pair_range = nullptr, long long n_pairs = 0) const {
         const FftShape s = shape(real_plane, spec_plane, batch, pair_range);
         const long long row_items = pair_range ? n_pairs : (long long)batch * s.npair;
         SURFH_DISPATCH_M(axis_b->m, {
-            using K = FftK<T, MM>;
             RowsR2C<T, MM> pass{in, z, s};
-            launch<MM>(pass, (row_items + K::G - 1) / K::G, *axis_b, st);
+            launch<MM>(pass, row_items, *axis_b, st);
         });
         SURFH_DISPATCH_M(axis_a.m, {
-            using K = FftK<T, MM>;
-            ColsPass<T, MM, false> pass{z, spec, s};
-            launch<MM>(pass, (long long)batch * ((nh + K::G - 1) / K::G), axis_a, st);
+            if (transposed) {
+                ColsPass<T, MM, false, true> pass{z, spec, s};
+                launch<MM>(pass, (long long)batch * nh, axis_a, st);
+            } else {
+                ColsPass<T, MM, false, false> pass{z, spec, s};
+                launch<MM>(pass, (long long)batch * nh, axis_a, st);
+            }
         });
         SURFH_CUDA(cudaGetLastError());
     }
 
-    // spec: [batch][na][nh] -> out: real planes; z: scratch
+    // spec -> out: real planes; z: scratch
     // pair_range: per-plane row pairs of the output that are wanted (the others are left untouched), or NULL
     void c2r(const C* spec, size_t spec_plane, T* out, size_t real_plane, C* z, int batch, cudaStream_t st,
-             const int2* pair_range = nullptr, long long n_pairs = 0) const {
+             bool transposed, const int2* pair_range = nullptr, long long n_pairs = 0) const {
         const FftShape s = shape(real_plane, spec_plane, batch, pair_range);
         const long long row_items = pair_range ? n_pairs : (long long)batch * s.npair;
         SURFH_DISPATCH_M(axis_a.m, {
-            using K = FftK<T, MM>;
-            ColsPass<T, MM, true> pass{spec, z, s};
-            launch<MM>(pass, (long long)batch * ((nh + K::G - 1) / K::G), axis_a, st);
+            if (transposed) {
+                ColsPass<T, MM, true, true> pass{spec, z, s};
+                launch<MM>(pass, (long long)batch * nh, axis_a, st);
+            } else {
+                ColsPass<T, MM, true, false> pass{spec, z, s};
+                launch<MM>(pass, (long long)batch * nh, axis_a, st);
+            }
         });
         SURFH_DISPATCH_M(axis_b->m, {
-            using K = FftK<T, MM>;
             RowsC2R<T, MM> pass{z, out, s};
-            launch<MM>(pass, (row_items + K::G - 1) / K::G, *axis_b, st);
+            launch<MM>(pass, row_items, *axis_b, st);
         });
         SURFH_CUDA(cudaGetLastError());
     }

@@ -164,6 +164,35 @@ cg_axpy_alpha_kernel(T* __restrict__ x, const T* __restrict__ d, size_t n, doubl
         x[i] = (T)((double)x[i] + alpha * (double)d[i]);
 }
 
+// y += s[idx] * x on n elements (the detector-space companion of x += alpha d: H x_k kept by linearity)
+template <typename T>
+__global__ void __launch_bounds__(kCgThreads)
+axpy_device_scalar_kernel(T* __restrict__ y, const T* __restrict__ x, size_t n, const double* __restrict__ s, int idx) {
+    const double a = s[idx];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = (T)((double)y[i] + a * (double)x[i]);
+}
+
+// Preconditioned CG: rho_z' = <r, z> (z = P r);  last block: beta = rho_z' / rho_z (s[5], 0 on the first call:
+// FIRST), s[3] = beta, s[5] = rho_z', and s[0] = rho_z' so that the next step length of the plain-CG update
+// kernels, s[0] / s[1], is rho_z / <d, Q d>.
+template <typename T, bool FIRST>
+__global__ void __launch_bounds__(kCgThreads)
+pcg_dot_kernel(const T* __restrict__ r, const T* __restrict__ z, size_t n, double* __restrict__ s, CgScratch sc) {
+    __shared__ double smem[32];
+    double part = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        part += (double)r[i] * (double)z[i];
+    const double bs = block_sum(part, smem);
+    double total;
+    if (finish_reduction(bs, sc.partial, sc.ticket, smem, total)) {
+        const double old = FIRST ? 0.0 : s[5];
+        s[3] = old > 0.0 ? total / old : 0.0;
+        s[5] = total;
+        s[0] = total;
+    }
+}
+
 // d = r + beta d
 template <typename T>
 __global__ void __launch_bounds__(kCgThreads)

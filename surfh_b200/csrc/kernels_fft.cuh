@@ -10,27 +10,35 @@
 // operator application.  Here each 1-D transform of length N is ONE chirp-z (Bluestein) evaluation
 // kept entirely in registers + shared memory:
 //     X[k] = a[k] * sum_n (x[n] a[n]) conj(a)[k-n],   a[n] = exp(-i pi n^2 / N)
-// i.e. chirp multiply on load -> radix-16 x radix-16 x radix-R3 FFT of length M = 256*R3 >= 2N-1
-// (decimation in frequency, output left in digit-reversed order) -> pointwise multiply with the
-// precomputed, identically permuted spectrum of the chirp filter -> the mirrored inverse FFT
-// (decimation in time, natural order out) -> chirp multiply on store.  No bit-reversal pass exists.
+// i.e. chirp multiply on load -> FFT of length M >= 2N-1 (decimation in frequency, output left in a
+// digit-scrambled order) -> pointwise multiply with the precomputed, identically scrambled spectrum of
+// the chirp filter -> the mirrored inverse FFT -> chirp multiply on store.  No bit-reversal pass exists.
 //
-// Execution model: ONE persistent CTA per SM walks the work items with a grid stride.
-//   * All tables (twiddles, filter spectrum, chirp) live in shared memory for the CTA's lifetime, so
-//     every table read has shared-memory latency; the only global traffic is the data itself.
-//   * The inputs of item i+1 are copied global -> shared by cp.async into thread-private slots while
-//     item i is transformed: HBM latency is off the critical path at 12 warps per SM.
-//   * A transform is spread over TT = M/16 threads that hold 16 points each; a CTA runs G transforms
-//     side by side, split into independent groups that synchronise with their own named barrier
-//     so that one group's shared-memory phases overlap the others' FP64 phases.
-//   * Of the 4 register<->register exchanges of one chirp-z, 2 go through shared memory (one barrier
-//     each), 2 are transposes among R3 adjacent lanes done with warp shuffles.
+// Execution model (round 2: ONE WARP = ONE TRANSFORM).
+//   * A transform of length M = 32 * PTS lives in the 32 lanes of one warp, PTS = 8 / 16 / 32 points per
+//     lane (M = 256 / 512 / 1024): FFT = radix-PTS in registers x radix-PTS in registers x radix-(32/PTS)
+//     among adjacent lanes by warp shuffles.  For M = 1024 (the 501-pixel maps) that is 32 x 32: two register
+//     stages and ONE transpose through shared memory, nothing else.  The only synchronisation inside a
+//     transform is __syncwarp(): no CTA or named barrier exists in the steady state, so the G warps of a CTA
+//     drift apart freely and one warp's shared-memory phase overlaps the others' FP64 phases.
+//   * ONE persistent CTA per SM; every warp walks its own stream of work items with a grid stride.  The
+//     chirp and the filter spectrum live in shared memory for the CTA's lifetime.  In fp64 the inter-stage
+//     twiddles w^k are generated from the lane's single root w (held in registers) by a multiplication chain:
+//     the kernels are co-limited by the FP64 pipe and the shared-memory crossbar, and a chain step costs 4
+//     FP64 instructions where a table read costs 4 shared-memory wavefronts per warp.
+//   * The inputs of a warp's next item are copied global -> shared by cp.async into that warp's staging
+//     buffer (natural order; every lane copies exactly the elements it will consume, so cp.async.wait_group
+//     is all the synchronisation the staging needs) while the current item is transformed.
 //
 // 2-D real transforms use the two-for-one trick: a pair of real rows is transformed as one complex row.
 //   R2C:  rows_r2c  real [Na][Nb] -> A/B-separated half spectra Y [Na][Nh]   (separation through the
-//                   transform's own shared buffer)            ->  cols  (-> spec [Na][Nh])
-//   C2R:  cols_c2r  spec [Na][Nh] -> Z [ceil(Na/2)][Nb], Z[p] = W[2p] + i W[2p+1] Hermitian-extended
+//                   warp's own shared buffer)                  ->  cols  (-> spectrum)
+//   C2R:  cols_c2r  spectrum -> Z [ceil(Na/2)][Nb], Z[p] = W[2p] + i W[2p+1] Hermitian-extended
 //                   (rows 2p, 2p+1 sit in adjacent lanes: pairing by shuffle) ->  rows_c2r (-> real [Na][Nb])
+// Spectrum layout: the operator keeps every half spectrum (OTF, map spectra, the working cube's spectrum)
+// TRANSPOSED, [Nh][Na]: a column of the 2-D transform is then one contiguous run of Na complex numbers, read
+// and written by the column passes as 512-byte warp accesses; the pointwise OTF / template kernels do not
+// care about the order.  The stand-alone surfh_rfft2 keeps numpy's [Na][Nh] (SPEC_T = false).
 // In the operator the rows passes only visit the row pairs some band's field of view touches (FftRanges).
 #pragma once
 #include "common.cuh"
@@ -39,84 +47,62 @@
 #ifndef SURFH_FFT_TWIDDLE_CHAIN
 #define SURFH_FFT_TWIDDLE_CHAIN 1
 #endif
-#ifndef SURFH_FFT_GROUPS
-#define SURFH_FFT_GROUPS 3
+#ifndef SURFH_FFT_WARPS_F64_1024
+#define SURFH_FFT_WARPS_F64_1024 8
 #endif
 
 namespace surfh {
 
 // Geometry of one chirp-z length M for arithmetic type T.
 template <typename T, int M> struct FftK {
-    static_assert(M == 256 || M == 512 || M == 1024 || M == 2048, "chirp-z length must be 256..2048");
+    static_assert(M == 256 || M == 512 || M == 1024, "chirp-z length must be 256, 512 or 1024");
     using C = cplx_t<T>;
-    static constexpr int R3 = M / 256;          // last radix: 1, 2, 4, 8
-    static constexpr int TT = M / 16;           // threads per transform
-    // 16 complex doubles per thread need ~168 registers to stay out of local memory: 384 threads per SM
-    // in fp64 (256 for M = 2048, whose tables are twice as large); fp32 runs 512 threads at 128 registers
-    static constexpr int NT = sizeof(T) == 8 ? (M == 2048 ? 256 : 384) : 512;
-    static constexpr int G = NT / TT;           // transforms per CTA step
-    // independently synchronised groups (named barriers 1..NH): one group's shared-memory phases overlap
-    // the others' FP64 phases.  Measured at N = 501 fp64 (ms per 512 planes, R2C / C2R): 2 groups 2.39 / 2.40,
-    // 3 groups 2.17 / 2.36, 6 groups (one transform each) 2.96 / 3.08 -- the transforms interleaved lane-wise
-    // inside a group keep the column accesses in contiguous runs, so fewer, fatter groups win.
-    static constexpr int pick_groups() {
-        int best = 1;
-        for (int nh = 1; nh <= SURFH_FFT_GROUPS && nh <= G; ++nh)
-            if (G % nh == 0 && (NT / nh) % 32 == 0) best = nh;
-        return best;
-    }
-    static constexpr int NH = pick_groups();
-    static constexpr int HT = NT / NH;          // threads per group
-    static constexpr int GH = G / NH;           // transforms per group
-    static_assert(GH * NH * TT == NT && HT % 32 == 0 && NH <= 15, "CTA shape");
-    // Exchange buffer of one transform: 16 blocks of TT elements (block q = the q-th sub-sequence) at pitch
-    // TP, buffers at pitch BUF.  A 128-byte wavefront serves 8/R3 (or 16/R3 in fp32) consecutive
-    // (block, transform) pairs of R3 elements each: with several transforms per group the pad of BUF
-    // staggers them over the banks, with one transform per group the pad of TP staggers the blocks.
-    static constexpr int TP = TT + (GH == 1 ? R3 : 0);
-    static constexpr int BUF = 16 * TP + R3;
-    // natural index n of the transform <-> its slot in the buffer (block n / TT, element n % TT)
-    __host__ __device__ static constexpr int slot(int n) { return n + (n / TT) * (TP - TT); }
-    static constexpr int N_TW = M + 16 * R3;    // tw1[q*TT + t] then tw2[q2*R3 + n2]
+    static constexpr int TT = 32;               // lanes per transform: one warp
+    static constexpr int PTS = M / 32;          // points per lane: 8, 16, 32
+    static constexpr int R3 = 32 / PTS;         // last radix, among adjacent lanes: 4, 2, 1
+    static constexpr int HP = PTS / 2;          // live points per lane on the zero-padded side
     static constexpr int HALF = M / 2;          // the transform length N must be <= HALF
-    static constexpr int SLOTS = 8;             // staged complex-sized elements per thread
-    // The kernels are bound by shared-memory (LSU) wavefronts while the FP64 pipe has slack, so in fp64 the
-    // inter-stage twiddles w^q, q = 1..15, are generated from the one loaded value w by a multiplication
-    // chain (+14 complex products, -14 table reads of 16 bytes per stage; error <= 15 ulp on |w^q| = 1).
-    // fp32 keeps the table: its FMA pipe is not idle and its tolerance is tighter relative to eps.
+    // warps (= transforms in flight) per CTA: 32 complex doubles per lane need ~250 registers (8 warps fill the
+    // register file), 16 need ~200 (10 warps); fp32 halves both
+    static constexpr int G = sizeof(T) == 8 ? (M == 1024 ? SURFH_FFT_WARPS_F64_1024 : 10) : 16;
+    static constexpr int NT = 32 * G;
+    // Exchange buffer of one transform: PTS rows (row k1 = the k1-th output of every lane's first-stage DFT)
+    // of 32 elements at pitch TP.  The transposed read of lane (q, n2) walks row q from element n2 in steps of
+    // R3: the pad of R3 elements staggers the rows over the banks (conflict-free per 128-byte wavefront).
+    static constexpr int TP = 32 + R3;
+    static constexpr int BUF = PTS * TP;
+    // natural index n of the transform <-> its slot in the buffer (row n / 32, element n % 32)
+    __host__ __device__ static constexpr int slot(int n) { return n + (n / 32) * (TP - 32); }
+    static constexpr int N_TW = M + PTS * R3;   // tw1[k1*32 + t] then tw2[q2*R3 + n2]
+    // fp64: twiddles by multiplication chains from the lane's root (error <= PTS ulp on |w^k| = 1); fp32 keeps
+    // the tables (its tolerance is tighter relative to eps, and its FMA pipe is not idle)
     static constexpr bool CHAIN = SURFH_FFT_TWIDDLE_CHAIN && sizeof(T) == 8;
     // shared-memory layout, in units of C
-    static constexpr int OFF_TW = 0;
-    static constexpr int OFF_FILT = OFF_TW + N_TW;
+    static constexpr int OFF_FILT = 0;
     static constexpr int OFF_CHIRP = OFF_FILT + M;
-    static constexpr int OFF_BUF = OFF_CHIRP + HALF;
+    static constexpr int OFF_TW = OFF_CHIRP + HALF;
+    static constexpr int OFF_BUF = OFF_TW + (CHAIN ? 0 : N_TW);
     static constexpr int OFF_STAGE = OFF_BUF + G * BUF;
-    static constexpr int N_SMEM = OFF_STAGE + SLOTS * NT;
+    static constexpr int N_SMEM = OFF_STAGE + G * HALF;
     // after the complex area: per-plane row-pair ranges of a pruned launch (start[MAX_PLANES+1], lo[MAX_PLANES])
     static constexpr int MAX_PLANES = 512;
     static constexpr size_t OFF_RANGES_BYTES = (size_t)N_SMEM * sizeof(C);
     static constexpr size_t SMEM_BYTES = OFF_RANGES_BYTES + (2 * MAX_PLANES + 2) * sizeof(int);
-    static constexpr size_t SMEM_BYTES_FILTER = (size_t)OFF_STAGE * sizeof(C);
+    static_assert(SMEM_BYTES <= 232448, "shared-memory budget of one CTA (227 KB)");
 };
 
-// Who am I: transform g (of G), thread t (of TT) = q*R3 + n2.  The R3 threads that exchange registers
-// in the last radix stage are adjacent lanes; the GH transforms of a group are interleaved next, so that a
-// warp touches GH adjacent columns in a column pass.  `half` = index of the barrier group.
-template <typename T, int M> struct FftThread {
+// Who am I inside the warp: lane = q*R3 + n2.  The R3 lanes that exchange registers in the last radix stage
+// are adjacent; `w1` / `w2` are the lane's twiddle roots (chains), read once per kernel.
+template <typename T, int M> struct FftLane {
     using K = FftK<T, M>;
-    int half, g, t, q, n2;
-    __device__ __forceinline__ FftThread(int tid) {
-        half = tid / K::HT;
-        const int l = tid % K::HT;
-        n2 = l % K::R3;
-        const int c = l / K::R3;
-        g = half * K::GH + c % K::GH;
-        q = c / K::GH;
-        t = q * K::R3 + n2;
-    }
-    // barrier among the threads of this group only
-    __device__ __forceinline__ void sync() const {
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "n"(K::HT) : "memory");
+    int lane, q, n2;
+    cplx_t<T> w1, w2;   // exp(-2 pi i lane / M), exp(-2 pi i n2 / 32)
+    __device__ __forceinline__ FftLane(int lane_, const cplx_t<T>* tw_global) {
+        lane = lane_;
+        n2 = lane % K::R3;
+        q = lane / K::R3;
+        w1 = tw_global[32 + lane];
+        w2 = tw_global[M + K::R3 + n2];
     }
 };
 
@@ -281,13 +267,13 @@ template <typename C> __device__ __forceinline__ C shfl_xor_c(C a, int lane_mask
 }
 
 // In-register transpose among the R3 adjacent lanes n2 = 0..R3-1 of one group: for every block c of R3
-// registers, thread n2 ends up with v[c*R3 + n] = (thread n's v[c*R3 + n2]).  Self-inverse.
-template <int R3, typename C> __device__ __forceinline__ void group_transpose(C* v, int n2) {
+// registers (PTS registers in all), thread n2 ends up with v[c*R3 + n] = (thread n's v[c*R3 + n2]).  Self-inverse.
+template <int R3, int PTS, typename C> __device__ __forceinline__ void group_transpose(C* v, int n2) {
 #pragma unroll
     for (int s = R3 / 2; s >= 1; s >>= 1) {
         const bool up = (n2 & s) != 0;
 #pragma unroll
-        for (int c = 0; c < 16 / R3; ++c)
+        for (int c = 0; c < PTS / R3; ++c)
 #pragma unroll
             for (int j = 0; j < R3; ++j) {
                 if (j & s) continue;
@@ -300,123 +286,197 @@ template <int R3, typename C> __device__ __forceinline__ void group_transpose(C*
     }
 }
 
-// Length-M forward FFT of the sequence held as v[m] = x[t + TT*m]; the result stays in registers in a
-// digit-reversed order that only fft_inv() (and the filter table built by the same code) needs to know.
-// `buf` is this transform's shared buffer, `tw` the shared twiddle table.  PRE_SYNC: other threads may
-// still be reading this buffer from the previous step (the passes that post-process through it).
-template <typename T, int M, bool HALF_IN, bool PRE_SYNC>
-__device__ __forceinline__ void fft_fwd(cplx_t<T>* v, cplx_t<T>* buf, const FftThread<T, M>& th, const cplx_t<T>* tw) {
-    using C = cplx_t<T>;
-    using K = FftK<T, M>;
-    constexpr int R3 = K::R3, TT = K::TT;
-    if (HALF_IN) dft16_in8<false>(v);  // v[8..15] are the zero padding
-    else dft16<false>(v);
-    if (PRE_SYNC) th.sync();
-    if (K::CHAIN) {
-        const C w = tw[TT + th.t];
-        C pw = w;
-        buf[th.t] = v[0];
-#pragma unroll
-        for (int q = 1; q < 16; ++q) {
-            buf[q * K::TP + th.t] = cmul(v[q], pw);
-            if (q < 15) pw = cmul(pw, w);
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            C x = v[q];
-            if (q) x = cmul(x, tw[q * TT + th.t]);
-            buf[q * K::TP + th.t] = x;
-        }
-    }
-    th.sync();
-    C* blk = buf + th.q * K::TP;
-#pragma unroll
-    for (int m = 0; m < 16; ++m) v[m] = blk[th.n2 + R3 * m];
-    dft16<false>(v);
-    if (R3 > 1) {
-        if (K::CHAIN) {
-            const C w = tw[M + R3 + th.n2];
-            C pw = w;
-#pragma unroll
-            for (int q2 = 1; q2 < 16; ++q2) {
-                v[q2] = cmul(v[q2], pw);
-                if (q2 < 15) pw = cmul(pw, w);
-            }
-        } else {
-#pragma unroll
-            for (int q2 = 1; q2 < 16; ++q2) v[q2] = cmul(v[q2], tw[M + q2 * R3 + th.n2]);
-        }
-        group_transpose<R3>(v, th.n2);
-#pragma unroll
-        for (int c = 0; c < 16 / R3; ++c) dft_r<false, R3>(v + c * R3);
+
+// cos / sin of 2 pi E / 32
+constexpr double kCos32[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                               0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                               0.19509032201612826785, 0.0, -0.19509032201612826785, -0.38268343236508977173,
+                               -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
+                               -0.92387953251128675613, -0.98078528040323044913};
+constexpr double kSin32[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
+                               0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613,
+                               0.98078528040323044913, 1.0, 0.98078528040323044913, 0.92387953251128675613,
+                               0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
+                               0.38268343236508977173, 0.19509032201612826785};
+
+// a * exp(-+ 2 pi i E / 32) (forward / inverse), E in [0, 16)
+template <bool INV, int E, typename C> __device__ __forceinline__ C mul_w32(C a) {
+    using R = decltype(a.x);
+    if constexpr (E == 0) return a;
+    else if constexpr (E == 8) return rot90<INV>(a);
+    else if constexpr (E == 4) return mul_w16<INV, 2>(a);
+    else if constexpr (E == 12) return mul_w16<INV, 6>(a);
+    else {
+        constexpr double c = kCos32[E], sn = kSin32[E];
+        C w;
+        w.x = R(c);
+        w.y = R(-sn);
+        return twmul<INV>(a, w);
     }
 }
 
-// Mirror of fft_fwd: takes the digit-reversed spectrum in registers, returns M * x[t + TT*m] in v[m].
-template <typename T, int M, bool HALF_OUT>
-__device__ __forceinline__ void fft_inv(cplx_t<T>* v, cplx_t<T>* buf, const FftThread<T, M>& th, const cplx_t<T>* tw) {
+// first level of the 32-point DFT for the pair (m, m + 16), m = I .. 15
+template <bool INV, int MODE, int I, typename C> __device__ __forceinline__ void dft32_level1(C* v) {
+    if constexpr (I < 16) {
+        if (MODE == 1) {
+            v[I + 16] = mul_w32<INV, I>(v[I]);
+        } else {
+            const C a = v[I], b = v[I + 16];
+            v[I] = cadd(a, b);
+            v[I + 16] = mul_w32<INV, I>(csub(a, b));
+        }
+        dft32_level1<INV, MODE, I + 1>(v);
+    }
+}
+
+// 32-point DFT, natural order in and out: one radix-2 decimation-in-frequency level, then two 16-point DFTs.
+// MODE 0: full.  MODE 1: inputs v[16..31] are zero (the zero padding of the chirp-z input; they are not read).
+// MODE 2: only the outputs X[0..15] are wanted (left in v[0..15]; v[16..31] are garbage).
+template <bool INV, int MODE, typename C> __device__ __forceinline__ void dft32(C* v) {
+    dft32_level1<INV, MODE, 0>(v);
+    C o[32];
+    if (MODE == 2) {
+        dft16_out8<INV>(v);        // X[2k]   = E[k]
+        dft16_out8<INV>(v + 16);   // X[2k+1] = O[k]
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { o[2 * k] = v[k]; o[2 * k + 1] = v[16 + k]; }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = o[k];
+    } else {
+        dft16<INV>(v);
+        dft16<INV>(v + 16);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { o[2 * k] = v[k]; o[2 * k + 1] = v[16 + k]; }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = o[k];
+    }
+}
+
+// PTS-point DFT over the lane's registers, natural order in and out.  MODE as for dft32 (the 8-point version
+// ignores it: its callers zero-fill / discard the unused half).
+template <bool INV, int PTS, int MODE, typename C> __device__ __forceinline__ void dft_pts(C* v) {
+    if (PTS == 32) dft32<INV, MODE>(v);
+    if (PTS == 16) {
+        if (MODE == 1) dft16_in8<INV>(v);
+        else if (MODE == 2) dft16_out8<INV>(v);
+        else dft16<INV>(v);
+    }
+    if (PTS == 8) dft8<INV>(v);
+}
+
+// Length-M forward FFT of the sequence held as v[m] = x[lane + 32*m]; the result stays in registers in a
+// digit-scrambled order that only fft_inv() (and the filter table built by the same code) needs to know
+// (natural -- X[lane + 32*j] in v[j] -- when R3 == 1).  `buf` is this warp's shared buffer, `tw` the shared
+// twiddle tables (unused with chains).  HALF_IN: v[PTS/2..] are the zero padding.
+template <typename T, int M, bool HALF_IN>
+__device__ __forceinline__ void fft_fwd(cplx_t<T>* v, cplx_t<T>* buf, const FftLane<T, M>& th, const cplx_t<T>* tw) {
     using C = cplx_t<T>;
     using K = FftK<T, M>;
-    constexpr int R3 = K::R3, TT = K::TT;
-    if (R3 > 1) {
-#pragma unroll
-        for (int c = 0; c < 16 / R3; ++c) dft_r<true, R3>(v + c * R3);
-        group_transpose<R3>(v, th.n2);
-        if (K::CHAIN) {
-            const C w = tw[M + R3 + th.n2];
-            C pw = w;
-#pragma unroll
-            for (int q2 = 1; q2 < 16; ++q2) {
-                v[q2] = cmul_conj(pw, v[q2]);
-                if (q2 < 15) pw = cmul(pw, w);
-            }
-        } else {
-#pragma unroll
-            for (int q2 = 1; q2 < 16; ++q2) v[q2] = cmul_conj(tw[M + q2 * R3 + th.n2], v[q2]);
-        }
-    }
-    dft16<true>(v);
-    // these are the very locations this thread read in fft_fwd: no barrier needed before the writes
-    C* blk = buf + th.q * K::TP;
-#pragma unroll
-    for (int m = 0; m < 16; ++m) blk[th.n2 + R3 * m] = v[m];
-    th.sync();
+    constexpr int R3 = K::R3, PTS = K::PTS;
+    dft_pts<false, PTS, HALF_IN ? 1 : 0>(v);
+    __syncwarp();  // the previous item's post-processing may still be reading this buffer
     if (K::CHAIN) {
-        const C w = tw[TT + th.t];
-        C pw = w;
-        v[0] = buf[th.t];
+        C pw = th.w1;
+        buf[th.lane] = v[0];
 #pragma unroll
-        for (int qq = 1; qq < 16; ++qq) {
-            v[qq] = cmul_conj(pw, buf[qq * K::TP + th.t]);
-            if (qq < 15) pw = cmul(pw, w);
+        for (int k1 = 1; k1 < PTS; ++k1) {
+            buf[k1 * K::TP + th.lane] = cmul(v[k1], pw);
+            if (k1 < PTS - 1) pw = cmul(pw, th.w1);
         }
     } else {
 #pragma unroll
-        for (int qq = 0; qq < 16; ++qq) {
-            C x = buf[qq * K::TP + th.t];
-            if (qq) x = cmul_conj(tw[qq * TT + th.t], x);
-            v[qq] = x;
+        for (int k1 = 0; k1 < PTS; ++k1) {
+            C x = v[k1];
+            if (k1) x = cmul(x, tw[k1 * 32 + th.lane]);
+            buf[k1 * K::TP + th.lane] = x;
         }
     }
-    if (HALF_OUT) dft16_out8<true>(v);  // only x[t + TT*m], m < 8, is wanted
-    else dft16<true>(v);
+    __syncwarp();
+    C* blk = buf + th.q * K::TP;
+#pragma unroll
+    for (int m = 0; m < PTS; ++m) v[m] = blk[th.n2 + R3 * m];
+    dft_pts<false, PTS, 0>(v);
+    if (R3 > 1) {
+        if (K::CHAIN) {
+            C pw = th.w2;
+#pragma unroll
+            for (int q2 = 1; q2 < PTS; ++q2) {
+                v[q2] = cmul(v[q2], pw);
+                if (q2 < PTS - 1) pw = cmul(pw, th.w2);
+            }
+        } else {
+#pragma unroll
+            for (int q2 = 1; q2 < PTS; ++q2) v[q2] = cmul(v[q2], tw[M + q2 * R3 + th.n2]);
+        }
+        group_transpose<R3, PTS>(v, th.n2);
+#pragma unroll
+        for (int c = 0; c < PTS / R3; ++c) dft_r<false, R3>(v + c * R3);
+    }
+}
+
+// Mirror of fft_fwd: takes the scrambled spectrum in registers, returns M * x[lane + 32*m] in v[m].
+// HALF_OUT: only m < PTS/2 is wanted.
+template <typename T, int M, bool HALF_OUT>
+__device__ __forceinline__ void fft_inv(cplx_t<T>* v, cplx_t<T>* buf, const FftLane<T, M>& th, const cplx_t<T>* tw) {
+    using C = cplx_t<T>;
+    using K = FftK<T, M>;
+    constexpr int R3 = K::R3, PTS = K::PTS;
+    if (R3 > 1) {
+#pragma unroll
+        for (int c = 0; c < PTS / R3; ++c) dft_r<true, R3>(v + c * R3);
+        group_transpose<R3, PTS>(v, th.n2);
+        if (K::CHAIN) {
+            C pw = th.w2;
+#pragma unroll
+            for (int q2 = 1; q2 < PTS; ++q2) {
+                v[q2] = cmul_conj(pw, v[q2]);
+                if (q2 < PTS - 1) pw = cmul(pw, th.w2);
+            }
+        } else {
+#pragma unroll
+            for (int q2 = 1; q2 < PTS; ++q2) v[q2] = cmul_conj(tw[M + q2 * R3 + th.n2], v[q2]);
+        }
+    }
+    dft_pts<true, PTS, 0>(v);
+    // these are the very locations this lane read in fft_fwd: no barrier needed before the writes
+    C* blk = buf + th.q * K::TP;
+#pragma unroll
+    for (int m = 0; m < PTS; ++m) blk[th.n2 + R3 * m] = v[m];
+    __syncwarp();
+    if (K::CHAIN) {
+        C pw = th.w1;
+        v[0] = buf[th.lane];
+#pragma unroll
+        for (int k1 = 1; k1 < PTS; ++k1) {
+            v[k1] = cmul_conj(pw, buf[k1 * K::TP + th.lane]);
+            if (k1 < PTS - 1) pw = cmul(pw, th.w1);
+        }
+    } else {
+#pragma unroll
+        for (int k1 = 0; k1 < PTS; ++k1) {
+            C x = buf[k1 * K::TP + th.lane];
+            if (k1) x = cmul_conj(tw[k1 * 32 + th.lane], x);
+            v[k1] = x;
+        }
+    }
+    dft_pts<true, PTS, HALF_OUT ? 2 : 0>(v);
 }
 
 // Device tables of one 1-D chirp-z plan (length n through M-point FFTs), in global memory; the kernels
-// copy them to shared memory once per CTA.
+// copy chirp and filter (and, without chains, the twiddles) to shared memory once per CTA.
 template <typename T> struct FftPlan1d {
     const cplx_t<T>* chirp;  // [n]   a[j] = exp(-i pi j^2 / n)
-    const cplx_t<T>* filt;   // [M]   FFT_M(conj(a) wrapped) / M, in fft_fwd's register order [j*TT + t]
-    const cplx_t<T>* tw;     // [M + 16*R3]  tw[q*TT + t] = exp(-2 pi i t q / M), then
-                             //              tw[M + q2*R3 + n2] = exp(-2 pi i n2 q2 / TT)
+    const cplx_t<T>* filt;   // [M]   FFT_M(conj(a) wrapped) / M, in fft_fwd's register order [j*32 + lane]
+    const cplx_t<T>* tw;     // [M + PTS*R3]  tw[k1*32 + t] = exp(-2 pi i t k1 / M), then
+                             //               tw[M + q2*R3 + n2] = exp(-2 pi i n2 q2 / 32)
     int n;
 };
 
 template <typename T, int M>
 __device__ __forceinline__ void fft_load_tables(cplx_t<T>* smem, const FftPlan1d<T>& p, bool with_filter) {
     using K = FftK<T, M>;
-    for (int i = threadIdx.x; i < K::N_TW; i += blockDim.x) smem[K::OFF_TW + i] = p.tw[i];
+    if (!K::CHAIN)
+        for (int i = threadIdx.x; i < K::N_TW; i += blockDim.x) smem[K::OFF_TW + i] = p.tw[i];
     if (with_filter) {
         for (int i = threadIdx.x; i < M; i += blockDim.x) smem[K::OFF_FILT + i] = p.filt[i];
         for (int i = threadIdx.x; i < p.n; i += blockDim.x) smem[K::OFF_CHIRP + i] = p.chirp[i];
@@ -424,44 +484,44 @@ __device__ __forceinline__ void fft_load_tables(cplx_t<T>* smem, const FftPlan1d
     __syncthreads();
 }
 
-// Circular convolution with the chirp filter: v[m] = (u * conj(a))[t + TT*m] for m < 8, with u given
-// the same way and u[t + TT*m] = 0 for m >= 8 (v[8..15] are ignored on entry, garbage on exit).
-template <typename T, int M, bool PRE_SYNC>
-__device__ __forceinline__ void chirp_convolve(cplx_t<T>* v, cplx_t<T>* smem, cplx_t<T>* buf, const FftThread<T, M>& th) {
+// Circular convolution with the chirp filter: v[m] = (u * conj(a))[lane + 32*m] for m < PTS/2, with u given
+// the same way and u[lane + 32*m] = 0 for m >= PTS/2 (v[PTS/2..] are ignored on entry -- except for PTS == 8,
+// whose callers zero them -- and garbage on exit).
+template <typename T, int M>
+__device__ __forceinline__ void chirp_convolve(cplx_t<T>* v, cplx_t<T>* smem, cplx_t<T>* buf, const FftLane<T, M>& th) {
     using K = FftK<T, M>;
-    fft_fwd<T, M, true, PRE_SYNC>(v, buf, th, smem + K::OFF_TW);
+    fft_fwd<T, M, true>(v, buf, th, smem + K::OFF_TW);
     const cplx_t<T>* filt = smem + K::OFF_FILT;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = cmul(v[j], filt[j * K::TT + th.t]);
+    for (int j = 0; j < K::PTS; ++j) v[j] = cmul(v[j], filt[j * 32 + th.lane]);
     fft_inv<T, M, true>(v, buf, th, smem + K::OFF_TW);
 }
 
 // Builds FftPlan1d::filt from the natural-order filter `b` (already scaled by 1/M) with the very code
-// that consumes it, so the digit-reversed order never has to be spelled out.  One CTA.
+// that consumes it, so the scrambled order never has to be spelled out.  One warp.
 template <typename T, int M>
-__global__ void __launch_bounds__(FftK<T, M>::NT, 1)
+__global__ void __launch_bounds__(32, 1)
 fft_filter_kernel(const cplx_t<T>* __restrict__ b, FftPlan1d<T> p, cplx_t<T>* __restrict__ filt) {
     using C = cplx_t<T>;
     using K = FftK<T, M>;
     extern __shared__ __align__(16) unsigned char fft_smem[];
     C* smem = reinterpret_cast<C*>(fft_smem);
     fft_load_tables<T, M>(smem, p, false);
-    const FftThread<T, M> th(threadIdx.x);
-    C* buf = smem + K::OFF_BUF + th.g * K::BUF;
-    C v[16];
+    const FftLane<T, M> th(threadIdx.x, p.tw);
+    C* buf = smem + K::OFF_BUF;
+    C v[K::PTS];
 #pragma unroll
-    for (int m = 0; m < 16; ++m) v[m] = b[th.t + K::TT * m];
-    fft_fwd<T, M, false, false>(v, buf, th, smem + K::OFF_TW);
-    if (th.g == 0)
+    for (int m = 0; m < K::PTS; ++m) v[m] = b[th.lane + 32 * m];
+    fft_fwd<T, M, false>(v, buf, th, smem + K::OFF_TW);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) filt[j * K::TT + th.t] = v[j];
+    for (int j = 0; j < K::PTS; ++j) filt[j * 32 + th.lane] = v[j];
 }
 
 struct FftShape {
     int na, nb, nh;          // rows, columns, nb/2+1
     int npair;               // ceil(na / 2)
     size_t real_plane;       // elements between real planes
-    size_t spec_plane;       // complex elements between spectrum planes ([na][nh], row pitch nh)
+    size_t spec_plane;       // complex elements between spectrum planes
     size_t z_plane;          // complex elements between planes of the intermediate buffer
     int batch;
     // Pruned transforms: per plane, only the row pairs [lo, lo + cnt) of the real image matter (C2R: the
@@ -530,89 +590,89 @@ __device__ __forceinline__ FftRanges fft_build_ranges(int* smem_i, const int2* p
     return r;  // visibility: the caller's __syncthreads (fft_load_tables) follows
 }
 
-// ---- asynchronous staging of the next item's inputs -------------------------------------------
-// Every thread copies exactly the elements it will itself consume into thread-private shared-memory
-// slots, so a cp.async.wait_group is all the synchronisation the staging needs.
-// A work item of a CTA step, seen from one thread: which plane and which row pair / column.
+// A work item of one warp: which plane and which row pair / column.  Every pass exposes
+//   items(rg)                      number of work items of the launch
+//   item(it, rg)                   decode
+//   prefetch(item, lane, stage)    cp.async the item's inputs into the warp's staging buffer (natural order;
+//                                  lane copies the elements lane + 32 r it will itself consume)
+//   load(item, lane, stage, v, chirp)        staged inputs x chirp -> registers v[0 .. PTS/2)
+//   finish(item, th, v, buf, chirp, rg)      chirp multiply, pass-specific post-processing, store
 struct FftItem {
-    bool live;
     int plane, idx;
+};
+
+template <typename T, int M> struct RowItems {
+    // row pairs of the (possibly pruned) launch
+    __device__ static long long count(const FftShape& s, const FftRanges& rg) {
+        return rg.start ? (long long)rg.total() : (long long)s.batch * s.npair;
+    }
+    __device__ static FftItem decode(long long it, const FftShape& s, const FftRanges& rg) {
+        FftItem r;
+        if (rg.start) {
+            r.plane = rg.plane_of((int)it);
+            r.idx = rg.lo[r.plane] + ((int)it - rg.start[r.plane]);
+        } else {
+            r.plane = (int)(it / s.npair);
+            r.idx = (int)(it % s.npair);
+        }
+        return r;
+    }
 };
 
 // ---- R2C pass 1: pairs of real rows -> the two Hermitian half spectra, rows 2p and 2p+1 of Y [Na][Nh]
 template <typename T, int M> struct RowsR2C {
     using C = cplx_t<T>;
     using K = FftK<T, M>;
-    static constexpr bool POST = true;    // post-processes through the shared buffer
     const T* in;
     C* y;
     FftShape s;
-    __device__ int steps(const FftRanges& rg) const {
-        const long long total = rg.start ? rg.total() : (long long)s.batch * s.npair;
-        return (int)((total + K::G - 1) / K::G);
-    }
-    __device__ FftItem item(int step, int g, const FftRanges& rg) const {
-        const long long it = (long long)step * K::G + g;
-        FftItem r;
-        if (rg.start) {
-            r.live = it < rg.total();
-            r.plane = r.live ? rg.plane_of((int)it) : 0;
-            r.idx = r.live ? rg.lo[r.plane] + ((int)it - rg.start[r.plane]) : 0;
-        } else {
-            r.live = it < (long long)s.batch * s.npair;
-            r.plane = r.live ? (int)(it / s.npair) : 0;
-            r.idx = r.live ? (int)(it % s.npair) : 0;
-        }
-        return r;
-    }
-    // staged: 16 reals per thread = 8 complex-sized slots; slot (m, k) at stage[(2m + k) * NT + tid] in reals
-    __device__ void prefetch(const FftItem& it, int t, C* stage_c, int tid, const FftRanges&) const {
-        if (!it.live) return;
+    __device__ long long items(const FftRanges& rg) const { return RowItems<T, M>::count(s, rg); }
+    __device__ FftItem item(long long it, const FftRanges& rg) const { return RowItems<T, M>::decode(it, s, rg); }
+    // staged as reals: row 2p at stage[n], row 2p+1 at stage[HALF + n]
+    __device__ void prefetch(const FftItem& it, int lane, C* stage_c, const FftRanges&) const {
         T* stage = reinterpret_cast<T*>(stage_c);
         const int r0 = 2 * it.idx;
         const T* ra = in + (size_t)it.plane * s.real_plane + (size_t)r0 * s.nb;
         const bool has_b = r0 + 1 < s.na;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int n = t + K::TT * m;
+        for (int m = 0; m < K::HP; ++m) {
+            const int n = lane + 32 * m;
             if (n < s.nb) {
-                cp_async<sizeof(T)>(stage + (2 * m) * K::NT + tid, ra + n);
-                if (has_b) cp_async<sizeof(T)>(stage + (2 * m + 1) * K::NT + tid, ra + s.nb + n);
+                cp_async<sizeof(T)>(stage + n, ra + n);
+                if (has_b) cp_async<sizeof(T)>(stage + K::HALF + n, ra + s.nb + n);
             }
         }
     }
-    __device__ void load(const FftItem& it, int t, const C* stage_c, int tid, C* v, const C* chirp, const FftRanges&) const {
+    __device__ void load(const FftItem& it, int lane, const C* stage_c, C* v, const C* chirp, const FftRanges&) const {
         const T* stage = reinterpret_cast<const T*>(stage_c);
         const bool has_b = 2 * it.idx + 1 < s.na;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int n = t + K::TT * m;
+        for (int m = 0; m < K::HP; ++m) {
+            const int n = lane + 32 * m;
             C u = make_c<T>(T(0), T(0));
-            if (it.live && n < s.nb) {
-                u.x = stage[(2 * m) * K::NT + tid];
-                u.y = has_b ? stage[(2 * m + 1) * K::NT + tid] : T(0);
+            if (n < s.nb) {
+                u.x = stage[n];
+                u.y = has_b ? stage[K::HALF + n] : T(0);
                 u = cmul(u, chirp[n]);
             }
             v[m] = u;
         }
     }
-    // Z[n] = FFT(row_even + i row_odd)[n] is written to the transform's buffer in natural order (these
-    // are the thread's own final-stage locations), then every thread separates A[j] = (Z[j] + conj
-    // Z[nb-j]) / 2 and B[j] = (Z[j] - conj Z[nb-j]) / 2i for its share of j < nh.
-    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C* buf, const C* chirp, const FftRanges& rg) const {
-        const int t = th.t;
+    // Z[n] = FFT(row_even + i row_odd)[n] is written to the warp's buffer in natural order, then every lane
+    // separates A[j] = (Z[j] + conj Z[nb-j]) / 2 and B[j] = (Z[j] - conj Z[nb-j]) / 2i for its share of j < nh.
+    __device__ void finish(const FftItem& it, const FftLane<T, M>& th, C* v, C* buf, const C* chirp, const FftRanges&) const {
+        const int lane = th.lane;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int n = t + K::TT * m;
+        for (int m = 0; m < K::HP; ++m) {
+            const int n = lane + 32 * m;
             if (n < s.nb) buf[K::slot(n)] = cmul(v[m], chirp[n]);
         }
-        th.sync();
-        if (!it.live) return;
+        __syncwarp();
         const bool has_b = 2 * it.idx + 1 < s.na;
         C* ya = y + (size_t)it.plane * s.z_plane + (size_t)(2 * it.idx) * s.nh;
 #pragma unroll
-        for (int m = 0; m < 5; ++m) {
-            const int j = t + K::TT * m;
+        for (int m = 0; m < K::HP / 2 + 1; ++m) {
+            const int j = lane + 32 * m;
             if (j < s.nh) {
                 const C a = buf[K::slot(j)], b = buf[K::slot(j == 0 ? 0 : s.nb - j)];
                 ya[j] = make_c<T>(T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y));
@@ -623,31 +683,29 @@ template <typename T, int M> struct RowsR2C {
 };
 
 // ---- column transforms of a half-complex plane, forward (R2C pass 2) or inverse (C2R pass 1)
-// INVERSE = false:  Y [Na][Nh] -> spec [Na][Nh]
-// INVERSE = true:   spec [Na][Nh] -> Z [npair][Nb], Z[p][j] = W[2p][j] + i W[2p+1][j] and its Hermitian
+// INVERSE = false:  Y [Na][Nh] -> spectrum
+// INVERSE = true:   spectrum -> Z [npair][Nb], Z[p][j] = W[2p][j] + i W[2p+1][j] and its Hermitian
 //                   extension Z[p][nb-j] = conj(W[2p][j]) + i conj(W[2p+1][j]), W = inverse column
 //                   transform (conj in, conj out around the forward chirp-z)
-template <typename T, int M, bool INVERSE> struct ColsPass {
+// SPEC_T: the spectrum is stored transposed, [Nh][Na] (the operator's layout: column j is contiguous);
+//         otherwise numpy's [Na][Nh].
+template <typename T, int M, bool INVERSE, bool SPEC_T> struct ColsPass {
     using C = cplx_t<T>;
     using K = FftK<T, M>;
-    // The C2R pairing is a lane-pair shuffle when the transform's adjacent threads are adjacent lanes
-    // (R3 >= 2), else a round trip through the shared buffer (which then needs the PRE_SYNC of fft_fwd).
-    static constexpr bool PAIR_BY_SHUFFLE = INVERSE && K::R3 >= 2;
-    static constexpr bool POST = INVERSE && !PAIR_BY_SHUFFLE;
     const C* src;
     C* dst;
     FftShape s;
-    __device__ int tiles() const { return (s.nh + K::G - 1) / K::G; }
-    __device__ int steps(const FftRanges&) const { return s.batch * tiles(); }
-    __device__ FftItem item(int step, int g, const FftRanges&) const {
-        const int tl = tiles();
+    __device__ long long items(const FftRanges&) const { return (long long)s.batch * s.nh; }
+    __device__ FftItem item(long long it, const FftRanges&) const {
         FftItem r;
-        r.plane = step / tl;
-        r.idx = (step % tl) * K::G + g;
-        r.live = r.idx < s.nh;
+        r.plane = (int)(it / s.nh);
+        r.idx = (int)(it % s.nh);
         return r;
     }
-    __device__ size_t src_plane() const { return INVERSE ? s.spec_plane : s.z_plane; }
+    // spectrum element (row i, column j) of a plane
+    __device__ __forceinline__ size_t spec_at(int i, int j) const {
+        return SPEC_T ? (size_t)j * s.na + i : (size_t)i * s.nh + j;
+    }
     // forward direction of a pruned launch: rows outside the plane's range are zero and are not read
     __device__ void row_window(const FftItem& it, const FftRanges& rg, int& r0, int& r1) const {
         r0 = 0;
@@ -657,41 +715,40 @@ template <typename T, int M, bool INVERSE> struct ColsPass {
             r1 = min(s.na, r0 + 2 * rg.cnt(it.plane));
         }
     }
-    __device__ void prefetch(const FftItem& it, int t, C* stage, int tid, const FftRanges& rg) const {
-        if (!it.live) return;
+    __device__ void prefetch(const FftItem& it, int lane, C* stage, const FftRanges& rg) const {
         int r0, r1;
         row_window(it, rg, r0, r1);
-        const C* col = src + (size_t)it.plane * src_plane() + it.idx;
+        const C* base = src + (size_t)it.plane * (INVERSE ? s.spec_plane : s.z_plane);
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int i = t + K::TT * m;
-            if (i >= r0 && i < r1) cp_async<sizeof(C)>(stage + m * K::NT + tid, col + (size_t)i * s.nh);
+        for (int m = 0; m < K::HP; ++m) {
+            const int i = lane + 32 * m;
+            if (i >= r0 && i < r1)
+                cp_async<sizeof(C)>(stage + i, base + (INVERSE ? spec_at(i, it.idx) : (size_t)i * s.nh + it.idx));
         }
     }
-    __device__ void load(const FftItem& it, int t, const C* stage, int tid, C* v, const C* chirp, const FftRanges& rg) const {
+    __device__ void load(const FftItem& it, int lane, const C* stage, C* v, const C* chirp, const FftRanges& rg) const {
         int r0, r1;
         row_window(it, rg, r0, r1);
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int i = t + K::TT * m;
+        for (int m = 0; m < K::HP; ++m) {
+            const int i = lane + 32 * m;
             C u = make_c<T>(T(0), T(0));
-            if (it.live && i >= r0 && i < r1) {
-                u = stage[m * K::NT + tid];
+            if (i >= r0 && i < r1) {
+                u = stage[i];
                 if (INVERSE) u.y = -u.y;
                 u = cmul(u, chirp[i]);
             }
             v[m] = u;
         }
     }
-    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C* buf, const C* chirp, const FftRanges& rg) const {
-        const int t = th.t;
+    __device__ void finish(const FftItem& it, const FftLane<T, M>& th, C* v, C*, const C* chirp, const FftRanges& rg) const {
+        const int lane = th.lane;
         if (!INVERSE) {
-            if (!it.live) return;
-            C* col = dst + (size_t)it.plane * s.spec_plane + it.idx;
+            C* plane = dst + (size_t)it.plane * s.spec_plane;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int i = t + K::TT * m;
-                if (i < s.na) col[(size_t)i * s.nh] = cmul(v[m], chirp[i]);
+            for (int m = 0; m < K::HP; ++m) {
+                const int i = lane + 32 * m;
+                if (i < s.na) plane[spec_at(i, it.idx)] = cmul(v[m], chirp[i]);
             }
             return;
         }
@@ -701,49 +758,24 @@ template <typename T, int M, bool INVERSE> struct ColsPass {
         const int p0 = rg.start ? rg.lo[it.plane] : 0;
         const int p1 = rg.start ? p0 + rg.cnt(it.plane) : s.npair;
         C* zp = dst + (size_t)it.plane * s.z_plane;
-        if (PAIR_BY_SHUFFLE) {
-            // rows 2p and 2p+1 sit in the adjacent lanes t and t^1 (t = ... + n2, n2 the fastest lane index):
-            // the even lane assembles Z[p][j], the odd lane its Hermitian mirror Z[p][nb-j]
-            const bool odd = (t & 1) != 0;
+        // rows 2p and 2p+1 sit in the adjacent lanes (lane even / odd, same register): the even lane assembles
+        // Z[p][j], the odd lane its Hermitian mirror Z[p][nb-j]
+        const bool odd = (lane & 1) != 0;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int i = t + K::TT * m;
-                C mine = make_c<T>(T(0), T(0));
-                if (i < s.na) {
-                    mine = cmul(v[m], chirp[i]);
-                    mine.y = self_mirror ? T(0) : -mine.y;
-                }
-                const C other = shfl_xor_c(mine, 1);
-                const C a = odd ? other : mine, b = odd ? mine : other;
-                const int p = i >> 1;
-                if (it.live && p >= p0 && p < p1) {
-                    C* row = zp + (size_t)p * s.nb;
-                    if (!odd) row[j] = make_c<T>(a.x - b.y, a.y + b.x);
-                    else if (!self_mirror) row[s.nb - j] = make_c<T>(a.x + b.y, b.x - a.y);
-                }
-            }
-            return;
-        }
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int i = t + K::TT * m;
+        for (int m = 0; m < K::HP; ++m) {
+            const int i = lane + 32 * m;
+            C mine = make_c<T>(T(0), T(0));
             if (i < s.na) {
-                C r = cmul(v[m], chirp[i]);
-                r.y = self_mirror ? T(0) : -r.y;
-                buf[K::slot(i)] = r;
+                mine = cmul(v[m], chirp[i]);
+                mine.y = self_mirror ? T(0) : -mine.y;
             }
-        }
-        th.sync();
-        if (!it.live) return;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int p = t + K::TT * m;
-            if (p >= p0 && p < p1) {
-                const C a = buf[K::slot(2 * p)];
-                const C b = 2 * p + 1 < s.na ? buf[K::slot(2 * p + 1)] : make_c<T>(T(0), T(0));
+            const C other = shfl_xor_c(mine, 1);
+            const C a = odd ? other : mine, b = odd ? mine : other;
+            const int p = i >> 1;
+            if (p >= p0 && p < p1 && p < s.npair) {
                 C* row = zp + (size_t)p * s.nb;
-                row[j] = make_c<T>(a.x - b.y, a.y + b.x);
-                if (!self_mirror) row[s.nb - j] = make_c<T>(a.x + b.y, b.x - a.y);
+                if (!odd) row[j] = make_c<T>(a.x - b.y, a.y + b.x);
+                else if (!self_mirror) row[s.nb - j] = make_c<T>(a.x + b.y, b.x - a.y);
             }
         }
     }
@@ -753,60 +785,41 @@ template <typename T, int M, bool INVERSE> struct ColsPass {
 template <typename T, int M> struct RowsC2R {
     using C = cplx_t<T>;
     using K = FftK<T, M>;
-    static constexpr bool POST = false;
     const C* z;
     T* out;
     FftShape s;
-    __device__ int steps(const FftRanges& rg) const {
-        const long long total = rg.start ? rg.total() : (long long)s.batch * s.npair;
-        return (int)((total + K::G - 1) / K::G);
-    }
-    __device__ FftItem item(int step, int g, const FftRanges& rg) const {
-        const long long it = (long long)step * K::G + g;
-        FftItem r;
-        if (rg.start) {
-            r.live = it < rg.total();
-            r.plane = r.live ? rg.plane_of((int)it) : 0;
-            r.idx = r.live ? rg.lo[r.plane] + ((int)it - rg.start[r.plane]) : 0;
-        } else {
-            r.live = it < (long long)s.batch * s.npair;
-            r.plane = r.live ? (int)(it / s.npair) : 0;
-            r.idx = r.live ? (int)(it % s.npair) : 0;
-        }
-        return r;
-    }
-    __device__ void prefetch(const FftItem& it, int t, C* stage, int tid, const FftRanges&) const {
-        if (!it.live) return;
+    __device__ long long items(const FftRanges& rg) const { return RowItems<T, M>::count(s, rg); }
+    __device__ FftItem item(long long it, const FftRanges& rg) const { return RowItems<T, M>::decode(it, s, rg); }
+    __device__ void prefetch(const FftItem& it, int lane, C* stage, const FftRanges&) const {
         const C* row = z + (size_t)it.plane * s.z_plane + (size_t)it.idx * s.nb;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int n = t + K::TT * m;
-            if (n < s.nb) cp_async<sizeof(C)>(stage + m * K::NT + tid, row + n);
+        for (int m = 0; m < K::HP; ++m) {
+            const int n = lane + 32 * m;
+            if (n < s.nb) cp_async<sizeof(C)>(stage + n, row + n);
         }
     }
     // IFFT(z) = conj(FFT(conj z)) = row_even + i row_odd
-    __device__ void load(const FftItem& it, int t, const C* stage, int tid, C* v, const C* chirp, const FftRanges&) const {
+    __device__ void load(const FftItem&, int lane, const C* stage, C* v, const C* chirp, const FftRanges&) const {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int n = t + K::TT * m;
+        for (int m = 0; m < K::HP; ++m) {
+            const int n = lane + 32 * m;
             C u = make_c<T>(T(0), T(0));
-            if (it.live && n < s.nb) {
-                u = stage[m * K::NT + tid];
+            if (n < s.nb) {
+                u = stage[n];
                 u.y = -u.y;
                 u = cmul(u, chirp[n]);
             }
             v[m] = u;
         }
     }
-    __device__ void finish(const FftItem& it, const FftThread<T, M>& th, C* v, C*, const C* chirp, const FftRanges&) const {
-        if (!it.live) return;
-        const int t = th.t, r0 = 2 * it.idx;
+    __device__ void finish(const FftItem& it, const FftLane<T, M>& th, C* v, C*, const C* chirp, const FftRanges&) const {
+        const int lane = th.lane, r0 = 2 * it.idx;
         const bool has_b = r0 + 1 < s.na;
         T* oa = out + (size_t)it.plane * s.real_plane + (size_t)r0 * s.nb;
         T* ob = oa + s.nb;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int n = t + K::TT * m;
+        for (int m = 0; m < K::HP; ++m) {
+            const int n = lane + 32 * m;
             if (n < s.nb) {
                 const C r = cmul(v[m], chirp[n]);
                 oa[n] = r.x;
@@ -816,34 +829,38 @@ template <typename T, int M> struct RowsC2R {
     }
 };
 
-// Persistent kernel shared by the four passes.
+// Persistent kernel shared by the four passes: every warp walks its own items.
 template <typename T, int M, typename Pass>
 __global__ void __launch_bounds__(FftK<T, M>::NT, 1) fft_pass_kernel(Pass pass, FftPlan1d<T> p) {
     using C = cplx_t<T>;
     using K = FftK<T, M>;
     extern __shared__ __align__(16) unsigned char fft_smem[];
     C* smem = reinterpret_cast<C*>(fft_smem);
-    const int tid = threadIdx.x;
-    const FftThread<T, M> th(tid);
-    C* buf = smem + K::OFF_BUF + th.g * K::BUF;
-    C* stage = smem + K::OFF_STAGE;
+    const int warp = threadIdx.x >> 5;
+    const FftLane<T, M> th(threadIdx.x & 31, p.tw);
+    C* buf = smem + K::OFF_BUF + warp * K::BUF;
+    C* stage = smem + K::OFF_STAGE + warp * K::HALF;
     const C* chirp = smem + K::OFF_CHIRP;
     const FftRanges rg = fft_build_ranges<K::MAX_PLANES>(reinterpret_cast<int*>(fft_smem + K::OFF_RANGES_BYTES),
                                                           pass.s.pair_range, pass.s.batch);
     fft_load_tables<T, M>(smem, p, true);
-    const int n_steps = pass.steps(rg);
-    int step = blockIdx.x;
-    if (step < n_steps) pass.prefetch(pass.item(step, th.g, rg), th.t, stage, tid, rg);
+    const long long n_items = pass.items(rg);
+    const long long stride = (long long)gridDim.x * K::G;
+    long long it = (long long)blockIdx.x * K::G + warp;
+    if (it < n_items) pass.prefetch(pass.item(it, rg), th.lane, stage, rg);
     cp_async_commit();
-    for (; step < n_steps; step += gridDim.x) {
-        C v[16];
-        const FftItem cur = pass.item(step, th.g, rg);
-        cp_async_wait_all();
-        pass.load(cur, th.t, stage, tid, v, chirp, rg);
-        if (step + (int)gridDim.x < n_steps)
-            pass.prefetch(pass.item(step + (int)gridDim.x, th.g, rg), th.t, stage, tid, rg);
+    for (; it < n_items; it += stride) {
+        C v[K::PTS];
+        const FftItem cur = pass.item(it, rg);
+        cp_async_wait_all();  // every lane consumes only what it copied itself
+        pass.load(cur, th.lane, stage, v, chirp, rg);
+        if (K::PTS == 8) {
+#pragma unroll
+            for (int m = K::HP; m < K::PTS; ++m) v[m] = make_c<T>(T(0), T(0));
+        }
+        if (it + stride < n_items) pass.prefetch(pass.item(it + stride, rg), th.lane, stage, rg);
         cp_async_commit();
-        chirp_convolve<T, M, Pass::POST>(v, smem, buf, th);
+        chirp_convolve<T, M>(v, smem, buf, th);
         pass.finish(cur, th, v, buf, chirp, rg);
     }
 }

@@ -125,13 +125,20 @@ otf_mul_kernel(cplx_t<T>* __restrict__ spec, const cplx_t<T>* __restrict__ otf, 
 // complex128 -> handle dtype with plane padding (used by surfh_set_otf)
 template <typename T>
 __global__ void otf_convert_kernel(const double2* __restrict__ src, cplx_t<T>* __restrict__ dst, size_t nf,
-                                   size_t nfp, int n_planes) {
+                                   size_t nfp, int n_planes, int na, int nh, int transposed) {
+    // dst element i of a plane: natural [na][nh] order, or -- the layout of the hand-written FFT's spectra --
+    // transposed [nh][na]
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int l = blockIdx.y;
     if (i >= nfp || l >= n_planes) return;
     cplx_t<T> v = make_c<T>(T(0), T(0));
     if (i < nf) {
-        const double2 s = src[(size_t)l * nf + i];
+        size_t from = i;
+        if (transposed) {
+            const size_t col = i / (size_t)na, row = i - col * (size_t)na;
+            from = row * (size_t)nh + col;
+        }
+        const double2 s = src[(size_t)l * nf + from];
         v = make_c<T>((T)s.x, (T)s.y);
     }
     dst[(size_t)l * nfp + i] = v;

@@ -69,6 +69,51 @@ def _torch():
     return torch
 
 
+def estimate_lambda_weights(model) -> np.ndarray:
+    """Mean gain w_l of the detector sampling A^T A (A = Sig R . L . Sum . S, summed over bands and dithers) on
+    smooth images at every cube wavelength, from the host tables alone.  For a locally constant plane the
+    box-sum over srf rows gives srf per kept row, the spectral response spreads it with the LSF, and A^T brings
+    srf * sum_l' W[l', l, b]^2 back onto each covered pixel and dither:
+        w_l = sum_bands  P * srf * mean_b sum_l' W_band[l', l, b]^2        (0 where no band observes).
+    Only the quality of the preconditioner depends on it, never the solution."""
+    w = np.zeros(len(model.wavelength_axis))
+    for it in model.local_bands:
+        t = model.band_tables[it]
+        if t.lsf is None:
+            raise ValueError("the Fourier-domain preconditioner is defined for bands with a spectral response")
+        gain = np.einsum("mlb,mlb->l", t.lsf, t.lsf) / t.nb
+        w[t.wave_local] += t.n_pointing * t.srf * gain
+    return w
+
+
+class FourierPreconditioner:
+    """P ~ (mu_s H^T H + mu_r R)^-1 with H^T H replaced by its shift-invariant part  T^T C^T (w_l) C T:
+    per spatial frequency a K x K block  mu_s sum_l w_l |OTF_l|^2 T_l T_l^T + mu_r d(f)^p I, inverted once on
+    the device; applying it costs two K-map FFTs and one pointwise K x K product (SURVEY section 8f-3;
+    reference: surfh/Models/mixing.py:131-207, surfh/ToolsDir/fusion_mixing.py:401-438)."""
+
+    def __init__(self, model, mu_spectro: float, mu_reg: float, gradient: str = "separated", weights=None,
+                 scale: float = 1.0):
+        if getattr(model, "partial", False):
+            raise ValueError("the Fourier-domain preconditioner needs the unsharded operator on this GPU")
+        if not model.lmm:
+            raise ValueError("the Fourier-domain preconditioner needs templates (LMM model)")
+        self.model = model
+        w = estimate_lambda_weights(model) if weights is None else np.asarray(weights, dtype=np.float64)
+        if w.shape != (len(model.wavelength_axis),):
+            raise ValueError("weights must have one entry per cube wavelength")
+        self.weights = np.ascontiguousarray(w * float(scale))
+        _capi.check(model.handle, model._lib.surfh_precond_build(model.handle, _capi.ptr(self.weights), float(mu_spectro),
+                                                                 float(mu_reg), 1 if gradient == "joint" else 0))
+
+    def apply(self, r, z):
+        """z = P r on flat device tensors of the model's input size."""
+        torch = _torch()
+        _capi.check(self.model.handle, self.model._lib.surfh_precond_apply(
+            self.model.handle, r.data_ptr(), z.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return z
+
+
 class DeviceCG:
     """Device-resident state of one lcg solve on a `spectroSigRLSCT` model."""
 
@@ -98,6 +143,13 @@ class DeviceCG:
         self.x = self.b = self.r = None
         self._y_sq = None       # |y|^2, for the criterion from the CG state
         self._state_evals = 0   # criterion evaluations served from the CG state (no forward pass)
+        # track_hx: keep H x_k next to the iterate by linearity (H x_{k+1} = H x_k + alpha H d, H d being the
+        # detector vector the fused H^T H call leaves behind) so that J(x_k) needs no forward pass whatever the
+        # adjoint flavour.  One extra axpy over the detector vector per iteration; unsharded models only.
+        self.track_hx = False
+        self.hx = self.hd = None
+        self.precond = None     # FourierPreconditioner: preconditioned CG (qmm.lcg's precond= argument)
+        self.z = None
 
     def _to_dev(self, a):
         torch = _torch()
@@ -120,7 +172,7 @@ class DeviceCG:
     def hessp(self, v, out):
         """out = mu_s H^T H v + mu_r R v ; s[1] = <v, out>, with R = L ('separated': D_r^T D_r + D_c^T D_c)
         or R = L L ('joint')."""
-        self.model.fwadj_into(v, out)
+        self.model.fwadj_into(v, out, y_scratch=self.hd)
         if self.gradient == "separated":
             self._check(self.lib.surfh_cg_regularise_dot(self.h, v.data_ptr(), out.data_ptr(), self.mu_s, self.mu_r,
                                                          self.s.data_ptr(), self._stream()))
@@ -142,23 +194,64 @@ class DeviceCG:
         self.q = torch.empty_like(self.b)
         self.r = torch.empty_like(self.b)
         self.d = torch.empty_like(self.b)
+        self.hx = self.hd = None
+        if self.track_hx and not getattr(self.model, "partial", False):
+            self.hd = torch.empty(self.model.osize, dtype=self.tdtype, device=self.dev)
         self.hessp(self.x, self.q)
+        if self.hd is not None:
+            self.hx = self.hd.clone()                     # H x_0
         self._check(self.lib.surfh_cg_start(self.h, self.b.data_ptr(), self.q.data_ptr(), self.r.data_ptr(),
                                             self.d.data_ptr(), self.s.data_ptr(), self._stream()))
+        if self.precond is not None:                      # d = z = P r ; rho_z = <r, z>
+            self.z = torch.empty_like(self.b)
+            self.precond.apply(self.r, self.z)
+            self._check(self.lib.surfh_pcg_direction(self.h, self.r.data_ptr(), self.z.data_ptr(), self.d.data_ptr(),
+                                                     self.s.data_ptr(), 1, self._stream()))
         self.iteration = 0
 
+    def _pcg_step(self, refresh: bool):
+        """One preconditioned iteration: alpha = <r,z>/<d,Qd>; x, r updates; z = P r; beta = <r,z>'/<r,z>;
+        d = z + beta d.  <r,r> still feeds the gradient-norm history and the stopping rule."""
+        lib, st = self.lib, self._stream()
+        self.hessp(self.d, self.q)
+        if refresh:
+            self._check(lib.surfh_cg_refresh(self.h, 0, self.x.data_ptr(), None, self.d.data_ptr(), None, None,
+                                             self.s.data_ptr(), st))           # x += alpha d
+            self.hessp(self.x, self.q)
+            if self.hx is not None:
+                self.hx.copy_(self.hd)
+            self._check(lib.surfh_pcg_update(self.h, 1, None, self.r.data_ptr(), None, self.q.data_ptr(),
+                                             self.b.data_ptr(), self.s.data_ptr(), st))   # r = b - Q x
+        else:
+            self._check(lib.surfh_pcg_update(self.h, 0, self.x.data_ptr(), self.r.data_ptr(), self.d.data_ptr(),
+                                             self.q.data_ptr(), None, self.s.data_ptr(), st))
+            if self.hx is not None:
+                self._check(lib.surfh_axpy_device_scalar(self.h, self.hx.data_ptr(), self.hd.data_ptr(),
+                                                         self.hx.numel(), self.s.data_ptr(), 2, st))
+        self.precond.apply(self.r, self.z)
+        self._check(lib.surfh_pcg_direction(self.h, self.r.data_ptr(), self.z.data_ptr(), self.d.data_ptr(),
+                                            self.s.data_ptr(), 0, st))
+        self.iteration += 1
+
     def step(self, refresh: bool):
+        if self.precond is not None:
+            return self._pcg_step(refresh)
         self.hessp(self.d, self.q)
         if refresh:
             self._check(self.lib.surfh_cg_refresh(self.h, 0, self.x.data_ptr(), None, self.d.data_ptr(), None, None,
                                                   self.s.data_ptr(), self._stream()))
             self.hessp(self.x, self.q)
+            if self.hx is not None:
+                self.hx.copy_(self.hd)                    # exact H x_{k+1}, like the residual
             self._check(self.lib.surfh_cg_refresh(self.h, 1, None, self.r.data_ptr(), self.d.data_ptr(),
                                                   self.b.data_ptr(), self.q.data_ptr(), self.s.data_ptr(),
                                                   self._stream()))
         else:
             self._check(self.lib.surfh_cg_update(self.h, self.x.data_ptr(), self.r.data_ptr(), self.d.data_ptr(),
                                                  self.q.data_ptr(), self.s.data_ptr(), self._stream()))
+            if self.hx is not None:                       # H x_{k+1} = H x_k + alpha H d   (s[2] = alpha)
+                self._check(self.lib.surfh_axpy_device_scalar(self.h, self.hx.data_ptr(), self.hd.data_ptr(),
+                                                              self.hx.numel(), self.s.data_ptr(), 2, self._stream()))
         self.iteration += 1
 
     def grad_norm_history(self):
@@ -171,20 +264,42 @@ class DeviceCG:
             return False
         return x.data_ptr() == self.x.data_ptr() and x.numel() == self.x.numel()
 
+    def state_criterion_available(self) -> bool:
+        """The criterion of the current iterate can be formed without applying H when H x_k is tracked
+        (`track_hx`), or -- exact adjoint only, where Q is symmetric and b = H^T y -- from the residual."""
+        return self.hx is not None or (self.r is not None and self.model.adjoint_mode == "exact")
+
     def criterion_from_state(self) -> float:
-        """J(x_k) of the current iterate from the CG recurrences, without applying H:
-            J(x) = 1/2 x^T Q x - b^T x + mu_s |y|^2 / 2  and  Q x = b - r   =>   J = mu_s |y|^2 / 2 - <x, b + r> / 2.
-        One fused dot-product kernel; one double crosses PCIe.  r is the recurrence residual (refreshed
-        exactly every REFRESH_PERIOD iterations, like qmm.lcg), so the value agrees with the explicit
-        evaluation to the drift of that recurrence (measured <= 1e-12 relative on C2 / C4)."""
+        """J(x_k) of the current iterate without applying H.
+          * H x_k tracked: J = (mu_s |y - H x_k|^2 + mu_r prior(x_k)) / 2, one fused reduction kernel -- valid
+            for both adjoint flavours (H x_k is refreshed exactly with the residual, every REFRESH_PERIOD);
+          * otherwise, exact adjoint: J(x) = 1/2 x^T Q x - b^T x + mu_s |y|^2 / 2 and Q x = b - r give
+            J = mu_s |y|^2 / 2 - <x, b + r> / 2 (one dot-product kernel).  Not valid with the reference's
+            `gridding_t` "adjoint", whose Q is not H^T H.
+        Two doubles cross PCIe."""
         torch = _torch()
+        if not self.state_criterion_available():
+            raise ValueError("criterion_from_state needs track_hx or an exact-adjoint model")
+        self._state_evals += 1
+        if self.hx is not None:
+            return self._criterion_given_hx(self.x, self.hx)
         if self._y_sq is None:
             self._y_sq = float(torch.dot(self.y.double(), self.y.double()))
         out = torch.empty(1, dtype=torch.float64, device=self.dev)
         self._check(self.lib.surfh_cg_dot_x_b_plus_r(self.h, self.x.data_ptr(), self.b.data_ptr(), self.r.data_ptr(),
                                                      out.data_ptr(), self._stream()))
-        self._state_evals += 1
         return 0.5 * self.mu_s * self._y_sq - 0.5 * float(out.item())
+
+    def _criterion_given_hx(self, x, hx) -> float:
+        torch = _torch()
+        out = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        self._check(self.lib.surfh_criterion_terms(self.h, self.y.data_ptr(), hx.data_ptr(), int(hx.numel()),
+                                                   x.data_ptr(), out.data_ptr(), self._stream()))
+        if self.gradient == "joint":  # ||L x||^2 instead of ||D_r x||^2 + ||D_c x||^2
+            lx = self.laplacian(x, torch.empty_like(x))
+            out[1] = torch.dot(lx.double(), lx.double())
+        t = out.cpu().numpy()
+        return float((self.mu_s * t[0] + self.mu_r * t[1]) / 2)
 
     def criterion(self, x) -> float:
         """J(x), everything reduced on the device; the only host traffic is two doubles.  Applies H once
@@ -193,35 +308,31 @@ class DeviceCG:
         torch = _torch()
         x = self._to_dev(x).reshape(-1)
         hx = self.model.forward(x.reshape(self.model.ishape))
-        out = torch.zeros(2, dtype=torch.float64, device=self.dev)
-        total = torch.zeros(2, dtype=torch.float64, device=self.dev)
-        idx = self.model._idx
         # forward() returns the complete detector vector on every rank (all-reduced when sharded),
         # so the criterion is evaluated redundantly and needs no scalar collective
         if self.comm is None and getattr(self.model, "partial", False):
             raise ValueError("a sharded model needs a comm to evaluate the criterion")
-        n = int(idx[-1])
-        self._check(self.lib.surfh_criterion_terms(self.h, self.y.data_ptr(), hx.data_ptr(), n, x.data_ptr(),
-                                                   out.data_ptr(), self._stream()))
-        total += out
-        if self.gradient == "joint":  # ||L x||^2 instead of ||D_r x||^2 + ||D_c x||^2
-            lx = self.laplacian(x, torch.empty_like(x))
-            total[1] = torch.dot(lx.double(), lx.double())
-        t = total.cpu().numpy()
-        return float((self.mu_s * t[0] + self.mu_r * t[1]) / 2)
+        return self._criterion_given_hx(x, hx.reshape(-1))
 
 
 def lcg(model, y, mu_spectro=1.0, mu_reg=1.0, x0=None, tol=1e-4, max_iter=500, min_iter=0,
         callback: Optional[Callable] = None, refresh: int = REFRESH_PERIOD, check_every: int = 1, comm=None,
-        numpy_result: bool = True, gradient: str = "separated", solver: Optional[DeviceCG] = None) -> OptimizeResult:
+        numpy_result: bool = True, gradient: str = "separated", solver: Optional[DeviceCG] = None,
+        precond=None) -> OptimizeResult:
     """Linear CG on the device.  `res.x` is a flat device tensor while iterating (callbacks may
     `.reshape` it) and, at return, a numpy array of the model's input shape (`numpy_result`).
 
     The stopping rule is qmm.lcg's, tested after every iteration (`check_every=1`: one double read back
     per iteration).  `check_every=n` tests it every n-th iteration only -- the loop then runs up to n-1
-    iterations past the tolerance but the host never waits on the device in between (opt-in)."""
+    iterations past the tolerance but the host never waits on the device in between (opt-in).
+
+    `precond`: None (qmm.lcg's default), a `FourierPreconditioner`, or True to build one for these
+    hyper-parameters -- preconditioned CG; the iterates then differ from plain CG's (same minimiser)."""
     torch = _torch()
     cg = solver if solver is not None else DeviceCG(model, y, mu_spectro, mu_reg, comm=comm, gradient=gradient)
+    if precond is True:
+        precond = FourierPreconditioner(model, mu_spectro, mu_reg, gradient)
+    cg.precond = precond
     if x0 is None:
         x0 = np.zeros(model.ishape)
     cg.start(x0, max_iter)
@@ -390,6 +501,7 @@ class QuadCriterion_MRS:
         if method == "lcg":
             # the solver is shared with get_crit_val: the criterion of the current iterate then comes from
             # the CG state (no extra forward pass per evaluation)
+            self._solver().track_hx = bool(calc_crit) and self.criterion_from_state
             res = lcg(self.model_spectro, self.y_spectro, self.mu_spectro, self.mu_reg, init, tol=tolerance,
                       max_iter=maximum_iterations, callback=callback, comm=self.comm, gradient=self.gradient,
                       solver=self._solver())
@@ -404,6 +516,6 @@ class QuadCriterion_MRS:
         """J(x_hat) (fusion_CT.py:242-265).  When x_hat is the running lcg iterate (what the callbacks of
         `run_method` pass) the value comes from the CG state; any other argument applies H once."""
         cg = self._solver()
-        if self.criterion_from_state and cg.is_current_iterate(x_hat):
+        if self.criterion_from_state and cg.is_current_iterate(x_hat) and cg.state_criterion_available():
             return cg.criterion_from_state()
         return cg.criterion(x_hat)

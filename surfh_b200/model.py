@@ -344,16 +344,20 @@ class spectroSigRLSCT(LinOp):
         res.copy_(q)  # device -> host (converts fp32 results), synchronises
         return out if out is not None else res.numpy()
 
-    def fwadj_into(self, x, out):
+    def fwadj_into(self, x, out, y_scratch=None):
         """out = H^T H x on device tensors.  Sharded (partial) models exchange the detector vector
         (all-reduce of the partial sums over wavelength shards) between the two halves and the
-        [K, N, N] result at the end; unsharded models run the fused library call."""
+        [K, N, N] result at the end; unsharded models run the fused library call.  `y_scratch`: optional
+        device tensor of `osize` elements that receives H x (unsharded models only)."""
         if not self.partial:
             # every rank holds the whole operator: nothing to sum (a comm on an unsharded model is ignored --
             # summing W identical copies would scale H^T H by W)
-            _capi.check(self._h, self._lib.surfh_fwadj(self._h, x.data_ptr(), out.data_ptr(), self.mode_code, None,
+            _capi.check(self._h, self._lib.surfh_fwadj(self._h, x.data_ptr(), out.data_ptr(), self.mode_code,
+                                                       None if y_scratch is None else y_scratch.data_ptr(),
                                                        self._stream()))
             return out
+        if y_scratch is not None:
+            raise ValueError("y_scratch is only available on an unsharded model")
         if self.comm is None:
             raise ValueError("a sharded model (lambda_range / local_bands) needs comm= to apply H^T H: "
                              "the detector vector has to be summed over the shards between H and H^T")

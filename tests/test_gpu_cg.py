@@ -171,3 +171,56 @@ def test_run_method_variants_match_oracle(torch_cuda, method, gradient):
     assert np.allclose(res.grad_norm[: len(ref.grad_norm)], ref.grad_norm, rtol=1e-7)
     j_cpu = (om.criterion_joint if gradient == "joint" else om.criterion)(oracle, y, ref.x, 1, mu)
     assert abs(quad.get_crit_val(res.x) - j_cpu) <= 1e-10 * abs(j_cpu)
+
+
+def test_fourier_block_preconditioner_matches_oracle_and_is_spd(torch_cuda):
+    """surfh_precond_build / _apply against the numpy restatement of the per-frequency K x K inverse
+    (mixing.py:131-207, fusion_mixing.py:401-438), both prior flavours, both FFT backends' spectrum layouts."""
+    import torch
+    from surfh_b200 import fusion_CT
+    from surfh_b200.model import spectroSigRLSCT
+    from surfh_oracle import precond as op
+    cfg = CASES["mini_2band_4p"]()
+    rng = np.random.default_rng(8)
+    r = rng.standard_normal(cfg.maps.shape)
+    for backend in ("own", "cufft"):
+        gpu = spectroSigRLSCT(**cfg.model_args(), fft_backend=backend)
+        w = fusion_CT.estimate_lambda_weights(gpu)
+        assert w.shape == (len(cfg.wavelength_axis),) and np.all(w >= 0) and np.count_nonzero(w) > 10
+        for gradient in ("separated", "joint"):
+            pre = fusion_CT.FourierPreconditioner(gpu, 1.0, 5.0, gradient)
+            rt = torch.as_tensor(r, device="cuda").reshape(-1)
+            z = pre.apply(rt, torch.empty_like(rt)).cpu().numpy().reshape(cfg.maps.shape)
+            want = op.apply(cfg.sotf(), cfg.templates, w, 1.0, 5.0, r, cfg.imshape, joint=gradient == "joint")
+            assert rel(z, want) <= 1e-11
+            r2 = torch.as_tensor(rng.standard_normal(cfg.maps.shape), device="cuda").reshape(-1)
+            z2 = pre.apply(r2, torch.empty_like(r2))
+            assert float(torch.dot(rt, torch.as_tensor(z, device="cuda").reshape(-1))) > 0
+            a, b = float(torch.dot(r2, torch.as_tensor(z, device="cuda").reshape(-1))), float(torch.dot(z2, rt))
+            assert abs(a - b) <= 1e-11 * abs(a)
+
+
+def test_preconditioned_cg_reaches_the_same_minimiser_faster(torch_cuda):
+    """qmm.lcg(precond=...): same normal equations, so the same solution; the Fourier-block preconditioner
+    must not cost iterations.  Both runs go to a tight tolerance on the mini configuration."""
+    from surfh_b200 import fusion_CT
+    from surfh_b200.model import spectroSigRLSCT
+    from surfh_oracle import model as om
+    cfg = CASES["mini_2band_4p"]()
+    args = cfg.model_args()
+    gpu = spectroSigRLSCT(**args, adjoint_mode="exact")
+    y = noisy_data(om.SpectroLMM(**args, adjoint_mode="exact"), cfg)
+    mu = 5.0
+    plain = fusion_CT.lcg(gpu, y, 1.0, mu, np.zeros(gpu.ishape), tol=1e-12, max_iter=400)
+    pre = fusion_CT.lcg(gpu, y, 1.0, mu, np.zeros(gpu.ishape), tol=1e-12, max_iter=400, precond=True)
+    g0 = plain.grad_norm[0]
+    def its(res, drop):
+        g = np.asarray(res.grad_norm)
+        hit = np.flatnonzero(g <= drop * g0)
+        return int(hit[0]) if len(hit) else len(g)
+    print("iterations to |r|^2 <= 1e-8 |r0|^2: plain", its(plain, 1e-8), "preconditioned", its(pre, 1e-8),
+          "| to 1e-14:", its(plain, 1e-14), its(pre, 1e-14))
+    assert rel(pre.x, plain.x) <= 1e-6
+    crit = fusion_CT.QuadCriterion_MRS(1, y, gpu, mu)
+    assert abs(crit.get_crit_val(pre.x) - crit.get_crit_val(plain.x)) <= 1e-9 * crit.get_crit_val(plain.x)
+    assert its(pre, 1e-8) <= its(plain, 1e-8)

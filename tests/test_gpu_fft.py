@@ -6,8 +6,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(251, 251), (501, 501), (2, 2), (3, 5), (16, 9), (64, 64), (128, 128), (129, 127), (256, 256),
-          (257, 255), (300, 1024), (1024, 513), (5, 600), (512, 512), (40, 1000)]
+SHAPES = [(251, 251), (501, 501), (301, 301), (2, 2), (3, 5), (16, 9), (64, 64), (128, 128), (129, 127), (256, 256),
+          (257, 255), (300, 512), (512, 257), (5, 500), (512, 512), (40, 96), (96, 96)]
 TOL = {"float64": 1e-13, "float32": 2e-6}
 
 
@@ -76,7 +76,7 @@ def test_rejects_cpu_tensors_and_long_axes(fft):
     with pytest.raises(TypeError):
         fft.rfft2(torch.zeros((4, 4), dtype=torch.float64))
     with pytest.raises(_capi.SurfhError):
-        fft.rfft2(torch.zeros((4, 1030), dtype=torch.float64, device="cuda"))
+        fft.rfft2(torch.zeros((4, 513), dtype=torch.float64, device="cuda"))
 
 
 @pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 1e-5)])

@@ -143,7 +143,7 @@ def test_c4_100_iteration_solve(c4):
       * the criterion trace (every 5th iteration) decreases monotonically and comes from the CG state,
         i.e. costs no forward pass; its last value equals the explicit evaluation through H to 1e-10;
       * the exact residual recomputation at iteration 50 (qmm.lcg's refresh) agrees with the recurrence:
-        a run without refresh has the same gradient-norm history to 1e-8 up to and beyond iteration 50;
+        |r|^2 after iteration 50 of a run that skips that refresh differs by <= 1e-8 relative;
       * the solution reproduces the data to the noise level."""
     import torch
     from surfh_b200 import fusion_CT
@@ -164,15 +164,20 @@ def test_c4_100_iteration_solve(c4):
     j_state = quad._solver().criterion_from_state()
     assert abs(j_state - explicit) <= 1e-10 * abs(explicit), (j_state, explicit)
     assert crit[-1] >= explicit * (1 - 1e-9)   # the trace's last entry is from an earlier iterate
-    no_refresh = fusion_CT.lcg(model, y, 1.0, 5e3, np.zeros(model.ishape), tol=1e-12, max_iter=60, refresh=0,
-                               check_every=60)
-    assert np.allclose(no_refresh.grad_norm[:61], res.grad_norm[:61], rtol=1e-8), \
-        np.max(np.abs(np.asarray(no_refresh.grad_norm[:61]) / np.asarray(res.grad_norm[:61]) - 1))
+    # same solve with the exact residual recomputation at iteration 50 switched off (refresh only at iteration 0):
+    # every kernel is deterministic, so the two runs are bit-identical through iteration 49 and differ at
+    # iteration 50 by exactly (recomputed residual) vs (recurrence residual)
+    rec = fusion_CT.lcg(model, y, 1.0, 5e3, np.zeros(model.ishape), tol=1e-12, max_iter=51, refresh=10 ** 6,
+                        check_every=51)
+    assert np.array_equal(rec.grad_norm[:51], res.grad_norm[:51])
+    drift = abs(rec.grad_norm[51] - res.grad_norm[51]) / res.grad_norm[51]
+    assert drift <= 1e-8, drift
     hx = model.forward(torch.as_tensor(res.x, device="cuda")).cpu().numpy()
     misfit = np.sqrt(np.mean((hx - y) ** 2))
     assert 0.5 * sigma < misfit < 1.5 * sigma, (misfit, sigma)
     print(f"C4 100-iteration solve: J {crit[0]:.6e} -> {explicit:.6e}, grad_norm {res.grad_norm[0]:.3e} -> "
           f"{res.grad_norm[-1]:.3e}, misfit/sigma {misfit / sigma:.3f}, "
+          f"refresh-vs-recurrence drift at iteration 50: {drift:.2e}, "
           f"{model.own_launch_count() - launches0} own kernel launches")
 
 
