@@ -141,12 +141,13 @@ template <typename T> struct OwnFft2d {
     }
 
     // complex elements per plane of the intermediate buffer
-    size_t z_plane() const { return std::max((size_t)((na + 1) / 2) * nb, (size_t)na * nh); }
+    int ypitch() const { return (na + 1) / 2 * 2; }
+    size_t z_plane() const { return std::max((size_t)((na + 1) / 2) * nb, (size_t)nh * ypitch()); }
 
     FftShape shape(size_t real_plane, size_t spec_plane, int batch, const int2* pair_range) const {
         FftShape s;
         s.na = na; s.nb = nb; s.nh = nh; s.npair = (na + 1) / 2;
-        s.real_plane = real_plane; s.spec_plane = spec_plane; s.z_plane = z_plane(); s.batch = batch;
+        s.real_plane = real_plane; s.spec_plane = spec_plane; s.z_plane = z_plane(); s.ypitch = ypitch(); s.batch = batch;
         s.pair_range = pair_range;
         if (pair_range && batch > FftK<T, 256>::MAX_PLANES) throw Error(SURFH_EINVAL, "pruned FFT launch: too many planes");
         return s;

@@ -31,8 +31,8 @@
 //     is all the synchronisation the staging needs) while the current item is transformed.
 //
 // 2-D real transforms use the two-for-one trick: a pair of real rows is transformed as one complex row.
-//   R2C:  rows_r2c  real [Na][Nb] -> A/B-separated half spectra Y [Na][Nh]   (separation through the
-//                   warp's own shared buffer)                  ->  cols  (-> spectrum)
+//   R2C:  rows_r2c  real [Na][Nb] -> A/B-separated half spectra Y, stored transposed [Nh][Na] (separation
+//                   through the warp's own shared buffer)      ->  cols  (-> spectrum)
 //   C2R:  cols_c2r  spectrum -> Z [ceil(Na/2)][Nb], Z[p] = W[2p] + i W[2p+1] Hermitian-extended
 //                   (rows 2p, 2p+1 sit in adjacent lanes: pairing by shuffle) ->  rows_c2r (-> real [Na][Nb])
 // Spectrum layout: the operator keeps every half spectrum (OTF, map spectra, the working cube's spectrum)
@@ -50,6 +50,15 @@
 #ifndef SURFH_FFT_WARPS_F64_1024
 #define SURFH_FFT_WARPS_F64_1024 8
 #endif
+#ifndef SURFH_FFT_WARPS_F64_512
+#define SURFH_FFT_WARPS_F64_512 8
+#endif
+#ifndef SURFH_FFT_BULK
+#define SURFH_FFT_BULK 1
+#endif
+#ifndef SURFH_FFT_STAGGER
+#define SURFH_FFT_STAGGER 0      // ns by which the second warp of every scheduler starts late (measured: no effect)
+#endif
 
 namespace surfh {
 
@@ -64,7 +73,7 @@ template <typename T, int M> struct FftK {
     static constexpr int HALF = M / 2;          // the transform length N must be <= HALF
     // warps (= transforms in flight) per CTA: 32 complex doubles per lane need ~250 registers (8 warps fill the
     // register file), 16 need ~200 (10 warps); fp32 halves both
-    static constexpr int G = sizeof(T) == 8 ? (M == 1024 ? SURFH_FFT_WARPS_F64_1024 : 10) : 16;
+    static constexpr int G = sizeof(T) == 8 ? (M == 1024 ? SURFH_FFT_WARPS_F64_1024 : SURFH_FFT_WARPS_F64_512) : 16;
     static constexpr int NT = 32 * G;
     // Exchange buffer of one transform: PTS rows (row k1 = the k1-th output of every lane's first-stage DFT)
     // of 32 elements at pitch TP.  The transposed read of lane (q, n2) walks row q from element n2 in steps of
@@ -81,28 +90,34 @@ template <typename T, int M> struct FftK {
     static constexpr int OFF_FILT = 0;
     static constexpr int OFF_CHIRP = OFF_FILT + M;
     static constexpr int OFF_TW = OFF_CHIRP + HALF;
-    static constexpr int OFF_BUF = OFF_TW + (CHAIN ? 0 : N_TW);
+    static constexpr int N_ROOTS = 32 + R3;     // chains: w1[lane], then w2[n2]
+    static constexpr int OFF_BUF = OFF_TW + (CHAIN ? N_ROOTS : N_TW);
     static constexpr int OFF_STAGE = OFF_BUF + G * BUF;
     static constexpr int N_SMEM = OFF_STAGE + G * HALF;
     // after the complex area: per-plane row-pair ranges of a pruned launch (start[MAX_PLANES+1], lo[MAX_PLANES])
     static constexpr int MAX_PLANES = 512;
     static constexpr size_t OFF_RANGES_BYTES = (size_t)N_SMEM * sizeof(C);
-    static constexpr size_t SMEM_BYTES = OFF_RANGES_BYTES + (2 * MAX_PLANES + 2) * sizeof(int);
+    // then one mbarrier per warp (bulk-copy staging, fp64)
+    static constexpr size_t OFF_MBAR_BYTES = (OFF_RANGES_BYTES + (2 * MAX_PLANES + 2) * sizeof(int) + 7) / 8 * 8;
+    static constexpr size_t SMEM_BYTES = OFF_MBAR_BYTES + G * 8;
+    // A pass whose input of one item is ONE contiguous, 16-byte-aligned run can stage it with a single bulk
+    // asynchronous copy (TMA) per warp instead of PTS/2 cp.async per lane: complex doubles only (16-byte
+    // elements keep every run aligned whatever the odd map size)
+    static constexpr bool BULK_OK = SURFH_FFT_BULK && sizeof(C) == 16;
     static_assert(SMEM_BYTES <= 232448, "shared-memory budget of one CTA (227 KB)");
 };
 
 // Who am I inside the warp: lane = q*R3 + n2.  The R3 lanes that exchange registers in the last radix stage
-// are adjacent; `w1` / `w2` are the lane's twiddle roots (chains), read once per kernel.
+// are adjacent.  The lane's twiddle roots (chains) w1 = exp(-2 pi i lane / M) and w2 = exp(-2 pi i n2 / 32)
+// are re-read from shared memory where a chain starts (32 + R3 table entries) rather than held in registers
+// across the whole transform: the 32-point kernels are register-bound.
 template <typename T, int M> struct FftLane {
     using K = FftK<T, M>;
     int lane, q, n2;
-    cplx_t<T> w1, w2;   // exp(-2 pi i lane / M), exp(-2 pi i n2 / 32)
-    __device__ __forceinline__ FftLane(int lane_, const cplx_t<T>* tw_global) {
+    __device__ __forceinline__ FftLane(int lane_) {
         lane = lane_;
         n2 = lane % K::R3;
         q = lane / K::R3;
-        w1 = tw_global[32 + lane];
-        w2 = tw_global[M + K::R3 + n2];
     }
 };
 
@@ -376,12 +391,13 @@ __device__ __forceinline__ void fft_fwd(cplx_t<T>* v, cplx_t<T>* buf, const FftL
     dft_pts<false, PTS, HALF_IN ? 1 : 0>(v);
     __syncwarp();  // the previous item's post-processing may still be reading this buffer
     if (K::CHAIN) {
-        C pw = th.w1;
+        const C w1 = tw[th.lane];
+        C pw = w1;
         buf[th.lane] = v[0];
 #pragma unroll
         for (int k1 = 1; k1 < PTS; ++k1) {
             buf[k1 * K::TP + th.lane] = cmul(v[k1], pw);
-            if (k1 < PTS - 1) pw = cmul(pw, th.w1);
+            if (k1 < PTS - 1) pw = cmul(pw, w1);
         }
     } else {
 #pragma unroll
@@ -398,11 +414,12 @@ __device__ __forceinline__ void fft_fwd(cplx_t<T>* v, cplx_t<T>* buf, const FftL
     dft_pts<false, PTS, 0>(v);
     if (R3 > 1) {
         if (K::CHAIN) {
-            C pw = th.w2;
+            const C w2 = tw[32 + th.n2];
+            C pw = w2;
 #pragma unroll
             for (int q2 = 1; q2 < PTS; ++q2) {
                 v[q2] = cmul(v[q2], pw);
-                if (q2 < PTS - 1) pw = cmul(pw, th.w2);
+                if (q2 < PTS - 1) pw = cmul(pw, w2);
             }
         } else {
 #pragma unroll
@@ -426,11 +443,12 @@ __device__ __forceinline__ void fft_inv(cplx_t<T>* v, cplx_t<T>* buf, const FftL
         for (int c = 0; c < PTS / R3; ++c) dft_r<true, R3>(v + c * R3);
         group_transpose<R3, PTS>(v, th.n2);
         if (K::CHAIN) {
-            C pw = th.w2;
+            const C w2 = tw[32 + th.n2];
+            C pw = w2;
 #pragma unroll
             for (int q2 = 1; q2 < PTS; ++q2) {
                 v[q2] = cmul_conj(pw, v[q2]);
-                if (q2 < PTS - 1) pw = cmul(pw, th.w2);
+                if (q2 < PTS - 1) pw = cmul(pw, w2);
             }
         } else {
 #pragma unroll
@@ -444,12 +462,13 @@ __device__ __forceinline__ void fft_inv(cplx_t<T>* v, cplx_t<T>* buf, const FftL
     for (int m = 0; m < PTS; ++m) blk[th.n2 + R3 * m] = v[m];
     __syncwarp();
     if (K::CHAIN) {
-        C pw = th.w1;
+        const C w1 = tw[th.lane];
+        C pw = w1;
         v[0] = buf[th.lane];
 #pragma unroll
         for (int k1 = 1; k1 < PTS; ++k1) {
             v[k1] = cmul_conj(pw, buf[k1 * K::TP + th.lane]);
-            if (k1 < PTS - 1) pw = cmul(pw, th.w1);
+            if (k1 < PTS - 1) pw = cmul(pw, w1);
         }
     } else {
 #pragma unroll
@@ -475,8 +494,12 @@ template <typename T> struct FftPlan1d {
 template <typename T, int M>
 __device__ __forceinline__ void fft_load_tables(cplx_t<T>* smem, const FftPlan1d<T>& p, bool with_filter) {
     using K = FftK<T, M>;
-    if (!K::CHAIN)
+    if (K::CHAIN) {  // the chain roots only: tw1[1][lane], lane < 32, then tw2[1][n2], n2 < R3
+        for (int i = threadIdx.x; i < K::N_ROOTS; i += blockDim.x)
+            smem[K::OFF_TW + i] = i < 32 ? p.tw[32 + i] : p.tw[M + K::R3 + (i - 32)];
+    } else {
         for (int i = threadIdx.x; i < K::N_TW; i += blockDim.x) smem[K::OFF_TW + i] = p.tw[i];
+    }
     if (with_filter) {
         for (int i = threadIdx.x; i < M; i += blockDim.x) smem[K::OFF_FILT + i] = p.filt[i];
         for (int i = threadIdx.x; i < p.n; i += blockDim.x) smem[K::OFF_CHIRP + i] = p.chirp[i];
@@ -507,7 +530,7 @@ fft_filter_kernel(const cplx_t<T>* __restrict__ b, FftPlan1d<T> p, cplx_t<T>* __
     extern __shared__ __align__(16) unsigned char fft_smem[];
     C* smem = reinterpret_cast<C*>(fft_smem);
     fft_load_tables<T, M>(smem, p, false);
-    const FftLane<T, M> th(threadIdx.x, p.tw);
+    const FftLane<T, M> th(threadIdx.x);
     C* buf = smem + K::OFF_BUF;
     C v[K::PTS];
 #pragma unroll
@@ -523,6 +546,7 @@ struct FftShape {
     size_t real_plane;       // elements between real planes
     size_t spec_plane;       // complex elements between spectrum planes
     size_t z_plane;          // complex elements between planes of the intermediate buffer
+    int ypitch;              // R2C intermediate Y^T [nh][ypitch]: na rounded up to even (rows 2p, 2p+1 share a sector)
     int batch;
     // Pruned transforms: per plane, only the row pairs [lo, lo + cnt) of the real image matter (C2R: the
     // others are not produced; R2C: the others are known to be zero).  NULL = all rows.  [batch] (lo, cnt)
@@ -606,28 +630,29 @@ template <typename T, int M> struct RowItems {
     __device__ static long long count(const FftShape& s, const FftRanges& rg) {
         return rg.start ? (long long)rg.total() : (long long)s.batch * s.npair;
     }
-    __device__ static FftItem decode(long long it, const FftShape& s, const FftRanges& rg) {
+    __device__ static FftItem decode(int it, const FftShape& s, const FftRanges& rg) {
         FftItem r;
         if (rg.start) {
-            r.plane = rg.plane_of((int)it);
-            r.idx = rg.lo[r.plane] + ((int)it - rg.start[r.plane]);
+            r.plane = rg.plane_of(it);
+            r.idx = rg.lo[r.plane] + (it - rg.start[r.plane]);
         } else {
-            r.plane = (int)(it / s.npair);
-            r.idx = (int)(it % s.npair);
+            r.plane = it / s.npair;
+            r.idx = it - r.plane * s.npair;
         }
         return r;
     }
 };
 
-// ---- R2C pass 1: pairs of real rows -> the two Hermitian half spectra, rows 2p and 2p+1 of Y [Na][Nh]
+// ---- R2C pass 1: pairs of real rows -> the two Hermitian half spectra, rows 2p and 2p+1 of Y (stored as Y^T)
 template <typename T, int M> struct RowsR2C {
     using C = cplx_t<T>;
     using K = FftK<T, M>;
+    static constexpr bool BULK = false;   // real rows of odd length are not 16-byte aligned
     const T* in;
     C* y;
     FftShape s;
     __device__ long long items(const FftRanges& rg) const { return RowItems<T, M>::count(s, rg); }
-    __device__ FftItem item(long long it, const FftRanges& rg) const { return RowItems<T, M>::decode(it, s, rg); }
+    __device__ FftItem item(int it, const FftRanges& rg) const { return RowItems<T, M>::decode(it, s, rg); }
     // staged as reals: row 2p at stage[n], row 2p+1 at stage[HALF + n]
     __device__ void prefetch(const FftItem& it, int lane, C* stage_c, const FftRanges&) const {
         T* stage = reinterpret_cast<T*>(stage_c);
@@ -669,21 +694,24 @@ template <typename T, int M> struct RowsR2C {
         }
         __syncwarp();
         const bool has_b = 2 * it.idx + 1 < s.na;
-        C* ya = y + (size_t)it.plane * s.z_plane + (size_t)(2 * it.idx) * s.nh;
+        // Y is stored TRANSPOSED, [nh][ypitch]: the two half spectra of a row pair land side by side (32 bytes,
+        // one full sector per column j) and the column pass that follows reads whole columns as contiguous runs
+        C* ya = y + (size_t)it.plane * s.z_plane + (size_t)(2 * it.idx);
 #pragma unroll
         for (int m = 0; m < K::HP / 2 + 1; ++m) {
             const int j = lane + 32 * m;
             if (j < s.nh) {
                 const C a = buf[K::slot(j)], b = buf[K::slot(j == 0 ? 0 : s.nb - j)];
-                ya[j] = make_c<T>(T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y));
-                if (has_b) ya[s.nh + j] = make_c<T>(T(0.5) * (a.y + b.y), T(0.5) * (b.x - a.x));
+                C* dst = ya + (size_t)j * s.ypitch;
+                dst[0] = make_c<T>(T(0.5) * (a.x + b.x), T(0.5) * (a.y - b.y));
+                if (has_b) dst[1] = make_c<T>(T(0.5) * (a.y + b.y), T(0.5) * (b.x - a.x));
             }
         }
     }
 };
 
 // ---- column transforms of a half-complex plane, forward (R2C pass 2) or inverse (C2R pass 1)
-// INVERSE = false:  Y [Na][Nh] -> spectrum
+// INVERSE = false:  Y^T [Nh][ypitch] -> spectrum
 // INVERSE = true:   spectrum -> Z [npair][Nb], Z[p][j] = W[2p][j] + i W[2p+1][j] and its Hermitian
 //                   extension Z[p][nb-j] = conj(W[2p][j]) + i conj(W[2p+1][j]), W = inverse column
 //                   transform (conj in, conj out around the forward chirp-z)
@@ -692,14 +720,25 @@ template <typename T, int M> struct RowsR2C {
 template <typename T, int M, bool INVERSE, bool SPEC_T> struct ColsPass {
     using C = cplx_t<T>;
     using K = FftK<T, M>;
+    // forward: Y^T columns are contiguous; inverse: the spectrum's columns are, in the transposed layout
+    static constexpr bool BULK = K::BULK_OK && (!INVERSE || SPEC_T);
     const C* src;
     C* dst;
     FftShape s;
+    // the item's input as one contiguous run: first element index within the column, count, source
+    __device__ const C* bulk_src(const FftItem& it, const FftRanges& rg, int& first, int& count) const {
+        int r0, r1;
+        row_window(it, rg, r0, r1);
+        first = r0;
+        count = r1 - r0;
+        const C* base = src + (size_t)it.plane * (INVERSE ? s.spec_plane : s.z_plane);
+        return base + (INVERSE ? (size_t)it.idx * s.na : (size_t)it.idx * s.ypitch) + r0;
+    }
     __device__ long long items(const FftRanges&) const { return (long long)s.batch * s.nh; }
-    __device__ FftItem item(long long it, const FftRanges&) const {
+    __device__ FftItem item(int it, const FftRanges&) const {
         FftItem r;
-        r.plane = (int)(it / s.nh);
-        r.idx = (int)(it % s.nh);
+        r.plane = it / s.nh;
+        r.idx = it - r.plane * s.nh;
         return r;
     }
     // spectrum element (row i, column j) of a plane
@@ -723,7 +762,7 @@ template <typename T, int M, bool INVERSE, bool SPEC_T> struct ColsPass {
         for (int m = 0; m < K::HP; ++m) {
             const int i = lane + 32 * m;
             if (i >= r0 && i < r1)
-                cp_async<sizeof(C)>(stage + i, base + (INVERSE ? spec_at(i, it.idx) : (size_t)i * s.nh + it.idx));
+                cp_async<sizeof(C)>(stage + i, base + (INVERSE ? spec_at(i, it.idx) : (size_t)it.idx * s.ypitch + i));
         }
     }
     __device__ void load(const FftItem& it, int lane, const C* stage, C* v, const C* chirp, const FftRanges& rg) const {
@@ -756,10 +795,12 @@ template <typename T, int M, bool INVERSE, bool SPEC_T> struct ColsPass {
         const int nyq = (s.nb & 1) ? -1 : s.nb / 2;
         const bool self_mirror = j == 0 || j == nyq;  // numpy's irfft ignores the imaginary part there
         const int p0 = rg.start ? rg.lo[it.plane] : 0;
-        const int p1 = rg.start ? p0 + rg.cnt(it.plane) : s.npair;
+        const int p1 = min(s.npair, rg.start ? p0 + rg.cnt(it.plane) : s.npair);
         C* zp = dst + (size_t)it.plane * s.z_plane;
         // rows 2p and 2p+1 sit in the adjacent lanes (lane even / odd, same register): the even lane assembles
-        // Z[p][j], the odd lane its Hermitian mirror Z[p][nb-j]
+        // Z[p][j], the odd lane its Hermitian mirror Z[p][nb-j].  Three separate sweeps (chirp products, lane-pair
+        // exchange, stores) so that the HP shared-memory reads / shuffles of a sweep are in flight together
+        // instead of one element's latency chain after the other (v[HP..] are dead here: registers are free).
         const bool odd = (lane & 1) != 0;
 #pragma unroll
         for (int m = 0; m < K::HP; ++m) {
@@ -769,14 +810,18 @@ template <typename T, int M, bool INVERSE, bool SPEC_T> struct ColsPass {
                 mine = cmul(v[m], chirp[i]);
                 mine.y = self_mirror ? T(0) : -mine.y;
             }
-            const C other = shfl_xor_c(mine, 1);
-            const C a = odd ? other : mine, b = odd ? mine : other;
-            const int p = i >> 1;
-            if (p >= p0 && p < p1 && p < s.npair) {
-                C* row = zp + (size_t)p * s.nb;
-                if (!odd) row[j] = make_c<T>(a.x - b.y, a.y + b.x);
-                else if (!self_mirror) row[s.nb - j] = make_c<T>(a.x + b.y, b.x - a.y);
-            }
+            v[m] = mine;
+        }
+#pragma unroll
+        for (int m = 0; m < K::HP; ++m) v[K::HP + m] = shfl_xor_c(v[m], 1);
+        C* mycol = zp + (odd ? (size_t)(s.nb - j) : (size_t)j);
+        const bool writes = !odd || !self_mirror;
+#pragma unroll
+        for (int m = 0; m < K::HP; ++m) {
+            const int p = (lane + 32 * m) >> 1;
+            const C a = odd ? v[K::HP + m] : v[m], b = odd ? v[m] : v[K::HP + m];
+            if (writes && p >= p0 && p < p1)
+                mycol[(size_t)p * s.nb] = odd ? make_c<T>(a.x + b.y, b.x - a.y) : make_c<T>(a.x - b.y, a.y + b.x);
         }
     }
 };
@@ -785,11 +830,17 @@ template <typename T, int M, bool INVERSE, bool SPEC_T> struct ColsPass {
 template <typename T, int M> struct RowsC2R {
     using C = cplx_t<T>;
     using K = FftK<T, M>;
+    static constexpr bool BULK = K::BULK_OK;   // a row of Z is one contiguous run
     const C* z;
     T* out;
     FftShape s;
+    __device__ const C* bulk_src(const FftItem& it, const FftRanges&, int& first, int& count) const {
+        first = 0;
+        count = s.nb;
+        return z + (size_t)it.plane * s.z_plane + (size_t)it.idx * s.nb;
+    }
     __device__ long long items(const FftRanges& rg) const { return RowItems<T, M>::count(s, rg); }
-    __device__ FftItem item(long long it, const FftRanges& rg) const { return RowItems<T, M>::decode(it, s, rg); }
+    __device__ FftItem item(int it, const FftRanges& rg) const { return RowItems<T, M>::decode(it, s, rg); }
     __device__ void prefetch(const FftItem& it, int lane, C* stage, const FftRanges&) const {
         const C* row = z + (size_t)it.plane * s.z_plane + (size_t)it.idx * s.nb;
 #pragma unroll
@@ -837,31 +888,63 @@ __global__ void __launch_bounds__(FftK<T, M>::NT, 1) fft_pass_kernel(Pass pass, 
     extern __shared__ __align__(16) unsigned char fft_smem[];
     C* smem = reinterpret_cast<C*>(fft_smem);
     const int warp = threadIdx.x >> 5;
-    const FftLane<T, M> th(threadIdx.x & 31, p.tw);
+    const FftLane<T, M> th(threadIdx.x & 31);
     C* buf = smem + K::OFF_BUF + warp * K::BUF;
     C* stage = smem + K::OFF_STAGE + warp * K::HALF;
     const C* chirp = smem + K::OFF_CHIRP;
     const FftRanges rg = fft_build_ranges<K::MAX_PLANES>(reinterpret_cast<int*>(fft_smem + K::OFF_RANGES_BYTES),
                                                           pass.s.pair_range, pass.s.batch);
-    fft_load_tables<T, M>(smem, p, true);
-    const long long n_items = pass.items(rg);
-    const long long stride = (long long)gridDim.x * K::G;
-    long long it = (long long)blockIdx.x * K::G + warp;
-    if (it < n_items) pass.prefetch(pass.item(it, rg), th.lane, stage, rg);
-    cp_async_commit();
+    if constexpr (Pass::BULK) {
+        if ((threadIdx.x & 31) == 0) mbar_init(fft_smem + K::OFF_MBAR_BYTES + 8 * warp, 1);
+        mbar_init_fence();
+    }
+    fft_load_tables<T, M>(smem, p, true);   // ends with __syncthreads
+    const int n_items = (int)pass.items(rg);   // < 2^31 (checked by the host)
+    const int stride = (int)gridDim.x * K::G;
+    int it = (int)blockIdx.x * K::G + warp;
+    // staging of an item's inputs: one bulk asynchronous copy per warp (TMA; completion on the warp's own
+    // mbarrier) where the input is a single contiguous run, else cp.async by every lane for its own elements
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(fft_smem + K::OFF_MBAR_BYTES) + warp;
+    unsigned parity = 0;
+    auto stage_in = [&](int item_index) {
+        const FftItem nxt = pass.item(item_index, rg);
+        if constexpr (Pass::BULK) {
+            __syncwarp();                        // every lane has consumed the previous contents of `stage`
+            if (th.lane == 0) {
+                int first, count;
+                const C* src = pass.bulk_src(nxt, rg, first, count);
+                fence_proxy_async_smem();
+                mbar_expect_tx(bar, (unsigned)count * (unsigned)sizeof(C));
+                bulk_copy_g2s(stage + first, src, (unsigned)count * (unsigned)sizeof(C), bar);
+            }
+        } else {
+            pass.prefetch(nxt, th.lane, stage, rg);
+            cp_async_commit();
+        }
+    };
+    if (it < n_items) stage_in(it);
+#if SURFH_FFT_STAGGER
+    // (Experiment, off: starting the second warp of every scheduler half a transform late, so that the two
+    // alternate between FP64-dense and latency-bound phases, changed nothing measurable.)
+    if ((warp >> 2) & 1) __nanosleep(SURFH_FFT_STAGGER);
+#endif
     for (; it < n_items; it += stride) {
         C v[K::PTS];
         const FftItem cur = pass.item(it, rg);
-        cp_async_wait_all();  // every lane consumes only what it copied itself
+        if constexpr (Pass::BULK) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else {
+            cp_async_wait_all();  // every lane consumes only what it copied itself
+        }
         pass.load(cur, th.lane, stage, v, chirp, rg);
         if (K::PTS == 8) {
 #pragma unroll
             for (int m = K::HP; m < K::PTS; ++m) v[m] = make_c<T>(T(0), T(0));
         }
-        if (it + stride < n_items) pass.prefetch(pass.item(it + stride, rg), th.lane, stage, rg);
-        cp_async_commit();
+        if (it + stride < n_items) stage_in(it + stride);
         chirp_convolve<T, M>(v, smem, buf, th);
-        pass.finish(cur, th, v, buf, chirp, rg);
+        pass.finish(pass.item(it, rg), th, v, buf, chirp, rg);
     }
 }
 
