@@ -1,6 +1,6 @@
+# the round's standard check: GPU parity suite, smoke, default bench line, reference arm
 set -x
-ncu --set full --clock-control none --import-source on -k regex:fft_pass -s 12 -c 2 -o gpurun_out/r02_fft_c2r_v2 python bench.py --no-cpu-baseline --no-e2e --solve-iters 0 --steps 1 --warmup 1 > gpurun_out/ncu_f1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fft_pass -s 22 -c 2 -o gpurun_out/r02_fft_r2c_v2 python bench.py --no-cpu-baseline --no-e2e --solve-iters 0 --steps 1 --warmup 1 > gpurun_out/ncu_f2.log 2>&1
-tail -2 gpurun_out/ncu_f2.log
-python tools/precond_sweep.py c2 150 > gpurun_out/precond_c2.txt 2>&1; cat gpurun_out/precond_c2.txt
-python tools/precond_sweep.py c2 150 5 > gpurun_out/precond_c2_mu5.txt 2>&1; cat gpurun_out/precond_c2_mu5.txt
+python -m pytest tests -m gpu -q -s --durations=8 > gpurun_out/pytest_gpu.log 2>&1; tail -16 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
+python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -2 gpurun_out/bench_default.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; tail -2 gpurun_out/bench_reference.err
