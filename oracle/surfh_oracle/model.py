@@ -367,3 +367,22 @@ def solve(model, y, mu_spectro, mu_reg, niter, method="lcg", gradient="separated
     if method == "lcg":
         return lcg(objs, init, tol=tol, max_iter=niter, callback=callback, refresh=refresh)
     return mmmg(objs, init, tol=tol, max_iter=niter, callback=callback)
+
+
+def solve_huber(model, y, mu_spectro, spat_reg, spat_th, niter, value_init=0.0, tol=1e-12, callback=None):
+    """`lmm_reconstruction` of surfh/ToolsDir/algorithms.py:71-106 on this operator: quadratic data term,
+    Huber priors of threshold `spat_th` on the row and column differences, qmm.mmmg.  The differences are the
+    circular NpDiff_r / NpDiff_c of fusion_CT.py:16-43 (the reference routine uses aljabr.Diff, absent here)."""
+    from .thirdparty import Huber, Objective, QuadObjective, mmmg
+    init = (np.ones(model.ishape) * value_init) if np.isscalar(value_init) else np.asarray(value_init)
+    objs = [QuadObjective(model.forward, model.adjoint, data=y, hyper=mu_spectro, name="Data adeq"),
+            Objective(diff_r, diff_r_t, Huber(spat_th), hyper=spat_reg, name="Row prior"),
+            Objective(diff_c, diff_c_t, Huber(spat_th), hyper=spat_reg, name="Col prior")]
+    return mmmg(objs, init, tol=tol, max_iter=niter, callback=callback)
+
+
+def criterion_huber(model, y, x, mu_spectro, spat_reg, spat_th):
+    from .thirdparty import Huber
+    h = Huber(spat_th)
+    return (mu_spectro * np.sum((y - model.forward(x)) ** 2) / 2
+            + spat_reg * float(np.sum(h.value(diff_r(x)) + h.value(diff_c(x)))))

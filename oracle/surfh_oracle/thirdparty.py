@@ -168,6 +168,49 @@ class QuadObjective:
         return f"QuadObjective(name={self.name!r}, hyper={self.hyper})"
 
 
+class Huber:
+    """qmm.Huber(delta): phi(u) = u^2 / 2 for |u| <= delta, delta |u| - delta^2 / 2 beyond; convex, and
+    majorised at any point by a quadratic of curvature phi'(u) / u = min(1, delta / |u|) (Geman-Reynolds
+    coefficients, `gr_coeffs`).  PARITY UNPINNED (qmm 0.18.2 is not in the reference tree); used by
+    surfh/ToolsDir/algorithms.py:27-106 (`vox_reconstruction`, `lmm_reconstruction`)."""
+
+    def __init__(self, delta):
+        self.delta = float(delta)
+        self.inf = 1.0
+
+    def value(self, u):
+        a = np.abs(u)
+        return np.where(a <= self.delta, u ** 2 / 2, self.delta * a - self.delta ** 2 / 2)
+
+    def gradient(self, u):
+        return np.where(np.abs(u) <= self.delta, u, self.delta * np.sign(u))
+
+    def gr_coeffs(self, u):
+        a = np.abs(u)
+        return np.where(a <= self.delta, 1.0, self.delta / np.maximum(a, np.finfo(float).tiny))
+
+
+class Objective:
+    """qmm.Objective(operator, adjoint, loss, data=None, hyper=1): J(x) = hyper * sum loss(V x - data);
+    gradient hyper * V^T loss'(V x - data); majorant curvature in a subspace spanned by `vecs` (given as
+    V vecs): hyper * (V vecs)^T diag(gr_coeffs(V x - data)) (V vecs)."""
+
+    def __init__(self, operator, adjoint, loss, data=None, hyper=1.0, name=""):
+        self.operator, self.adjoint, self.loss = operator, adjoint, loss
+        self.data = 0.0 if data is None else data
+        self.hyper, self.name = hyper, name
+
+    def value(self, x):
+        return self.hyper * float(np.sum(self.loss.value(self.operator(x) - self.data)))
+
+    def gradient(self, x):
+        return self.hyper * self.adjoint(self.loss.gradient(self.operator(x) - self.data))
+
+    def norm_mat_major(self, op_vecs, x):
+        w = self.loss.gr_coeffs(self.operator(x) - self.data).reshape((-1, 1))
+        return self.hyper * (op_vecs.T @ (w * op_vecs))
+
+
 def lcg(objv_list, x0, tol=1e-4, max_iter=500, min_iter=0, callback=None, refresh=50):
     """qmm.lcg: unpreconditioned linear conjugate gradient on  Q x = b,
     Q = sum_i hyper_i V_i^T V_i,  b = sum_i hyper_i V_i^T data_i   (call site
@@ -246,9 +289,10 @@ def mmmg(objv_list, x0, tol=1e-4, max_iter=500, min_iter=0, callback=None):
             move = directions @ step;  x += move;  callback(res)
 
     For QuadObjective the majorant curvature `norm_mat_major` is hyper * vecs^T vecs, i.e. the exact
-    2 x 2 Hessian restricted to the plane, so every iteration is an exact plane search.
+    2 x 2 Hessian restricted to the plane, so every iteration is an exact plane search; an `Objective` with a
+    non-quadratic loss (Huber) contributes hyper * (V vecs)^T diag(gr_coeffs(V x - data)) (V vecs).
     """
-    if isinstance(objv_list, QuadObjective):
+    if isinstance(objv_list, (QuadObjective, Objective)):
         objv_list = [objv_list]
     shape = np.shape(x0)
     vect = lambda op, v: np.reshape(op(np.reshape(v, shape)), (-1, 1))  # noqa: E731
@@ -277,7 +321,8 @@ def mmmg(objv_list, x0, tol=1e-4, max_iter=500, min_iter=0, callback=None):
         directions = np.c_[-grad, move]
         op_directions = [np.c_[vect(obj.operator, directions[:, 0]), prev @ step]
                          for obj, prev in zip(objv_list, op_directions)]
-        mat = sum(obj.hyper * (od.T @ od) for obj, od in zip(objv_list, op_directions))
+        mat = sum(obj.norm_mat_major(od, arr) if isinstance(obj, Objective) else obj.hyper * (od.T @ od)
+                  for obj, od in zip(objv_list, op_directions))
         step = -np.linalg.lstsq(mat, directions.T @ grad, rcond=None)[0]
         move = directions @ step
         res["x"] += move

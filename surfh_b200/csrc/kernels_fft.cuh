@@ -816,12 +816,14 @@ template <typename T, int M, bool INVERSE, bool SPEC_T> struct ColsPass {
         for (int m = 0; m < K::HP; ++m) v[K::HP + m] = shfl_xor_c(v[m], 1);
         C* mycol = zp + (odd ? (size_t)(s.nb - j) : (size_t)j);
         const bool writes = !odd || !self_mirror;
+        // with mine = this lane's row and other = its partner's: the even lane (rows a = mine, b = other) stores
+        // Z[p][j] = (a.x - b.y, a.y + b.x), the odd lane (a = other, b = mine) Z[p][nb-j] = (a.x + b.y, b.x - a.y):
+        // the same two numbers, swapped
 #pragma unroll
         for (int m = 0; m < K::HP; ++m) {
             const int p = (lane + 32 * m) >> 1;
-            const C a = odd ? v[K::HP + m] : v[m], b = odd ? v[m] : v[K::HP + m];
-            if (writes && p >= p0 && p < p1)
-                mycol[(size_t)p * s.nb] = odd ? make_c<T>(a.x + b.y, b.x - a.y) : make_c<T>(a.x - b.y, a.y + b.x);
+            const T re = v[m].x - v[K::HP + m].y, im = v[m].y + v[K::HP + m].x;
+            if (writes && p >= p0 && p < p1) mycol[(size_t)p * s.nb] = odd ? make_c<T>(im, re) : make_c<T>(re, im);
         }
     }
 };

@@ -426,6 +426,93 @@ def mmmg(model, y, mu_spectro=1.0, mu_reg=1.0, x0=None, tol=1e-4, max_iter=500, 
     return res
 
 
+def huber_value(u, delta: float):
+    """qmm.Huber: u^2 / 2 inside [-delta, delta], delta |u| - delta^2 / 2 outside (torch tensors)."""
+    a = u.abs()
+    return _torch().where(a <= delta, 0.5 * u * u, delta * a - 0.5 * delta * delta)
+
+
+def mmmg_huber(model, y, mu_spectro=1.0, spat_reg=1.0, spat_th=1.0, x0=None, tol=1e-4, max_iter=500, min_iter=0,
+               callback: Optional[Callable] = None, numpy_result: bool = True) -> OptimizeResult:
+    """`lmm_reconstruction` (surfh/ToolsDir/algorithms.py:71-106) on the device: quadratic data term +
+    Huber priors (threshold `spat_th`, weight `spat_reg`) on the row and column differences of every map,
+    minimised by qmm.mmmg (3MG): each iteration minimises, over the plane spanned by -grad and the previous
+    move, the quadratic majorant whose curvature for the priors is diag(min(1, delta / |D x|)).
+
+        J(x) = mu_s / 2 |y - H x|^2 + spat_reg * sum_{D in (D_r, D_c)} sum huber_delta(D x)
+
+    One H^T H application and one H application per iteration (the operator work, on the CUDA library); the
+    prior terms are elementwise / circular-shift tensor operations on the K maps.  D_r, D_c are the circular
+    differences of fusion_CT.py:16-43 (the reference routine's aljabr.Diff is not in the reference tree);
+    qmm itself is restated: parity unpinned."""
+    torch = _torch()
+    cg = DeviceCG(model, y, mu_spectro, 0.0)
+    if x0 is None:
+        x0 = np.zeros(model.ishape)
+    cg.start(x0, 1)                          # b = mu_s H^T y
+    x, b = cg.x, cg.b
+    shape = model.ishape
+    n = x.numel()
+    delta, lam = float(spat_th), float(spat_reg)
+    d_r = lambda v: torch.roll(v, 1, dims=1) - v      # noqa: E731  NpDiff_r.forward
+    d_c = lambda v: torch.roll(v, 1, dims=2) - v      # noqa: E731  NpDiff_c.forward
+    d_r_t = lambda v: torch.roll(v, -1, dims=1) - v   # noqa: E731
+    d_c_t = lambda v: torch.roll(v, -1, dims=2) - v   # noqa: E731
+    move = torch.zeros_like(x)
+    h_move = torch.zeros(model.osize, dtype=x.dtype, device=x.device)
+    q = torch.empty_like(x)
+    res = OptimizeResult(x=x, success=False, status=99, nit=max_iter, grad_norm=[], time=[time.time()],
+                         message="maximum number of iterations reached")
+    for iteration in range(max_iter):
+        xm = x.reshape(shape)
+        ur, uc = d_r(xm), d_c(xm)
+        cg.hessp(x, q)                                   # mu_s H^T H x  (mu_reg = 0 in this solver object)
+        g = q.sub_(b)
+        g.add_((d_r_t(ur.clamp(-delta, delta)) + d_c_t(uc.clamp(-delta, delta))).reshape(-1), alpha=lam)
+        gn = float(torch.dot(g, g))
+        res["grad_norm"].append(gn)
+        if gn < n * tol and iteration >= min_iter:
+            res["success"], res["status"], res["nit"] = True, 1, iteration
+            res["message"] = "gradient norm below tolerance"
+            break
+        h_g = model.forward(g.reshape(shape))            # H g; the direction is -g
+        gm, mm = g.reshape(shape), move.reshape(shape)
+        m00 = cg.mu_s * torch.dot(h_g, h_g)
+        m01 = -cg.mu_s * torch.dot(h_g, h_move)
+        m11 = cg.mu_s * torch.dot(h_move, h_move)
+        for u, dg, dm in ((ur, d_r(gm), d_r(mm)), (uc, d_c(gm), d_c(mm))):
+            w = torch.clamp(delta / u.abs().clamp_min(1e-300), max=1.0)       # gr_coeffs
+            m00 = m00 + lam * (w * dg * dg).sum()
+            m01 = m01 - lam * (w * dg * dm).sum()
+            m11 = m11 + lam * (w * dm * dm).sum()
+        rhs = torch.stack([-torch.dot(g, g), torch.dot(move, g)]).double().cpu().numpy()
+        vals = torch.stack([m00, m01, m11]).double().cpu().numpy()
+        mat = np.array([[vals[0], vals[1]], [vals[1], vals[2]]])
+        step = -np.linalg.lstsq(mat, rhs, rcond=None)[0]
+        move.mul_(float(step[1])).add_(g, alpha=-float(step[0]))
+        h_move.mul_(float(step[1])).add_(h_g, alpha=-float(step[0]))
+        x.add_(move)
+        res["time"].append(time.time())
+        if callback is not None:
+            callback(res)
+    torch.cuda.current_stream().synchronize()
+    res["x"] = x.reshape(shape).cpu().numpy().astype(np.float64) if numpy_result else x.reshape(shape)
+    res["solver"] = cg
+    return res
+
+
+def criterion_huber(model, y, x, mu_spectro, spat_reg, spat_th) -> float:
+    """J(x) of `mmmg_huber` (one forward pass)."""
+    torch = _torch()
+    cg = DeviceCG(model, y, mu_spectro, 0.0)
+    xd = cg._to_dev(x).reshape(model.ishape)
+    hx = model.forward(xd).reshape(-1)
+    data = 0.5 * float(mu_spectro) * float(torch.sum((cg.y - hx) ** 2))
+    prior = float(torch.sum(huber_value(torch.roll(xd, 1, dims=1) - xd, float(spat_th))
+                            + huber_value(torch.roll(xd, 1, dims=2) - xd, float(spat_th))))
+    return data + float(spat_reg) * prior
+
+
 class QuadCriterion_MRS:
     """Same constructor and `run_method` as the reference class, run on the device: gradient =
     'separated' (NpDiff_r / NpDiff_c) or 'joint' (Difference_Operator_Joint), method = 'lcg' or anything

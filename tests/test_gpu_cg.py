@@ -230,3 +230,29 @@ def test_preconditioned_cg_reaches_the_same_minimiser_faster(torch_cuda):
     assert j_pre < 1e-3 * j0 and j_plain < 1e-3 * j0
     assert abs(j_pre - j_plain) <= 1e-2 * j_plain
     assert its(pre, 1e-8) <= its(plain, 1e-8)
+
+
+def test_huber_3mg_matches_oracle(torch_cuda):
+    """`lmm_reconstruction` (algorithms.py:71-106): Huber priors on the map differences, qmm.mmmg -- device
+    solver vs the oracle's restated qmm on the oracle operator; the threshold is chosen so that a good share of
+    the differences sits in the linear part of the Huber function."""
+    from surfh_b200 import fusion_CT
+    from surfh_b200.model import spectroSigRLSCT
+    from surfh_oracle import model as om
+    cfg = CASES["mini_2band_4p"]()
+    args = cfg.model_args()
+    oracle = om.SpectroLMM(**args, adjoint_mode="exact")
+    gpu = spectroSigRLSCT(**args, adjoint_mode="exact")
+    y = noisy_data(oracle, cfg)
+    reg, th, n_it = 50.0, 0.05, 10
+    ref = om.solve_huber(oracle, y, 1.0, reg, th, n_it, value_init=0.0)
+    res = fusion_CT.mmmg_huber(gpu, y, 1.0, reg, th, np.zeros(gpu.ishape), tol=1e-12, max_iter=n_it)
+    diffs = np.abs(om.diff_r(ref.x))
+    assert 0.05 < np.mean(diffs > th) < 0.95     # both branches of the Huber function are exercised
+    assert rel(res.x, ref.x) <= 1e-8
+    assert np.allclose(res.grad_norm[: len(ref.grad_norm)], ref.grad_norm, rtol=1e-7)
+    j_gpu = fusion_CT.criterion_huber(gpu, y, res.x, 1.0, reg, th)
+    j_cpu = om.criterion_huber(oracle, y, ref.x, 1.0, reg, th)
+    assert abs(j_gpu - j_cpu) <= 1e-9 * abs(j_cpu)
+    vals = [fusion_CT.criterion_huber(gpu, y, np.zeros(gpu.ishape), 1.0, reg, th), j_gpu]
+    assert vals[1] < vals[0]
