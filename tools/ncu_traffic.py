@@ -26,8 +26,8 @@ for r in rows[1:]:
 
 
 def stage_of(name):
-    table = [("RowsR2C", "chirpz_rfft"), ("ColsPass<double, 1024, 0>", "chirpz_rfft"), ("ColsPass<float, 1024, 0>", "chirpz_rfft"),
-             ("RowsC2R", "chirpz_irfft"), ("ColsPass<double, 1024, 1>", "chirpz_irfft"), ("ColsPass<float, 1024, 1>", "chirpz_irfft"),
+    table = [("RowsR2C", "chirpz_rfft"), ("ColsPass<double, 1024, 0,", "chirpz_rfft"), ("ColsPass<float, 1024, 0,", "chirpz_rfft"),
+             ("RowsC2R", "chirpz_irfft"), ("ColsPass<double, 1024, 1,", "chirpz_irfft"), ("ColsPass<float, 1024, 1,", "chirpz_irfft"),
              ("lmm_otf_fwd", "lmm_otf_fwd"), ("lmm_otf_adj", "lmm_otf_adj"), ("slit_gather", "slit_gather"),
              ("slit_scatter", "slit_scatter"), ("dgemm_mma_kernel<1, 1>", "spectral_gemm_fwd"),
              ("dgemm_mma_kernel<0, 0>", "spectral_gemm_adj"), ("otgemm_kernel", "spectral_gemm")]
