@@ -23,6 +23,7 @@
 #include "fft_plan.cuh"
 #include "kernels_cg.cuh"
 #include "kernels_gemm.cuh"
+#include "kernels_gemm_tma.cuh"
 #include "kernels_lmm.cuh"
 #include "kernels_precond.cuh"
 #include "kernels_slit.cuh"
@@ -133,6 +134,11 @@ template <typename T> struct BandT {
     int csr_rows[2] = {0, 0};
     int64_t csr_nnz[2] = {0, 0};
     DevBuf t_ident, t_wrow, t_gK, t_gN, t_yM, t_yN;
+    // TMA contraction (fp64): transposed LSF copy, K-fast detector block, epilogue tables in n' order, tensor maps
+    DevBuf lsf_t, yk, t_yNp, t_gNp;
+    int ndp = 0;                       // nd rounded up to even: row pitch of lsf_t / yk (16-byte multiple)
+    CUtensorMap map_w, map_g, map_wt, map_yk;
+    bool tma_ready = false;
     DevBuf G;  // [nl][ncol] slit-space vector (forward G / adjoint Gt), columns in INTERNAL order
     // The ABI (and the detector) order slit-space columns as ((p*S + s)*na + a)*nb + b; internally they are
     // stored as ((p*na + a)*S + s)*nb + b, so that the 32 consecutive cube pixels a warp of the scatter owns
@@ -146,6 +152,19 @@ template <typename T> struct BandT {
         const int ss = r % S, pp = r / S;
         return ((pp * na + aa) * S + ss) * nb + bb;
     }
+    // Element (l, n', b) of G lives at n' * g_col + l * g_l + b (see SlitTables): K-fast per detector column for
+    // bands with a spectral response, [l][n'][b] for beta-sum bands.
+    int g_col = 0, g_l = 0;
+    // detector sample n = (p*S + s)*na + a  ->  internal detector column n' = (p*na + a)*S + s
+    int nprime_of_sample(int n) const {
+        const int aa = n % na, ps = n / na, ss = ps % S, pp = ps / S;
+        return (pp * na + aa) * S + ss;
+    }
+    // offset in plane 0 of G of the ABI slit-space column c = ((p*S + s)*na + a)*nb + b
+    int32_t g_offset(int c) const {
+        const int ic = internal_col(c);
+        return (int32_t)((int64_t)(ic / nb) * g_col + ic % nb);
+    }
 
     SlitTables<T> slit_tables() const {
         SlitTables<T> t;
@@ -155,6 +174,7 @@ template <typename T> struct BandT {
         t.grid_base = grid_base.as<int32_t>();
         t.grid_frac = grid_frac.as<T>();
         t.P = P; t.S = S; t.na = na; t.nb = nb; t.srf = srf; t.A = A; t.B = B; t.ncol = ncol;
+        t.g_col = g_col; t.g_l = g_l;
         return t;
     }
     CsrTable<T> csr(int mode) const {
@@ -184,6 +204,36 @@ template <> struct FftTraits<double> {
 template <typename T> struct GemmCfg;
 template <> struct GemmCfg<double> { static constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4; };
 template <> struct GemmCfg<float> { static constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8; };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        SURFH_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) throw Error(SURFH_ECUDA, "cuTensorMapEncodeTiled is not available");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// fp64 matrix [rows][inner] with `inner` contiguous and `pitch` elements between rows -> tiles of box_rows x 16
+// doubles (128 bytes) with the 128-byte swizzle; out-of-range elements read as zero
+static CUtensorMap tensor_map_2d_f64(const void* base, int inner, int rows, size_t pitch, int box_rows) {
+    CUtensorMap m;
+    const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)kTBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), gdim, gstride, box,
+                                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(SURFH_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
 
 template <typename T> struct ModelImpl : surfh_model {
     using C = cplx_t<T>;
@@ -310,6 +360,8 @@ template <typename T> struct ModelImpl : surfh_model {
         b->Nn = b->P * b->S * b->na;
         b->ncol = b->Nn * b->nb;
         b->KB = b->nl * b->nb;
+        if (b->mode == SURFH_SPECTRAL_LSF) { b->g_col = b->KB; b->g_l = b->nb; }
+        else { b->g_col = b->nb; b->g_l = b->ncol; }
         b->out_offset = d->out_offset;
         b->out_size = (int64_t)b->Nn * b->nd;
         SURFH_REQUIRE(d->out_offset >= 0, "negative out_offset");
@@ -377,7 +429,7 @@ template <typename T> struct ModelImpl : surfh_model {
             for (int r = 0; r < n_rows; ++r) {
                 const int64_t at = slice_ptr[(size_t)(r / 32)] + r % 32;
                 for (int64_t e = cs[m]->row_ptr[r], k = 0; e < cs[m]->row_ptr[r + 1]; ++e, ++k) {
-                    col[(size_t)(at + 32 * k)] = b->internal_col(cs[m]->col[e]);
+                    col[(size_t)(at + 32 * k)] = b->g_offset(cs[m]->col[e]);
                     val[(size_t)(at + 32 * k)] = cs[m]->val[e];
                 }
             }
@@ -395,10 +447,10 @@ template <typename T> struct ModelImpl : surfh_model {
             for (int i = 0; i < b->nd; ++i) v[i] = i * b->KB;
             upload_converted<int32_t>(b->t_wrow, v.data(), b->nd);
             v.assign(b->KB, 0);
-            for (int k = 0; k < b->KB; ++k) v[k] = (k / b->nb) * b->ncol + k % b->nb;
+            for (int k = 0; k < b->KB; ++k) v[k] = (k / b->nb) * b->g_l + k % b->nb;   // = k in the K-fast layout
             upload_converted<int32_t>(b->t_gK, v.data(), b->KB);
             v.assign(b->Nn, 0);
-            for (int n = 0; n < b->Nn; ++n) v[n] = b->internal_col(n * b->nb);  // n = (p*S + s)*na + a
+            for (int n = 0; n < b->Nn; ++n) v[n] = b->nprime_of_sample(n) * b->g_col;  // n = (p*S + s)*na + a
             upload_converted<int32_t>(b->t_gN, v.data(), b->Nn);
             v.assign(b->nd, 0);
             for (int m = 0; m < b->nd; ++m) v[m] = m * b->na;
@@ -408,6 +460,28 @@ template <typename T> struct ModelImpl : surfh_model {
             upload_converted<int32_t>(b->t_yN, v.data(), b->Nn);
         }
         b->G.alloc((size_t)b->nl * b->ncol * sizeof(T));
+        if (b->mode == SURFH_SPECTRAL_LSF && std::is_same<T, double>::value) {
+            // operands and tables of the TMA contraction (kernels_gemm_tma.cuh)
+            b->ndp = (b->nd + 1) / 2 * 2;
+            std::vector<double> wt((size_t)b->KB * b->ndp, 0.0);
+            for (int m = 0; m < b->nd; ++m)
+                for (int k = 0; k < b->KB; ++k) wt[(size_t)k * b->ndp + m] = d->lsf[(size_t)m * b->KB + k];
+            upload_converted<double>(b->lsf_t, wt.data(), wt.size());
+            b->yk.alloc((size_t)b->Nn * b->ndp * sizeof(double));
+            std::vector<int32_t> v(b->Nn);
+            for (int np = 0; np < b->Nn; ++np) {   // n' = (p*na + a)*S + s
+                const int ss = np % b->S, pa = np / b->S, aa = pa % b->na, pp = pa / b->na;
+                v[np] = (pp * b->S + ss) * (b->nd * b->na) + aa;
+            }
+            upload_converted<int32_t>(b->t_yNp, v.data(), b->Nn);
+            for (int np = 0; np < b->Nn; ++np) v[np] = np * b->g_col;
+            upload_converted<int32_t>(b->t_gNp, v.data(), b->Nn);
+            b->map_w = tensor_map_2d_f64(b->lsf.p, b->KB, b->nd, (size_t)b->KB, kTBM);
+            b->map_g = tensor_map_2d_f64(b->G.p, b->KB, b->Nn, (size_t)b->g_col, kTBN);
+            b->map_wt = tensor_map_2d_f64(b->lsf_t.p, b->nd, b->KB, (size_t)b->ndp, kTBM);
+            b->map_yk = tensor_map_2d_f64(b->yk.p, b->nd, b->Nn, (size_t)b->ndp, kTBN);
+            b->tma_ready = true;
+        }
         bands.push_back(std::move(b));
     }
 
@@ -511,7 +585,9 @@ template <typename T> struct ModelImpl : surfh_model {
             SURFH_CUDA(cudaFuncSetAttribute(sgemm_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)sgemm_smem_bytes<false, false>()));
         }
+        if (const char* e = std::getenv("SURFH_F64_GEMM")) f64_tma_gemm = std::strcmp(e, "mma") != 0;
         if (std::is_same<T, double>::value) {
+            SURFH_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmemBytes));
             SURFH_CUDA(cudaFuncSetAttribute(dgemm_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)dgemm_smem_bytes<true, true>()));
             SURFH_CUDA(cudaFuncSetAttribute(dgemm_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -650,6 +726,8 @@ template <typename T> struct ModelImpl : surfh_model {
     // FP32 tensor path (3xTF32 split), same grouping; SURFH_F32_GEMM=simt selects the FFMA kernel
     void gemm_grouped_f32(float* y, bool adjoint, cudaStream_t st);
     bool f32_tensor_gemm = true;
+    bool f64_tma_gemm = true;   // SURFH_F64_GEMM=mma selects the round-1 offset-table DMMA kernel (A/B runs)
+    void gemm_grouped_f64_tma(double* y, bool adjoint, cudaStream_t st);
 
     void beta_sum(BandT<T>& b, T* y, bool adjoint, cudaStream_t st) {
         const size_t n = (size_t)b.nl * b.Nn * (adjoint ? b.nb : 1);
@@ -703,7 +781,7 @@ template <typename T> struct ModelImpl : surfh_model {
             dim3 grid(ceil_div(b.S * b.na * b.nb, 32 * chunks), ceil_div(nl, kLB));
             slit_gather_kernel<T, kLB><<<grid, 128, 0, st>>>(cubebuf.as<T>() + (size_t)(lo - c0) * plane, plane, Nb, nl,
                                                              b.slit_tables(),
-                                                             b.G.template as<T>() + (size_t)(lo - b.l0) * b.ncol);
+                                                             b.G.template as<T>() + (size_t)(lo - b.l0) * b.g_l);
             SURFH_CUDA(cudaGetLastError());
         }
     }
@@ -728,7 +806,7 @@ template <typename T> struct ModelImpl : surfh_model {
             dim3 grid(ceil_div(b.csr_rows[mode], 128), ceil_div(nl, kLBs));
             const double bytes = sizeof(T) * ((double)nl * b.ncol + 2.0 * nl * b.csr_rows[mode]);
             Scope sc(this, ST_SLIT_SCATTER, st, bytes, 2.0 * nl * (double)b.csr_nnz[mode], 1, true);
-            slit_scatter_kernel<T, kLBs><<<grid, 128, 0, st>>>(b.G.template as<T>() + (size_t)(lo - b.l0) * b.ncol, b.ncol,
+            slit_scatter_kernel<T, kLBs><<<grid, 128, 0, st>>>(b.G.template as<T>() + (size_t)(lo - b.l0) * b.g_l, b.g_l,
                                                               nl, b.csr(mode),
                                                               cubebuf.as<T>() + (size_t)(lo - c0) * plane, plane);
             SURFH_CUDA(cudaGetLastError());
@@ -1108,7 +1186,59 @@ template <> void ModelImpl<float>::gemm_grouped_f32(float* y, bool adjoint, cuda
     }
 }
 
+template <> void ModelImpl<float>::gemm_grouped_f64_tma(double*, bool, cudaStream_t) {
+    throw Error(SURFH_ESTATE, "internal: fp64 GEMM on an fp32 model");
+}
+
+template <> void ModelImpl<double>::gemm_grouped_f64_tma(double* y, bool adjoint, cudaStream_t st) {
+    std::vector<size_t> lsf_bands;
+    for (size_t i = 0; i < bands.size(); ++i)
+        if (bands[i]->mode == SURFH_SPECTRAL_LSF) lsf_bands.push_back(i);
+    std::stable_sort(lsf_bands.begin(), lsf_bands.end(), [&](size_t x, size_t y2) {
+        const int kx = adjoint ? bands[x]->nd : bands[x]->KB, ky = adjoint ? bands[y2]->nd : bands[y2]->KB;
+        return kx > ky;
+    });
+    if (adjoint) {
+        // detector blocks -> K-fast per detector column (the B operand of Gt = Wt . Yk)
+        double bytes = 0;
+        for (size_t j : lsf_bands) bytes += 2.0 * sizeof(double) * (double)bands[j]->out_size;
+        Scope sc(this, ST_GEMM_ADJ, st, bytes, 0, (int)lsf_bands.size(), true);
+        for (size_t j : lsf_bands) {
+            BandT<double>& b = *bands[j];
+            const size_t n = (size_t)b.Nn * b.nd;
+            detector_to_kfast_kernel<<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.S, b.na, b.nd, b.Nn, b.ndp,
+                                                                        b.yk.as<double>());
+        }
+        SURFH_CUDA(cudaGetLastError());
+    }
+    for (size_t first = 0; first < lsf_bands.size(); first += kMaxGemmGroup) {
+        GemmTmaBatch batch;
+        batch.count = 0;
+        batch.tile_start[0] = 0;
+        double bytes = 0, flops = 0;
+        for (size_t j = first; j < std::min(lsf_bands.size(), first + (size_t)kMaxGemmGroup); ++j) {
+            BandT<double>& b = *bands[lsf_bands[j]];
+            GemmTmaProblem& g = batch.p[batch.count];
+            if (!adjoint) {   // y = W . G
+                g.a = b.map_w; g.b = b.map_g; g.M = b.nd; g.N = b.Nn; g.K = b.KB;
+                g.C = y + b.out_offset; g.cM = b.t_yM.as<int32_t>(); g.cN = b.t_yNp.as<int32_t>();
+            } else {          // Gt = Wt . Yk
+                g.a = b.map_wt; g.b = b.map_yk; g.M = b.KB; g.N = b.Nn; g.K = b.nd;
+                g.C = b.G.as<double>(); g.cM = b.t_ident.as<int32_t>(); g.cN = b.t_gNp.as<int32_t>();
+            }
+            batch.tile_start[batch.count + 1] = batch.tile_start[batch.count] + ceil_div(g.M, kTBM) * ceil_div(g.N, kTBN);
+            batch.count++;
+            bytes += sizeof(double) * ((double)b.nd * b.KB + (double)b.nl * b.ncol + (double)b.out_size);
+            flops += 2.0 * g.M * g.N * g.K;
+        }
+        Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, flops, 1, true);
+        dgemm_tma_kernel<<<batch.tile_start[batch.count], kTThreads, kTSmemBytes, st>>>(batch);
+        SURFH_CUDA(cudaGetLastError());
+    }
+}
+
 template <> void ModelImpl<double>::gemm_grouped_f64(double* y, bool adjoint, cudaStream_t st) {
+    if (f64_tma_gemm) return gemm_grouped_f64_tma(y, adjoint, st);
     std::vector<size_t> lsf_bands;
     for (size_t i = 0; i < bands.size(); ++i)
         if (bands[i]->mode == SURFH_SPECTRAL_LSF) lsf_bands.push_back(i);

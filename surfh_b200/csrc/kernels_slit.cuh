@@ -32,6 +32,11 @@ template <typename T> struct SlitTables {
     const T* grid_frac;        // [P, A*B, 2]
     int32_t P, S, na, nb, srf, A, B;
     int32_t ncol;  // P*S*na*nb
+    // slit-space vector G: element (wavelength l, detector column n' = (p*na + a)*S + s, beta b) lives at
+    // n' * g_col + l * g_l + b.  Bands with a spectral response store it K-fast per detector column
+    // (g_col = Lambda_b * nb, g_l = nb: the contraction's operand is then a plain [n'][k = l*nb + b] matrix, a 2-D TMA
+    // tensor map); beta-sum bands keep [l][n'][b] (g_col = nb, g_l = ncol).
+    int32_t g_col, g_l;
 };
 
 template <typename T, int LB>
@@ -57,7 +62,7 @@ slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube
     const int s = r % t.S;
     const int a = r / t.S;
   for (int p = warp % pp; p < t.P; p += pp) {
-    const int c = ((p * t.na + a) * t.S + s) * t.nb + b;  // internal slit-space order: contiguous in (s, b)
+    const size_t c = (size_t)((p * t.na + a) * t.S + s) * t.g_col + b;  // column n' = (p, a, s) of the slit space
     const int j = t.slit_b0[s] + b;
     const int i_first = t.slit_a0[s] + a * t.srf;
     const int32_t* gb = t.grid_base + (size_t)p * t.A * t.B;
@@ -89,7 +94,7 @@ slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube
     const T w = t.slit_w[s * t.nb + b];
 #pragma unroll
     for (int u = 0; u < LB; ++u)
-        if (l0 + u < n_l) G[(size_t)(l0 + u) * t.ncol + c] = w * acc[u];
+        if (l0 + u < n_l) G[c + (size_t)(l0 + u) * t.g_l] = w * acc[u];
   }
 }
 
@@ -106,7 +111,8 @@ slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube
 template <typename T> struct CsrTable {
     const int32_t* row_pixel;   // [n_rows]
     const int64_t* slice_ptr;   // [n_slices + 1] entry offset of every slice (multiples of 32)
-    const int32_t* col;         // [slice_ptr[n_slices]]  entry k of row r at slice_ptr[r/32] + 32 k + r % 32
+    const int32_t* col;         // [slice_ptr[n_slices]]  entry k of row r at slice_ptr[r/32] + 32 k + r % 32;
+                                // the value is the element offset n' * g_col + b of the entry in plane 0 of G
     const T* val;               // same layout
     int32_t n_rows;
 };
@@ -114,8 +120,8 @@ template <typename T> struct CsrTable {
 // cube[l, pixel] += sum_e val[e] * Gt[l, col[e]]     (the rows of the cube are zeroed by the caller)
 template <typename T, int LB>
 __global__ void __launch_bounds__(128)
-slit_scatter_kernel(const T* __restrict__ Gt, int ncol, int n_l, CsrTable<T> t, T* __restrict__ cube,
-                    size_t plane) {
+slit_scatter_kernel(const T* __restrict__ Gt, int g_l /* elements between wavelengths of G */, int n_l, CsrTable<T> t,
+                    T* __restrict__ cube, size_t plane) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int slice = r >> 5, lane = r & 31;             // warp-uniform slice: no divergence on the loop bound
     if ((slice << 5) >= t.n_rows) return;
@@ -125,7 +131,7 @@ slit_scatter_kernel(const T* __restrict__ Gt, int ncol, int n_l, CsrTable<T> t, 
     T acc[LB];
 #pragma unroll
     for (int u = 0; u < LB; ++u) acc[u] = T(0);
-    const T* g = Gt + (size_t)l0 * ncol;
+    const T* g = Gt + (size_t)l0 * g_l;
     const int32_t* col = t.col + base + lane;
     const T* val = t.val + base + lane;
 #pragma unroll 4  // 4 entries = 16 dependent G loads in flight (unroll 1: 3.28 ms, 4: 2.59 ms, 8: 2.79 ms on C4)
@@ -134,7 +140,7 @@ slit_scatter_kernel(const T* __restrict__ Gt, int ncol, int n_l, CsrTable<T> t, 
         const T v = __ldg(val + 32 * k);
 #pragma unroll
         for (int u = 0; u < LB; ++u)
-            if (l0 + u < n_l) acc[u] = fma(v, __ldg(g + (size_t)u * ncol + c), acc[u]);
+            if (l0 + u < n_l) acc[u] = fma(v, __ldg(g + (size_t)u * g_l + c), acc[u]);
     }
     if (r >= t.n_rows) return;
     T* dst = cube + (size_t)l0 * plane + t.row_pixel[r];
