@@ -135,7 +135,7 @@ template <typename T> struct BandT {
     int64_t csr_nnz[2] = {0, 0};
     DevBuf t_ident, t_wrow, t_gK, t_gN, t_yM, t_yN;
     // TMA contraction (fp64): transposed LSF copy, K-fast detector block, epilogue tables in n' order, tensor maps
-    DevBuf lsf_t, yk, t_yNp, t_gNp;
+    DevBuf lsf_t, yk;
     int ndp = 0;                       // nd rounded up to even: row pitch of lsf_t / yk (16-byte multiple)
     CUtensorMap map_w, map_g, map_wt, map_yk;
     bool tma_ready = false;
@@ -152,19 +152,17 @@ template <typename T> struct BandT {
         const int ss = r % S, pp = r / S;
         return ((pp * na + aa) * S + ss) * nb + bb;
     }
-    // Element (l, n', b) of G lives at n' * g_col + l * g_l + b (see SlitTables): K-fast per detector column for
-    // bands with a spectral response, [l][n'][b] for beta-sum bands.
-    int g_col = 0, g_l = 0;
-    // detector sample n = (p*S + s)*na + a  ->  internal detector column n' = (p*na + a)*S + s
-    int nprime_of_sample(int n) const {
+    // Element (l, column, b) of G lives at column * g_col + l * g_l + b (see SlitTables): K-fast per detector
+    // column in the detector's order for bands with a spectral response, [l][n'][b] for beta-sum bands.
+    int g_col = 0, g_l = 0, g_psa = 0;
+    // detector sample n = (p*S + s)*na + a  ->  its column of G
+    int column_of_sample(int n) const {
+        if (g_psa) return n;
         const int aa = n % na, ps = n / na, ss = ps % S, pp = ps / S;
         return (pp * na + aa) * S + ss;
     }
     // offset in plane 0 of G of the ABI slit-space column c = ((p*S + s)*na + a)*nb + b
-    int32_t g_offset(int c) const {
-        const int ic = internal_col(c);
-        return (int32_t)((int64_t)(ic / nb) * g_col + ic % nb);
-    }
+    int32_t g_offset(int c) const { return (int32_t)((int64_t)column_of_sample(c / nb) * g_col + c % nb); }
 
     SlitTables<T> slit_tables() const {
         SlitTables<T> t;
@@ -174,7 +172,7 @@ template <typename T> struct BandT {
         t.grid_base = grid_base.as<int32_t>();
         t.grid_frac = grid_frac.as<T>();
         t.P = P; t.S = S; t.na = na; t.nb = nb; t.srf = srf; t.A = A; t.B = B; t.ncol = ncol;
-        t.g_col = g_col; t.g_l = g_l;
+        t.g_col = g_col; t.g_l = g_l; t.g_psa = g_psa;
         return t;
     }
     CsrTable<T> csr(int mode) const {
@@ -242,7 +240,9 @@ template <typename T> struct ModelImpl : surfh_model {
     DevBuf tpl_raw;   // [K][Nl] real, unscaled (maps_to_cube)
     DevBuf xhat;      // [K][nfp] complex
     DevBuf spec;      // [chunk][nfp] complex
-    DevBuf cubebuf;   // [chunk][plane] real
+    DevBuf cubebuf;   // [chunk][cplane] real
+    size_t cplane = 0;  // elements between planes of the working cube: `plane` rounded up to even with the hand-written
+                        // FFT, so that every row pair starts 16-byte aligned (one TMA bulk copy stages it)
     DevBuf fft_work;
     DevBuf zbuf;      // [max(chunk, K)][z_plane] complex: intermediate of the hand-written FFT passes
     OwnFft2d<T> ownfft;
@@ -360,8 +360,8 @@ template <typename T> struct ModelImpl : surfh_model {
         b->Nn = b->P * b->S * b->na;
         b->ncol = b->Nn * b->nb;
         b->KB = b->nl * b->nb;
-        if (b->mode == SURFH_SPECTRAL_LSF) { b->g_col = b->KB; b->g_l = b->nb; }
-        else { b->g_col = b->nb; b->g_l = b->ncol; }
+        if (b->mode == SURFH_SPECTRAL_LSF) { b->g_col = b->KB; b->g_l = b->nb; b->g_psa = 1; }
+        else { b->g_col = b->nb; b->g_l = b->ncol; b->g_psa = 0; }
         b->out_offset = d->out_offset;
         b->out_size = (int64_t)b->Nn * b->nd;
         SURFH_REQUIRE(d->out_offset >= 0, "negative out_offset");
@@ -450,7 +450,7 @@ template <typename T> struct ModelImpl : surfh_model {
             for (int k = 0; k < b->KB; ++k) v[k] = (k / b->nb) * b->g_l + k % b->nb;   // = k in the K-fast layout
             upload_converted<int32_t>(b->t_gK, v.data(), b->KB);
             v.assign(b->Nn, 0);
-            for (int n = 0; n < b->Nn; ++n) v[n] = b->nprime_of_sample(n) * b->g_col;  // n = (p*S + s)*na + a
+            for (int n = 0; n < b->Nn; ++n) v[n] = b->column_of_sample(n) * b->g_col;  // n = (p*S + s)*na + a
             upload_converted<int32_t>(b->t_gN, v.data(), b->Nn);
             v.assign(b->nd, 0);
             for (int m = 0; m < b->nd; ++m) v[m] = m * b->na;
@@ -468,14 +468,6 @@ template <typename T> struct ModelImpl : surfh_model {
                 for (int k = 0; k < b->KB; ++k) wt[(size_t)k * b->ndp + m] = d->lsf[(size_t)m * b->KB + k];
             upload_converted<double>(b->lsf_t, wt.data(), wt.size());
             b->yk.alloc((size_t)b->Nn * b->ndp * sizeof(double));
-            std::vector<int32_t> v(b->Nn);
-            for (int np = 0; np < b->Nn; ++np) {   // n' = (p*na + a)*S + s
-                const int ss = np % b->S, pa = np / b->S, aa = pa % b->na, pp = pa / b->na;
-                v[np] = (pp * b->S + ss) * (b->nd * b->na) + aa;
-            }
-            upload_converted<int32_t>(b->t_yNp, v.data(), b->Nn);
-            for (int np = 0; np < b->Nn; ++np) v[np] = np * b->g_col;
-            upload_converted<int32_t>(b->t_gNp, v.data(), b->Nn);
             b->map_w = tensor_map_2d_f64(b->lsf.p, b->KB, b->nd, (size_t)b->KB, kTBM);
             b->map_g = tensor_map_2d_f64(b->G.p, b->KB, b->Nn, (size_t)b->g_col, kTBN);
             b->map_wt = tensor_map_2d_f64(b->lsf_t.p, b->nd, b->KB, (size_t)b->ndp, kTBM);
@@ -538,7 +530,9 @@ template <typename T> struct ModelImpl : surfh_model {
         chunk = std::min(chunk, longest);
         spec.alloc((size_t)chunk * nfp * sizeof(C));
         SURFH_CUDA(cudaMemset(spec.p, 0, spec.bytes));
-        cubebuf.alloc((size_t)chunk * plane * sizeof(T));
+        cplane = use_own_fft ? (plane + 1) / 2 * 2 : plane;
+        cubebuf.alloc(((size_t)chunk * cplane + Nb) * sizeof(T));   // + one row of slack: the bulk copy of a plane's
+                                                                      // last (unpaired) row reads a full pair
         if (K > 0) {
             xhat.alloc((size_t)K * nfp * sizeof(C));
             SURFH_CUDA(cudaMemset(xhat.p, 0, xhat.bytes));
@@ -665,7 +659,9 @@ template <typename T> struct ModelImpl : surfh_model {
     }
     // prune_c0 >= 0: the real side is the working cube of planes [prune_c0, prune_c0 + batch), of which only
     // the rows some band touches matter (C2R: produced; R2C: non-zero)
-    void fft_exec(int kind, int batch, void* in, void* out, cudaStream_t st, int prune_c0 = -1) {
+    // real_stride: elements between the real planes (0 = `plane`: caller-owned contiguous maps / cubes)
+    void fft_exec(int kind, int batch, void* in, void* out, cudaStream_t st, int prune_c0 = -1, size_t real_stride = 0) {
+        if (real_stride == 0) real_stride = plane;
         if (use_own_fft) {
             const int2* pr = nullptr;
             long long n_pairs = 0;
@@ -674,10 +670,10 @@ template <typename T> struct ModelImpl : surfh_model {
                 for (int l = prune_c0; l < prune_c0 + batch; ++l) n_pairs += plane_pair_cnt[l];
             }
             if (kind == 0)
-                ownfft.r2c(reinterpret_cast<const T*>(in), plane, reinterpret_cast<C*>(out), nfp, zbuf.as<C>(), batch, st,
+                ownfft.r2c(reinterpret_cast<const T*>(in), real_stride, reinterpret_cast<C*>(out), nfp, zbuf.as<C>(), batch, st,
                            true, pr, n_pairs);
             else
-                ownfft.c2r(reinterpret_cast<const C*>(in), nfp, reinterpret_cast<T*>(out), plane, zbuf.as<C>(), batch, st,
+                ownfft.c2r(reinterpret_cast<const C*>(in), nfp, reinterpret_cast<T*>(out), real_stride, zbuf.as<C>(), batch, st,
                            true, pr, n_pairs);
             return;
         }
@@ -779,7 +775,7 @@ template <typename T> struct ModelImpl : surfh_model {
             Scope sc(this, ST_SLIT_GATHER, st, bytes, 8.0 * nl * b.ncol * b.srf, 1, true);
             const int pp = std::min(b.P, 4), chunks = 4 / pp;  // see the kernel: 4 warps = pp pointings x chunks
             dim3 grid(ceil_div(b.S * b.na * b.nb, 32 * chunks), ceil_div(nl, kLB));
-            slit_gather_kernel<T, kLB><<<grid, 128, 0, st>>>(cubebuf.as<T>() + (size_t)(lo - c0) * plane, plane, Nb, nl,
+            slit_gather_kernel<T, kLB><<<grid, 128, 0, st>>>(cubebuf.as<T>() + (size_t)(lo - c0) * cplane, cplane, Nb, nl,
                                                              b.slit_tables(),
                                                              b.G.template as<T>() + (size_t)(lo - b.l0) * b.g_l);
             SURFH_CUDA(cudaGetLastError());
@@ -792,11 +788,11 @@ template <typename T> struct ModelImpl : surfh_model {
             for (int l = c0; l < c1; ++l) rows += 2.0 * plane_pair_cnt[l];
             Scope sc(this, ST_MEMSET, st, rows * Nb * sizeof(T), 0, 1, true);
             dim3 grid(32, c1 - c0);
-            zero_row_hull_kernel<T><<<grid, 256, 0, st>>>(cubebuf.as<T>(), plane, Na, Nb, plane_pairs.as<int2>() + c0);
+            zero_row_hull_kernel<T><<<grid, 256, 0, st>>>(cubebuf.as<T>(), cplane, Na, Nb, plane_pairs.as<int2>() + c0);
             SURFH_CUDA(cudaGetLastError());
         } else {
             Scope sc(this, ST_MEMSET, st, (double)(c1 - c0) * plane * sizeof(T), 0, 1, false);
-            SURFH_CUDA(cudaMemsetAsync(cubebuf.p, 0, (size_t)(c1 - c0) * plane * sizeof(T), st));
+            SURFH_CUDA(cudaMemsetAsync(cubebuf.p, 0, (size_t)(c1 - c0) * cplane * sizeof(T), st));
         }
         for (auto& bp : bands) {
             BandT<T>& b = *bp;
@@ -808,7 +804,7 @@ template <typename T> struct ModelImpl : surfh_model {
             Scope sc(this, ST_SLIT_SCATTER, st, bytes, 2.0 * nl * (double)b.csr_nnz[mode], 1, true);
             slit_scatter_kernel<T, kLBs><<<grid, 128, 0, st>>>(b.G.template as<T>() + (size_t)(lo - b.l0) * b.g_l, b.g_l,
                                                               nl, b.csr(mode),
-                                                              cubebuf.as<T>() + (size_t)(lo - c0) * plane, plane);
+                                                              cubebuf.as<T>() + (size_t)(lo - c0) * cplane, cplane);
             SURFH_CUDA(cudaGetLastError());
         }
     }
@@ -847,7 +843,7 @@ template <typename T> struct ModelImpl : surfh_model {
                 }
                 {
                     Scope sc(this, ST_IRFFT_CUBE, st, fft_bytes(nl, c0), fft_flops(nl, c0), fft_launches(), use_own_fft);
-                    fft_exec(1, nl, spec.p, cubebuf.p, st, c0);
+                    fft_exec(1, nl, spec.p, cubebuf.p, st, c0, cplane);
                 }
                 gather_chunk(c0, c1, st);
             }
@@ -873,7 +869,7 @@ template <typename T> struct ModelImpl : surfh_model {
                 scatter_chunk(c0, c1, mode, st);
                 {
                     Scope sc(this, ST_RFFT_CUBE, st, fft_bytes(nl, c0), fft_flops(nl, c0), fft_launches(), use_own_fft);
-                    fft_exec(0, nl, cubebuf.p, spec.p, st, c0);
+                    fft_exec(0, nl, cubebuf.p, spec.p, st, c0, cplane);
                 }
                 if (K > 0) {
                     Scope sc(this, ST_LMM_OTF_ADJ, st, (double)nl * nf * sizeof(C) * 2 + (double)K * nf * sizeof(C),
@@ -1206,7 +1202,7 @@ template <> void ModelImpl<double>::gemm_grouped_f64_tma(double* y, bool adjoint
         for (size_t j : lsf_bands) {
             BandT<double>& b = *bands[j];
             const size_t n = (size_t)b.Nn * b.nd;
-            detector_to_kfast_kernel<<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.S, b.na, b.nd, b.Nn, b.ndp,
+            detector_to_kfast_kernel<<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.na, b.nd, b.Nn, b.ndp,
                                                                         b.yk.as<double>());
         }
         SURFH_CUDA(cudaGetLastError());
@@ -1221,10 +1217,10 @@ template <> void ModelImpl<double>::gemm_grouped_f64_tma(double* y, bool adjoint
             GemmTmaProblem& g = batch.p[batch.count];
             if (!adjoint) {   // y = W . G
                 g.a = b.map_w; g.b = b.map_g; g.M = b.nd; g.N = b.Nn; g.K = b.KB;
-                g.C = y + b.out_offset; g.cM = b.t_yM.as<int32_t>(); g.cN = b.t_yNp.as<int32_t>();
+                g.C = y + b.out_offset; g.cM = b.t_yM.as<int32_t>(); g.cN = b.t_yN.as<int32_t>();
             } else {          // Gt = Wt . Yk
                 g.a = b.map_wt; g.b = b.map_yk; g.M = b.KB; g.N = b.Nn; g.K = b.nd;
-                g.C = b.G.as<double>(); g.cM = b.t_ident.as<int32_t>(); g.cN = b.t_gNp.as<int32_t>();
+                g.C = b.G.as<double>(); g.cM = b.t_ident.as<int32_t>(); g.cN = b.t_gN.as<int32_t>();
             }
             batch.tile_start[batch.count + 1] = batch.tile_start[batch.count] + ceil_div(g.M, kTBM) * ceil_div(g.N, kTBN);
             batch.count++;

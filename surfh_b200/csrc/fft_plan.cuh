@@ -45,7 +45,8 @@ template <typename T> struct FftAxis {
                                         (int)FftK<T, M>::SMEM_BYTES));
     }
     template <int M> static void set_smem_attr() {
-        set_pass_attr<M, RowsR2C<T, M>>();
+        set_pass_attr<M, RowsR2C<T, M, false>>();
+        set_pass_attr<M, RowsR2C<T, M, true>>();
         set_pass_attr<M, ColsPass<T, M, false, false>>();
         set_pass_attr<M, ColsPass<T, M, true, false>>();
         set_pass_attr<M, ColsPass<T, M, false, true>>();
@@ -170,9 +171,16 @@ template <typename T> struct OwnFft2d {
              bool transposed, const int2* pair_range = nullptr, long long n_pairs = 0) const {
         const FftShape s = shape(real_plane, spec_plane, batch, pair_range);
         const long long row_items = pair_range ? n_pairs : (long long)batch * s.npair;
+        // one TMA bulk copy per row pair when every pair is 16-byte aligned and a multiple of 16 bytes long
+        const bool aligned = sizeof(T) == 8 && real_plane % 2 == 0 && reinterpret_cast<uintptr_t>(in) % 16 == 0;
         SURFH_DISPATCH_M(axis_b->m, {
-            RowsR2C<T, MM> pass{in, z, s};
-            launch<MM>(pass, row_items, *axis_b, st);
+            if (aligned) {
+                RowsR2C<T, MM, true> pass{in, z, s};
+                launch<MM>(pass, row_items, *axis_b, st);
+            } else {
+                RowsR2C<T, MM, false> pass{in, z, s};
+                launch<MM>(pass, row_items, *axis_b, st);
+            }
         });
         SURFH_DISPATCH_M(axis_a.m, {
             if (transposed) {

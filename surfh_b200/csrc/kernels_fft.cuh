@@ -644,16 +644,25 @@ template <typename T, int M> struct RowItems {
 };
 
 // ---- R2C pass 1: pairs of real rows -> the two Hermitian half spectra, rows 2p and 2p+1 of Y (stored as Y^T)
-template <typename T, int M> struct RowsR2C {
+// ALIGNED: the caller guarantees that every row pair starts on a 16-byte boundary and spans a multiple of 16
+// bytes (the operator's working cube: fp64, plane stride padded to even) -> one TMA bulk copy per item; else
+// (caller-owned maps, fp32) every lane copies its own elements with cp.async.
+template <typename T, int M, bool ALIGNED> struct RowsR2C {
     using C = cplx_t<T>;
     using K = FftK<T, M>;
-    static constexpr bool BULK = false;   // real rows of odd length are not 16-byte aligned
+    static constexpr bool BULK = ALIGNED && K::BULK_OK;
     const T* in;
     C* y;
     FftShape s;
     __device__ long long items(const FftRanges& rg) const { return RowItems<T, M>::count(s, rg); }
     __device__ FftItem item(int it, const FftRanges& rg) const { return RowItems<T, M>::decode(it, s, rg); }
-    // staged as reals: row 2p at stage[n], row 2p+1 at stage[HALF + n]
+    // staged as reals: row 2p at stage[n], row 2p+1 at stage[nb + n] (the pair is contiguous in memory)
+    __device__ const C* bulk_src(const FftItem& it, const FftRanges&, int& first, int& count) const {
+        first = 0;
+        count = s.nb;   // in units of C = two reals: 2 nb reals (a plane's last, unpaired row drags nb stray reals
+                        // along: the buffer has a row of slack and `load` ignores them)
+        return reinterpret_cast<const C*>(in + (size_t)it.plane * s.real_plane + (size_t)(2 * it.idx) * s.nb);
+    }
     __device__ void prefetch(const FftItem& it, int lane, C* stage_c, const FftRanges&) const {
         T* stage = reinterpret_cast<T*>(stage_c);
         const int r0 = 2 * it.idx;
@@ -664,7 +673,7 @@ template <typename T, int M> struct RowsR2C {
             const int n = lane + 32 * m;
             if (n < s.nb) {
                 cp_async<sizeof(T)>(stage + n, ra + n);
-                if (has_b) cp_async<sizeof(T)>(stage + K::HALF + n, ra + s.nb + n);
+                if (has_b) cp_async<sizeof(T)>(stage + s.nb + n, ra + s.nb + n);
             }
         }
     }
@@ -677,7 +686,7 @@ template <typename T, int M> struct RowsR2C {
             C u = make_c<T>(T(0), T(0));
             if (n < s.nb) {
                 u.x = stage[n];
-                u.y = has_b ? stage[K::HALF + n] : T(0);
+                u.y = has_b ? stage[s.nb + n] : T(0);
                 u = cmul(u, chirp[n]);
             }
             v[m] = u;

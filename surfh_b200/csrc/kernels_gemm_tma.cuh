@@ -1,7 +1,7 @@
 // k4 / k4^T on TMA (fp64): the spectral response as plain "TN" matrix products whose operands are 2-D tensor maps.
 //
-//   forward   y[m, n']  = sum_k W [m, k]  * G [n', k]     m = detector wavelength l', k = (l, b), n' = (p, a, s)
-//   adjoint   Gt[n', k] = sum_m Wt[k, m]  * Yk[n', m]     Wt = W^T (a second copy, uploaded once), Yk = y permuted
+//   forward   y[m, n]  = sum_k W [m, k]  * G [n, k]     m = detector wavelength l', k = (l, b), n = (p, s, a)
+//   adjoint   Gt[n, k] = sum_m Wt[k, m]  * Yk[n, m]     Wt = W^T (a second copy, uploaded once), Yk = y permuted
 //
 // Replaces jax_utils.wblur_subSampling + the alpha decimation and jax_utils.wblur_t + np.repeat
 // (surfh/ToolsDir/jax_utils.py:72-91; surfh/Models/spectroModelChannel.py:229, 242-252), like kernels_gemm.cuh.
@@ -160,15 +160,15 @@ dgemm_tma_kernel(const __grid_constant__ GemmTmaBatch batch) {
     }
 }
 
-// Yk[n'][m] = y[((p*S + s)*nd + m)*na + a],  n' = (p*na + a)*S + s  (row pitch ldk >= nd): the detector block of a
-// band re-laid K-fast per detector column, the B operand of the adjoint product.
+// Yk[n][m] = y[(ps*nd + m)*na + a],  n = ps*na + a  (row pitch ldk >= nd): the detector block of a band re-laid
+// K-fast per detector column, the B operand of the adjoint product (per (p, s): an [nd][na] -> [na][nd] transpose).
 __global__ void __launch_bounds__(256)
-detector_to_kfast_kernel(const double* __restrict__ y, int S, int na, int nd, int Nn, int ldk, double* __restrict__ yk) {
+detector_to_kfast_kernel(const double* __restrict__ y, int na, int nd, int Nn, int ldk, double* __restrict__ yk) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)Nn * nd) return;
-    const int m = (int)(idx % nd), np = (int)(idx / nd);
-    const int s = np % S, pa = np / S, a = pa % na, p = pa / na;
-    yk[(size_t)np * ldk + m] = y[((size_t)(p * S + s) * nd + m) * na + a];
+    const int m = (int)(idx % nd), n = (int)(idx / nd);
+    const int a = n % na, ps = n / na;
+    yk[(size_t)n * ldk + m] = y[((size_t)ps * nd + m) * na + a];
 }
 
 }  // namespace surfh

@@ -32,11 +32,12 @@ template <typename T> struct SlitTables {
     const T* grid_frac;        // [P, A*B, 2]
     int32_t P, S, na, nb, srf, A, B;
     int32_t ncol;  // P*S*na*nb
-    // slit-space vector G: element (wavelength l, detector column n' = (p*na + a)*S + s, beta b) lives at
-    // n' * g_col + l * g_l + b.  Bands with a spectral response store it K-fast per detector column
-    // (g_col = Lambda_b * nb, g_l = nb: the contraction's operand is then a plain [n'][k = l*nb + b] matrix, a 2-D TMA
-    // tensor map); beta-sum bands keep [l][n'][b] (g_col = nb, g_l = ncol).
-    int32_t g_col, g_l;
+    // slit-space vector G: element (wavelength l, detector column n, beta b) lives at n * g_col + l * g_l + b.
+    // Bands with a spectral response store it K-fast per detector column, columns in the detector's own order
+    // n = (p*S + s)*na + a (g_col = Lambda_b * nb, g_l = nb, g_psa = 1): the contraction's operand is then a plain
+    // [n][k = l*nb + b] matrix, a 2-D TMA tensor map.  Beta-sum bands keep [l][n'][b] with n' = (p*na + a)*S + s
+    // (g_col = nb, g_l = ncol, g_psa = 0).
+    int32_t g_col, g_l, g_psa;
 };
 
 template <typename T, int LB>
@@ -62,7 +63,8 @@ slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube
     const int s = r % t.S;
     const int a = r / t.S;
   for (int p = warp % pp; p < t.P; p += pp) {
-    const size_t c = (size_t)((p * t.na + a) * t.S + s) * t.g_col + b;  // column n' = (p, a, s) of the slit space
+    const int n_col = t.g_psa ? (p * t.S + s) * t.na + a : (p * t.na + a) * t.S + s;
+    const size_t c = (size_t)n_col * t.g_col + b;
     const int j = t.slit_b0[s] + b;
     const int i_first = t.slit_a0[s] + a * t.srf;
     const int32_t* gb = t.grid_base + (size_t)p * t.A * t.B;
