@@ -558,6 +558,11 @@ def run_b200(args):
         for k in ("tflops", "frac_of_fp_peak", "limiter", "algorithmic_bytes_per_launch"):
             if k in top:
                 roofline[k] = top[k]
+        # every stage in one compact list, inside the object the driver keeps
+        roofline["stages"] = [{"stage": r["stage"], "ms": round(r["ms_per_step"], 4), "bound": r.get("bound"),
+                               "frac": None if r.get("frac") is None else round(r["frac"], 4),
+                               "frac_of_fp_peak": None if r.get("frac_of_fp_peak") is None else round(r["frac_of_fp_peak"], 4)}
+                              for r in stage_rows]
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

@@ -215,6 +215,16 @@ int surfh_pcg_update(surfh_handle h, int32_t phase, void* x, void* r, const void
 /* rho_z' = <r, z>; beta = rho_z'/rho_z (0 when first != 0); d = z + beta d */
 int surfh_pcg_direction(surfh_handle h, const void* r, const void* z, void* d, double* s, int32_t first, void* stream);
 
+/* ---- distortion-correction pre-processing -------------------------------------------------- */
+/* Exponential modified-Shepard interpolation of n_in irregular samples (alpha, lambda, value) onto n_out grid
+ * points (float32, [device] pointers): out = sum w v / sum w, w = exp(-alpha * d^p) for d <= pixel_cutoff,
+ * d = pixel distance + epsilon; 0 where no sample is within the cutoff.  Replaces
+ * surfh/ToolsDir/shepard_interpolation.pyx:77-141 (`exponential_modified_shepard`) as called by
+ * surfh/Preprocessing/distorsion_correction.py:55-98.  Errors via surfh_last_error(NULL). */
+int surfh_shepard(const float* alpha_coord, const float* lambda_coord, const float* values, int32_t n_in,
+                  const float* alpha_mesh, const float* lambda_mesh, int32_t n_out, float p, float alpha,
+                  float pixel_cutoff, float alpha_res, float lambda_res, float epsilon, float* out, void* stream);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* number of kernels (own + cuFFT exec calls) this handle has launched since creation */
 int64_t surfh_launch_count(surfh_handle h);

@@ -71,7 +71,58 @@ def prepare_scratch() -> str:
         subprocess.check_call([sys.executable, "setup_cy.py", "build_ext", "--inplace"], cwd=pkg, env=env,
                               stdout=subprocess.DEVNULL)
         open(os.path.join(pkg, "surfh", "ToolsDir", "BUILT"), "w").write("ok\n")
+    if not os.path.exists(os.path.join(pkg, "surfh", "ToolsDir", "BUILT_SHEPARD")):
+        setup = (
+            "from setuptools import setup, Extension\n"
+            "from Cython.Build import cythonize\nimport numpy\n"
+            "ext = Extension('surfh.ToolsDir.shepard_interpolation', ['surfh/ToolsDir/shepard_interpolation.pyx'],\n"
+            "    extra_compile_args=['-O2'], include_dirs=[numpy.get_include()])\n"
+            "setup(ext_modules=cythonize([ext], compiler_directives={'binding': True, 'language_level': 3}))\n"
+        )
+        open(os.path.join(pkg, "setup_shepard.py"), "w").write(setup)
+        env = dict(os.environ, CC="/usr/bin/gcc", LDSHARED="/usr/bin/gcc -shared")
+        subprocess.check_call([sys.executable, "setup_shepard.py", "build_ext", "--inplace"], cwd=pkg, env=env,
+                              stdout=subprocess.DEVNULL)
+        open(os.path.join(pkg, "surfh", "ToolsDir", "BUILT_SHEPARD"), "w").write("ok\n")
     return pkg
+
+
+def shepard_inputs(seed=3, n_lambda=64, n_alpha_det=26, na=19):
+    """One synthetic slit: detector samples on a sheared, slightly curved (alpha, lambda) lattice with a few
+    NaN-removed holes, to be interpolated onto the model's regular [n_lambda, na] grid (the geometry of
+    distorsion_correction.py:150-176: alpha_res, lambda_res from the grid extents, p = 2, alpha = 2, cutoff = 2)."""
+    rng = np.random.default_rng(seed)
+    ii, jj = np.meshgrid(np.arange(n_lambda * 2), np.arange(n_alpha_det), indexing="ij")
+    lam = 5.0 + 0.0004 * ii + 0.00003 * jj + 2e-7 * jj ** 2
+    alpha = -1.6 + 0.13 * jj + 0.0008 * ii + 0.01 * rng.standard_normal(ii.shape)
+    val = np.sin(3.0 * alpha) + 0.2 * np.cos(900.0 * (lam - 5.0)) + 0.05 * rng.standard_normal(ii.shape)
+    keep = rng.random(ii.shape) > 0.03
+    alpha, lam, val = alpha[keep], lam[keep], val[keep]
+    chan_wavelength = np.linspace(lam.min(), lam.max(), n_lambda)
+    grid_alpha = np.linspace(alpha.min(), alpha.max(), na)
+    alpha_mesh, lambda_mesh = np.meshgrid(grid_alpha, chan_wavelength)
+    alpha_res = (grid_alpha.max() - grid_alpha.min()) / alpha_mesh.shape[1]
+    lambda_res = (chan_wavelength.max() - chan_wavelength.min()) / lambda_mesh.shape[0]
+    return dict(alpha=alpha, lam=lam, val=val, alpha_mesh=alpha_mesh, lambda_mesh=lambda_mesh,
+                alpha_res=alpha_res, lambda_res=lambda_res)
+
+
+def run_shepard():
+    """The reference's compiled shepard_interpolation.pyx on the synthetic slit, through the same float32 casts
+    as perform_shepard_interpolation (distorsion_correction.py:89-94)."""
+    from surfh.ToolsDir import shepard_interpolation
+    d = shepard_inputs()
+    f = np.float32
+    out = {}
+    for tag, (p, a_exp, cut) in {"p2": (2, 2.0, 2), "p15": (1.5, 1.0, 3)}.items():
+        out[tag] = np.asarray(shepard_interpolation.exponential_modified_shepard(
+            d["alpha"].astype(f), d["lam"].astype(f), d["val"].astype(f), d["alpha_mesh"].astype(f),
+            d["lambda_mesh"].astype(f), p=p, alpha=a_exp, pixel_cutoff=cut, alpha_res=d["alpha_res"],
+            lambda_res=d["lambda_res"]))
+    path = os.path.join(GOLDEN, "shepard.npz")
+    np.savez_compressed(path, **out)
+    print(f"shepard: {out['p2'].shape} grid from {len(d['val'])} samples, |out|={np.linalg.norm(out['p2']):.6e} "
+          f"-> {os.path.getsize(path) / 1e3:.0f} kB")
 
 
 def _shell(name, **attrs):
@@ -297,6 +348,8 @@ def main(names=None):
     pkg = prepare_scratch()
     model_mod, ref_instru = import_reference(pkg)
     os.makedirs(GOLDEN, exist_ok=True)
+    if not names or "shepard" in names:
+        run_shepard()
     for name, cfg, l_idx in blind_cases():
         if names and name not in names:
             continue

@@ -28,7 +28,7 @@ SYMBOLS = [
     "surfh_abi_version", "surfh_create", "surfh_set_otf", "surfh_add_band", "surfh_finalize", "surfh_destroy",
     "surfh_last_error", "surfh_input_size", "surfh_output_size", "surfh_workspace_bytes", "surfh_forward",
     "surfh_adjoint", "surfh_fwadj", "surfh_maps_to_cube", "surfh_forward_host", "surfh_adjoint_host",
-    "surfh_cg_regularise_dot", "surfh_laplacian_axpby", "surfh_cg_start", "surfh_cg_update", "surfh_cg_refresh", "surfh_criterion_terms", "surfh_cg_dot_x_b_plus_r", "surfh_axpy_device_scalar", "surfh_precond_build", "surfh_precond_apply", "surfh_pcg_update", "surfh_pcg_direction",
+    "surfh_cg_regularise_dot", "surfh_laplacian_axpby", "surfh_cg_start", "surfh_cg_update", "surfh_cg_refresh", "surfh_criterion_terms", "surfh_cg_dot_x_b_plus_r", "surfh_axpy_device_scalar", "surfh_precond_build", "surfh_precond_apply", "surfh_pcg_update", "surfh_pcg_direction", "surfh_shepard",
     "surfh_launch_count", "surfh_own_launch_count", "surfh_profile_enable", "surfh_profile_read", "surfh_rfft2",
 ]
 
@@ -105,6 +105,8 @@ def load() -> C.CDLL:
         "surfh_precond_apply": (C.c_int, [vp, vp, vp, vp]),
         "surfh_pcg_update": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
         "surfh_pcg_direction": (C.c_int, [vp, vp, vp, vp, vp, i32, vp]),
+        "surfh_shepard": (C.c_int, [vp, vp, vp, i32, vp, vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.c_float, vp, vp]),
         "surfh_rfft2": (C.c_int, [i32, i32, i32, i32, i32, vp, vp, vp]),
         "surfh_launch_count": (i64, [vp]),
         "surfh_own_launch_count": (i64, [vp]),

@@ -26,6 +26,7 @@
 #include "kernels_gemm_tma.cuh"
 #include "kernels_lmm.cuh"
 #include "kernels_precond.cuh"
+#include "kernels_shepard.cuh"
 #include "kernels_slit.cuh"
 
 namespace surfh {
@@ -1486,6 +1487,27 @@ int surfh_rfft2(int32_t dtype, int32_t n_alpha, int32_t n_beta, int32_t batch, i
         if (dtype == SURFH_F64) return rfft2_impl<double>(n_alpha, n_beta, batch, inverse, in, out, (cudaStream_t)stream);
         if (dtype == SURFH_F32) return rfft2_impl<float>(n_alpha, n_beta, batch, inverse, in, out, (cudaStream_t)stream);
         throw Error(SURFH_EINVAL, "dtype must be SURFH_F32 or SURFH_F64");
+    } catch (const surfh::Error& e) {
+        g_create_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return SURFH_EINVAL;
+    }
+}
+
+int surfh_shepard(const float* alpha_coord, const float* lambda_coord, const float* values, int32_t n_in,
+                  const float* alpha_mesh, const float* lambda_mesh, int32_t n_out, float p, float alpha,
+                  float pixel_cutoff, float alpha_res, float lambda_res, float epsilon, float* out, void* stream) {
+    try {
+        if (n_in < 0 || n_out <= 0 || !alpha_mesh || !lambda_mesh || !out || (n_in > 0 && (!alpha_coord || !lambda_coord || !values)))
+            throw Error(SURFH_EINVAL, "surfh_shepard: bad size or NULL buffer");
+        if (!(alpha_res != 0.f) || !(lambda_res != 0.f)) throw Error(SURFH_EINVAL, "surfh_shepard: zero resolution");
+        shepard_kernel<<<ceil_div(n_out, 256), 256, 0, (cudaStream_t)stream>>>(
+            alpha_coord, lambda_coord, values, n_in, alpha_mesh, lambda_mesh, n_out, p, alpha, pixel_cutoff,
+            1.f / alpha_res, 1.f / lambda_res, epsilon, out);
+        SURFH_CUDA(cudaGetLastError());
+        return SURFH_OK;
     } catch (const surfh::Error& e) {
         g_create_error = e.what();
         return e.code;
