@@ -1,6 +1,3 @@
 set -x
-python -m pytest tests/test_gpu_fft.py tests/test_gpu_parity.py tests/test_blind.py -q -x -m gpu > gpurun_out/pytest_par.log 2>&1; tail -4 gpurun_out/pytest_par.log
-python bench.py --no-cpu-baseline --no-e2e --solve-iters 0 > gpurun_out/b_sym.json 2> gpurun_out/b_sym.err; tail -1 gpurun_out/b_sym.err
-SURFH_B200_LIB=$PWD/surfh_b200/libsurfh_nopipe.so python bench.py --no-cpu-baseline --no-e2e --solve-iters 0 > gpurun_out/b_nopipe.json 2> gpurun_out/b_nopipe.err; tail -1 gpurun_out/b_nopipe.err
-python bench.py --config c2 --no-cpu-baseline --no-e2e --solve-iters 0 > gpurun_out/b2_sym.json 2> gpurun_out/b2_sym.err; tail -1 gpurun_out/b2_sym.err
-python bench.py --dtype float32 --no-cpu-baseline --no-e2e --solve-iters 0 > gpurun_out/b_sym_f32.json 2> gpurun_out/b_sym_f32.err; tail -1 gpurun_out/b_sym_f32.err
+python -m pytest tests/test_distorsion_correction.py tests/test_gpu_fft.py -q -m gpu > gpurun_out/pytest_dc.log 2>&1; tail -4 gpurun_out/pytest_dc.log
+python bench.py --no-cpu-baseline --no-e2e --solve-iters 0 > gpurun_out/b_chk.json 2> gpurun_out/b_chk.err; tail -1 gpurun_out/b_chk.err
