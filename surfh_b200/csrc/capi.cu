@@ -127,6 +127,7 @@ namespace surfh {
 
 template <typename T> struct BandT {
     int P, S, na, nb, srf, A, B, l0, nl, nd, ncol, Nn, KB, mode, det_start;
+    int KBp = 0;  // KB rounded up to even: row pitch of the LSF and of G (TMA wants 16-byte multiples)
     int row_lo = 0, row_hi = 0;  // cube rows this band reads (gather) or writes (either adjoint table)
     int64_t footprint = 0;       // distinct cube pixels the bilinear taps of ALL pointings read (union)
     int64_t out_offset, out_size;
@@ -361,13 +362,14 @@ template <typename T> struct ModelImpl : surfh_model {
         b->Nn = b->P * b->S * b->na;
         b->ncol = b->Nn * b->nb;
         b->KB = b->nl * b->nb;
-        if (b->mode == SURFH_SPECTRAL_LSF) { b->g_col = b->KB; b->g_l = b->nb; b->g_psa = 1; }
+        b->KBp = (b->KB + 1) / 2 * 2;
+        if (b->mode == SURFH_SPECTRAL_LSF) { b->g_col = b->KBp; b->g_l = b->nb; b->g_psa = 1; }
         else { b->g_col = b->nb; b->g_l = b->ncol; b->g_psa = 0; }
         b->out_offset = d->out_offset;
         b->out_size = (int64_t)b->Nn * b->nd;
         SURFH_REQUIRE(d->out_offset >= 0, "negative out_offset");
         SURFH_REQUIRE(b->mode == SURFH_SPECTRAL_BETA_SUM ||
-                          ((int64_t)b->nd * b->KB < (1ll << 31) && (int64_t)b->nl * b->ncol < (1ll << 31) &&
+                          ((int64_t)b->nd * b->KBp < (1ll << 31) && (int64_t)b->Nn * b->KBp < (1ll << 31) &&
                            b->out_size < (1ll << 31)), "band too large for 32-bit operand offsets");
         const int AB = b->A * b->B;
         for (int s = 0; s < b->S; ++s) {
@@ -407,7 +409,12 @@ template <typename T> struct ModelImpl : surfh_model {
         upload_converted<int32_t>(b->slit_a0, d->slit_a0, b->S);
         upload_converted<int32_t>(b->slit_b0, d->slit_b0, b->S);
         upload_converted<T>(b->slit_w, d->slit_w, (size_t)b->S * b->nb);
-        if (b->mode == SURFH_SPECTRAL_LSF) upload_converted<T>(b->lsf, d->lsf, (size_t)b->nd * b->KB);
+        if (b->mode == SURFH_SPECTRAL_LSF) {   // rows at pitch KBp (the pad element, if any, is zero)
+            std::vector<double> w((size_t)b->nd * b->KBp, 0.0);
+            for (int m = 0; m < b->nd; ++m)
+                std::copy(d->lsf + (size_t)m * b->KB, d->lsf + (size_t)(m + 1) * b->KB, w.begin() + (size_t)m * b->KBp);
+            upload_converted<T>(b->lsf, w.data(), w.size());
+        }
         upload_converted<int32_t>(b->grid_base, d->grid_base, (size_t)b->P * AB);
         upload_converted<T>(b->grid_frac, d->grid_frac, (size_t)b->P * AB * 2);
         const surfh_csr* cs[2] = {&d->adj_exact, &d->adj_reference};
@@ -445,7 +452,7 @@ template <typename T> struct ModelImpl : surfh_model {
             for (int i = 0; i < nmax; ++i) v[i] = i;
             upload_converted<int32_t>(b->t_ident, v.data(), nmax);
             v.assign(b->nd, 0);
-            for (int i = 0; i < b->nd; ++i) v[i] = i * b->KB;
+            for (int i = 0; i < b->nd; ++i) v[i] = i * b->KBp;
             upload_converted<int32_t>(b->t_wrow, v.data(), b->nd);
             v.assign(b->KB, 0);
             for (int k = 0; k < b->KB; ++k) v[k] = (k / b->nb) * b->g_l + k % b->nb;   // = k in the K-fast layout
@@ -460,7 +467,10 @@ template <typename T> struct ModelImpl : surfh_model {
             for (int n = 0; n < b->Nn; ++n) v[n] = (n / b->na) * (b->nd * b->na) + n % b->na;
             upload_converted<int32_t>(b->t_yN, v.data(), b->Nn);
         }
-        b->G.alloc((size_t)b->nl * b->ncol * sizeof(T));
+        // K-fast layout: Nn rows at pitch g_col = KBp; beta-sum layout: nl planes of ncol
+        const size_t g_elems = b->mode == SURFH_SPECTRAL_LSF ? (size_t)b->Nn * b->KBp : (size_t)b->nl * b->ncol;
+        b->G.alloc(g_elems * sizeof(T));
+        SURFH_CUDA(cudaMemset(b->G.p, 0, b->G.bytes));   // the pad column is never written: keep it finite (zero)
         if (b->mode == SURFH_SPECTRAL_LSF && std::is_same<T, double>::value) {
             // operands and tables of the TMA contraction (kernels_gemm_tma.cuh)
             b->ndp = (b->nd + 1) / 2 * 2;
@@ -469,7 +479,7 @@ template <typename T> struct ModelImpl : surfh_model {
                 for (int k = 0; k < b->KB; ++k) wt[(size_t)k * b->ndp + m] = d->lsf[(size_t)m * b->KB + k];
             upload_converted<double>(b->lsf_t, wt.data(), wt.size());
             b->yk.alloc((size_t)b->Nn * b->ndp * sizeof(double));
-            b->map_w = tensor_map_2d_f64(b->lsf.p, b->KB, b->nd, (size_t)b->KB, kTBM);
+            b->map_w = tensor_map_2d_f64(b->lsf.p, b->KB, b->nd, (size_t)b->KBp, kTBM);
             b->map_g = tensor_map_2d_f64(b->G.p, b->KB, b->Nn, (size_t)b->g_col, kTBN);
             b->map_wt = tensor_map_2d_f64(b->lsf_t.p, b->nd, b->KB, (size_t)b->ndp, kTBM);
             b->map_yk = tensor_map_2d_f64(b->yk.p, b->nd, b->Nn, (size_t)b->ndp, kTBN);

@@ -158,6 +158,12 @@ class BandExchange:
                 self.plan.append((int(blocks[b][0]), int(blocks[b][1]), groups[key] if groups[key] is not None
                                   else comm.group))
 
+    def owned_blocks(self):
+        """(offset, size) of the detector blocks this rank accounts for in a sum over all bands: every band is
+        owned by the lowest rank that holds a share of it -- after `reduce_shared` that rank's block is complete."""
+        return [(int(off), int(size)) for (off, size), ranks in zip(self.blocks, self.rank_sets)
+                if ranks and ranks[0] == self.comm.rank]
+
     def reduce_shared(self, y):
         """In place: y[block of b] = sum over the ranks sharing band b, for the bands of this rank."""
         dist = self.comm.dist

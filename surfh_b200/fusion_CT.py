@@ -150,6 +150,9 @@ class DeviceCG:
         self.hx = self.hd = None
         self.precond = None     # FourierPreconditioner: preconditioned CG (qmm.lcg's precond= argument)
         self.z = None
+        # sharded model: H d is the model's exchanged detector vector; this rank tracks H x_k on the blocks it owns
+        self._sharded_track = False
+        self._blocks = None
 
     def _to_dev(self, a):
         torch = _torch()
@@ -172,7 +175,7 @@ class DeviceCG:
     def hessp(self, v, out):
         """out = mu_s H^T H v + mu_r R v ; s[1] = <v, out>, with R = L ('separated': D_r^T D_r + D_c^T D_c)
         or R = L L ('joint')."""
-        self.model.fwadj_into(v, out, y_scratch=self.hd)
+        self.model.fwadj_into(v, out, y_scratch=None if self._sharded_track else self.hd)
         if self.gradient == "separated":
             self._check(self.lib.surfh_cg_regularise_dot(self.h, v.data_ptr(), out.data_ptr(), self.mu_s, self.mu_r,
                                                          self.s.data_ptr(), self._stream()))
@@ -195,9 +198,17 @@ class DeviceCG:
         self.r = torch.empty_like(self.b)
         self.d = torch.empty_like(self.b)
         self.hx = self.hd = None
-        if self.track_hx and not getattr(self.model, "partial", False):
+        self._sharded_track, self._blocks = False, None
+        partial = getattr(self.model, "partial", False)
+        if self.track_hx and not partial:
             self.hd = torch.empty(self.model.osize, dtype=self.tdtype, device=self.dev)
         self.hessp(self.x, self.q)
+        if self.track_hx and partial and self.model.lambda_range is not None and self.comm is not None:
+            # wavelength shards: after the band exchange the model's detector vector holds the complete H v on
+            # the blocks of the bands this rank touches; the rank owning a band tracks H x_k on that block
+            self._sharded_track = True
+            self.hd = self.model._y_shard
+            self._blocks = self.model._band_exchange().owned_blocks()
         if self.hd is not None:
             self.hx = self.hd.clone()                     # H x_0
         self._check(self.lib.surfh_cg_start(self.h, self.b.data_ptr(), self.q.data_ptr(), self.r.data_ptr(),
@@ -208,6 +219,16 @@ class DeviceCG:
             self._check(self.lib.surfh_pcg_direction(self.h, self.r.data_ptr(), self.z.data_ptr(), self.d.data_ptr(),
                                                      self.s.data_ptr(), 1, self._stream()))
         self.iteration = 0
+
+    def _advance_hx(self):
+        if self.hx is None:
+            return
+        item = self.hx.element_size()
+        blocks = self._blocks if self._sharded_track else [(0, self.hx.numel())]
+        for off, size in blocks:
+            self._check(self.lib.surfh_axpy_device_scalar(self.h, self.hx.data_ptr() + off * item,
+                                                          self.hd.data_ptr() + off * item, size, self.s.data_ptr(), 2,
+                                                          self._stream()))
 
     def _pcg_step(self, refresh: bool):
         """One preconditioned iteration: alpha = <r,z>/<d,Qd>; x, r updates; z = P r; beta = <r,z>'/<r,z>;
@@ -225,9 +246,7 @@ class DeviceCG:
         else:
             self._check(lib.surfh_pcg_update(self.h, 0, self.x.data_ptr(), self.r.data_ptr(), self.d.data_ptr(),
                                              self.q.data_ptr(), None, self.s.data_ptr(), st))
-            if self.hx is not None:
-                self._check(lib.surfh_axpy_device_scalar(self.h, self.hx.data_ptr(), self.hd.data_ptr(),
-                                                         self.hx.numel(), self.s.data_ptr(), 2, st))
+            self._advance_hx()
         self.precond.apply(self.r, self.z)
         self._check(lib.surfh_pcg_direction(self.h, self.r.data_ptr(), self.z.data_ptr(), self.d.data_ptr(),
                                             self.s.data_ptr(), 0, st))
@@ -249,9 +268,7 @@ class DeviceCG:
         else:
             self._check(self.lib.surfh_cg_update(self.h, self.x.data_ptr(), self.r.data_ptr(), self.d.data_ptr(),
                                                  self.q.data_ptr(), self.s.data_ptr(), self._stream()))
-            if self.hx is not None:                       # H x_{k+1} = H x_k + alpha H d   (s[2] = alpha)
-                self._check(self.lib.surfh_axpy_device_scalar(self.h, self.hx.data_ptr(), self.hd.data_ptr(),
-                                                              self.hx.numel(), self.s.data_ptr(), 2, self._stream()))
+            self._advance_hx()                            # H x_{k+1} = H x_k + alpha H d   (s[2] = alpha)
         self.iteration += 1
 
     def grad_norm_history(self):
@@ -281,6 +298,8 @@ class DeviceCG:
         if not self.state_criterion_available():
             raise ValueError("criterion_from_state needs track_hx or an exact-adjoint model")
         self._state_evals += 1
+        if self.hx is not None and self._sharded_track:
+            return self._criterion_sharded()
         if self.hx is not None:
             return self._criterion_given_hx(self.x, self.hx)
         if self._y_sq is None:
@@ -289,6 +308,25 @@ class DeviceCG:
         self._check(self.lib.surfh_cg_dot_x_b_plus_r(self.h, self.x.data_ptr(), self.b.data_ptr(), self.r.data_ptr(),
                                                      out.data_ptr(), self._stream()))
         return 0.5 * self.mu_s * self._y_sq - 0.5 * float(out.item())
+
+    def _criterion_sharded(self) -> float:
+        """Data term summed over the detector blocks this rank owns, all-reduced (one double); the prior is
+        evaluated redundantly on the identical maps."""
+        torch = _torch()
+        item = self.hx.element_size()
+        data = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        out = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        for off, size in self._blocks:
+            self._check(self.lib.surfh_criterion_terms(self.h, self.y.data_ptr() + off * item, self.hx.data_ptr() + off * item,
+                                                       size, None, out.data_ptr(), self._stream()))
+            data += out[:1]
+        self.comm.allreduce_sum(data)
+        self._check(self.lib.surfh_criterion_terms(self.h, None, None, 0, self.x.data_ptr(), out.data_ptr(), self._stream()))
+        prior = out[1]
+        if self.gradient == "joint":
+            lx = self.laplacian(self.x, torch.empty_like(self.x))
+            prior = torch.dot(lx.double(), lx.double())
+        return float((self.mu_s * data[0] + self.mu_r * prior).item() / 2)
 
     def _criterion_given_hx(self, x, hx) -> float:
         torch = _torch()

@@ -48,6 +48,20 @@ def check_mini(torch, comm, dev, bench):
           f"crit {abs(j_s - j_f) / abs(j_f):.2e} crit(state) {abs(j_state - j_f) / abs(j_f):.2e}", flush=True)
     assert e_f < 1e-12 and e_q < 1e-12 and e_x < 1e-9 and abs(j_s - j_f) < 1e-10 * abs(j_f)
     assert abs(j_state - j_f) < 1e-10 * abs(j_f)
+    # the reference driver's call on a sharded model, reference adjoint: the criterion trace comes from H x_k
+    # tracked on the detector blocks each rank owns (one scalar all-reduce), no forward pass
+    sh_ref = spectroSigRLSCT(**args, adjoint_mode="reference", lambda_range=lam, comm=comm)
+    fu_ref = spectroSigRLSCT(**args, adjoint_mode="reference")
+    qs = fusion_CT.QuadCriterion_MRS(1, y, sh_ref, 5.0)
+    qf = fusion_CT.QuadCriterion_MRS(1, y, fu_ref, 5.0)
+    rs = qs.run_method("lcg", 12, perf_crit=1, calc_crit=True, value_init=0)
+    rf = qf.run_method("lcg", 12, perf_crit=1, calc_crit=True, value_init=0)
+    e_c = max(abs(a - b) / abs(b) for a, b in zip(qs.L_crit_val, qf.L_crit_val))
+    print(f"[mini] rank {comm.rank}: run_method criterion trace sharded vs unsharded {e_c:.2e} "
+          f"({qs._solver()._state_evals} of {len(qs.L_crit_val)} from the CG state)", flush=True)
+    assert len(qs.L_crit_val) == len(qf.L_crit_val) == 3 and e_c < 1e-10
+    assert qs._solver()._state_evals == len(qs.L_crit_val)
+    assert float(np.linalg.norm(rs.x - rf.x) / np.linalg.norm(rf.x)) < 1e-9
     # an unsharded model with a comm must not sum W identical copies
     dup = spectroSigRLSCT(**args, adjoint_mode="exact", comm=comm)
     assert rel(dup.fwadj(x), full.fwadj(x)) < 1e-14 and rel(dup.forward(x), full.forward(x)) < 1e-14

@@ -141,3 +141,25 @@ def test_device_tensors_and_fwadj(built):
     # deterministic: bitwise-identical across runs (no atomics anywhere on the path)
     assert torch.equal(q, gpu.fwadj(x))
     assert torch.equal(gpu.adjoint(y), gpu.adjoint(y))
+
+
+def test_wavelength_shards_sum_to_the_full_operator(built):
+    """Two wavelength shards built in ONE process (no communicator): their partial forwards / adjoints add up to the
+    unsharded operator's.  The cuts are chosen so that a band's local window has an odd number of wavelengths and
+    an odd beta width: the K-fast slit-space rows then need their padded (even) pitch for the TMA tensor maps."""
+    import torch
+    cfg = CASES["mini_2band_4p"]()
+    args = cfg.model_args()
+    n_l = len(cfg.wavelength_axis)
+    full = built(**args, adjoint_mode="exact")
+    x = torch.as_tensor(cfg.maps, device="cuda")
+    v = torch.as_tensor(np.random.default_rng(2).standard_normal(full.osize), device="cuda")
+    y_full, a_full = full.forward(x), full.adjoint(v)
+    for cut in (n_l // 2, n_l // 2 + 1, 7):
+        lo = built(**args, adjoint_mode="exact", lambda_range=(0, cut))
+        hi = built(**args, adjoint_mode="exact", lambda_range=(cut, n_l))
+        assert lo.partial and hi.partial
+        assert rel((lo.forward(x) + hi.forward(x)).cpu().numpy(), y_full.cpu().numpy()) <= 1e-13
+        assert rel((lo.adjoint(v) + hi.adjoint(v)).cpu().numpy(), a_full.cpu().numpy()) <= 1e-13
+        with pytest.raises(ValueError, match="needs comm"):
+            lo.fwadj(x)
