@@ -612,9 +612,9 @@ template <typename T> struct ModelImpl : surfh_model {
         int64_t t = otf.bytes + tpl.bytes + tpl_raw.bytes + xhat.bytes + spec.bytes + cubebuf.bytes + fft_work.bytes + zbuf.bytes +
                     y_internal.bytes + x_stage.bytes + y_stage.bytes + dbl_stage.bytes;
         for (auto& b : bands)
-            t += b->lsf.bytes + b->G.bytes + b->grid_base.bytes + b->grid_frac.bytes + b->csr_col[0].bytes +
-                 b->csr_val[0].bytes + b->csr_col[1].bytes + b->csr_val[1].bytes;
-        return t;
+            t += b->lsf.bytes + b->lsf_t.bytes + b->yk.bytes + b->G.bytes + b->grid_base.bytes + b->grid_frac.bytes +
+                 b->csr_col[0].bytes + b->csr_val[0].bytes + b->csr_col[1].bytes + b->csr_val[1].bytes;
+        return t + precond_inv.bytes;
     }
 
     // ---- launch helpers ---------------------------------------------------------------------
@@ -682,7 +682,7 @@ template <typename T> struct ModelImpl : surfh_model {
             }
             if (kind == 0)
                 ownfft.r2c(reinterpret_cast<const T*>(in), real_stride, reinterpret_cast<C*>(out), nfp, zbuf.as<C>(), batch, st,
-                           true, pr, n_pairs);
+                           true, pr, n_pairs, /*row_slack=*/in == cubebuf.p);
             else
                 ownfft.c2r(reinterpret_cast<const C*>(in), nfp, reinterpret_cast<T*>(out), real_stride, zbuf.as<C>(), batch, st,
                            true, pr, n_pairs);

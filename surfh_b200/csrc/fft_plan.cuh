@@ -167,12 +167,15 @@ template <typename T> struct OwnFft2d {
     // `transposed`; z: scratch.
     // pair_range: [device] per-plane (first row pair, count) outside of which the input rows are zero, or NULL;
     // n_pairs: sum of the counts (host copy), ignored without pair_range
+    // row_slack: the caller's real buffer has at least one row of readable slack after its last plane (the
+    //             operator's working cube), so an unpaired last row may be staged as a full pair
     void r2c(const T* in, size_t real_plane, C* spec, size_t spec_plane, C* z, int batch, cudaStream_t st,
-             bool transposed, const int2* pair_range = nullptr, long long n_pairs = 0) const {
+             bool transposed, const int2* pair_range = nullptr, long long n_pairs = 0, bool row_slack = false) const {
         const FftShape s = shape(real_plane, spec_plane, batch, pair_range);
         const long long row_items = pair_range ? n_pairs : (long long)batch * s.npair;
         // one TMA bulk copy per row pair when every pair is 16-byte aligned and a multiple of 16 bytes long
-        const bool aligned = sizeof(T) == 8 && real_plane % 2 == 0 && reinterpret_cast<uintptr_t>(in) % 16 == 0;
+        const bool aligned = sizeof(T) == 8 && real_plane % 2 == 0 && reinterpret_cast<uintptr_t>(in) % 16 == 0 &&
+                             (na % 2 == 0 || row_slack);
         SURFH_DISPATCH_M(axis_b->m, {
             if (aligned) {
                 RowsR2C<T, MM, true> pass{in, z, s};
