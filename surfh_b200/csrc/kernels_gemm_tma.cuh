@@ -29,7 +29,10 @@
 
 namespace surfh {
 
-constexpr int kTBM = 128, kTBN = 64, kTBK = 16, kTStages = 4;
+#ifndef SURFH_GEMM_STAGES
+#define SURFH_GEMM_STAGES 4
+#endif
+constexpr int kTBM = 128, kTBN = 64, kTBK = 16, kTStages = SURFH_GEMM_STAGES;
 constexpr int kTConsumerWarps = 8;
 constexpr int kTThreads = 32 * kTConsumerWarps;
 constexpr int kTStageBytes = (kTBM + kTBN) * kTBK * 8;   // 24 KB

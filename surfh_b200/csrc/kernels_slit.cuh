@@ -22,8 +22,8 @@
 #pragma once
 #include "common.cuh"
 
-#ifndef SURFH_GATHER_PIPELINE
-#define SURFH_GATHER_PIPELINE 0   // measured on C4: 3.11 ms pipelined vs 3.07 ms plain -- kept for the record
+#ifndef SURFH_GATHER_MERGE
+#define SURFH_GATHER_MERGE 1
 #endif
 
 namespace surfh {
@@ -77,42 +77,45 @@ slit_gather_kernel(const T* __restrict__ cube, size_t plane /* elements per cube
 #pragma unroll
     for (int u = 0; u < LB; ++u) acc[u] = T(0);
     const T* base_l = cube + (size_t)l0 * plane;
-#if SURFH_GATHER_PIPELINE
-    // software pipeline over the srf rows of the box-sum: the table entry (tap offset, two fractions) of row m + 1
-    // is in flight while the 4 x LB taps of row m are loaded -- the two dependent round trips of an iteration
-    // (table -> taps) overlap instead of adding up
-    auto table_index = [&](int m) {
-        int i = i_first + m;
-        i = i >= t.A ? i - t.A : i;  // circular wrap of the FFT box-sum
-        return i * t.B + j;
-    };
-    int q = table_index(0);
-    int32_t off = __ldg(gb + q);
-    T y0 = __ldg(gf + 2 * q), y1 = __ldg(gf + 2 * q + 1);
-    for (int m = 0; m < t.srf; ++m) {
-        const int32_t off_c = off;
-        const T y0c = y0, y1c = y1;
-        if (m + 1 < t.srf) {
-            q = table_index(m + 1);
-            off = __ldg(gb + q);
-            y0 = __ldg(gf + 2 * q);
-            y1 = __ldg(gf + 2 * q + 1);
-        }
-        const T w00 = (T(1) - y0c) * (T(1) - y1c), w01 = (T(1) - y0c) * y1c;
-        const T w10 = y0c * (T(1) - y1c), w11 = y0c * y1c;
+#if SURFH_GATHER_MERGE
+    // The srf bilinear samples of the box-sum walk down (almost) one cube column: the lower row of sample m is the
+    // upper row of sample m + 1 (the rotated local row step is 0.99 pixel), usually in the same two columns.  The
+    // lower-row weights are therefore carried to the next sample and merged with its upper-row weights: 2 loads per
+    // sample and plane (+ 2 to flush) instead of 4 -- 16 instead of 28 for srf = 7.  Whenever the carried pair does
+    // not sit where the next sample's upper row is (the column index stepped, or the row index did not), it is
+    // flushed on its own: every case stays exact, only the order of the additions differs from 4 taps per sample.
+    auto emit = [&](int32_t o, T w0, T w1) {
 #pragma unroll
         for (int u = 0; u < LB; ++u) {
             if (l0 + u < n_l) {
-                const T* pl = base_l + (size_t)u * plane + off_c;
-                T v = __ldg(pl) * w00;
-                v = fma(__ldg(pl + 1), w01, v);
-                v = fma(__ldg(pl + n_beta), w10, v);
-                v = fma(__ldg(pl + n_beta + 1), w11, v);
-                acc[u] += v;
+                const T* pl = base_l + (size_t)u * plane + o;
+                acc[u] = fma(__ldg(pl), w0, acc[u]);
+                acc[u] = fma(__ldg(pl + 1), w1, acc[u]);
             }
         }
+    };
+    int32_t poff = -1;
+    T p0 = T(0), p1 = T(0);
+    for (int m = 0; m < t.srf; ++m) {
+        int i = i_first + m;
+        i = i >= t.A ? i - t.A : i;  // circular wrap of the FFT box-sum
+        const int q = i * t.B + j;
+        const int32_t off = __ldg(gb + q);
+        const T y0 = __ldg(gf + 2 * q), y1 = __ldg(gf + 2 * q + 1);
+        T u0 = (T(1) - y0) * (T(1) - y1), u1 = (T(1) - y0) * y1;
+        if (poff == off) {
+            u0 += p0;
+            u1 += p1;
+        } else if (poff >= 0) {
+            emit(poff, p0, p1);
+        }
+        emit(off, u0, u1);
+        poff = off + n_beta;
+        p0 = y0 * (T(1) - y1);
+        p1 = y0 * y1;
     }
-#else
+    emit(poff, p0, p1);
+#else   // 4 taps per sample (round 1; a software-pipelined table read was measured: 3.11 vs 3.07 ms, removed)
     for (int m = 0; m < t.srf; ++m) {
         int i = i_first + m;
         i = i >= t.A ? i - t.A : i;  // circular wrap of the FFT box-sum
