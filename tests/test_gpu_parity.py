@@ -163,3 +163,18 @@ def test_wavelength_shards_sum_to_the_full_operator(built):
         assert rel((lo.adjoint(v) + hi.adjoint(v)).cpu().numpy(), a_full.cpu().numpy()) <= 1e-13
         with pytest.raises(ValueError, match="needs comm"):
             lo.fwadj(x)
+
+
+def test_partial_handle_host_forward_after_adjoint_has_zero_foreign_blocks(built):
+    """A handle that owns only some bands shares one host staging buffer between `adjoint` (input) and `forward`
+    (output): the blocks of the bands it does not own must read as zeros whatever was staged before
+    (round-1 ADVICE: they used to return the previous adjoint's input)."""
+    cfg = CASES["mini_2band_4p"]()
+    full = built(**cfg.model_args())
+    part = built(**cfg.model_args(), local_bands=[0])
+    v = np.random.default_rng(6).standard_normal(full.osize) + 3.0
+    part.adjoint(v)                       # stages v, non-zero everywhere
+    y = part.forward(cfg.maps)
+    cut = int(full._idx[1])
+    assert np.all(y[cut:] == 0.0)
+    assert rel(y[:cut], full.forward(cfg.maps)[:cut]) <= 1e-13
