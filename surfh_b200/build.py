@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libsurfh_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["common.cuh", "host_util.cuh", "fft_plan.cuh", "kernels_fft.cuh", "kernels_lmm.cuh", "kernels_slit.cuh", "kernels_gemm.cuh", "kernels_cg.cuh",
+HEADERS = ["common.cuh", "host_util.cuh", "fft_plan.cuh", "kernels_fft.cuh", "kernels_lmm.cuh", "kernels_slit.cuh", "kernels_gemm.cuh", "kernels_gemm_tma.cuh", "kernels_ozaki.cuh", "kernels_precond.cuh", "kernels_shepard.cuh", "kernels_cg.cuh",
            os.path.join("..", "..", "include", "surfh_b200.h")]
 
 

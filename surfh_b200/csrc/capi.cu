@@ -24,6 +24,7 @@
 #include "kernels_cg.cuh"
 #include "kernels_gemm.cuh"
 #include "kernels_gemm_tma.cuh"
+#include "kernels_ozaki.cuh"
 #include "kernels_lmm.cuh"
 #include "kernels_precond.cuh"
 #include "kernels_shepard.cuh"
@@ -141,6 +142,12 @@ template <typename T> struct BandT {
     int ndp = 0;                       // nd rounded up to even: row pitch of lsf_t / yk (16-byte multiple)
     CUtensorMap map_w, map_g, map_wt, map_yk;
     bool tma_ready = false;
+    // int8-sliced tcgen05 contraction (kernels_ozaki.cuh): digit planes [S][rows][pitch] + per-row scales of the LSF
+    // and its transpose (cut once), of the slit-space vector G and of the K-fast detector block (cut per call)
+    DevBuf oz_w, oz_wt, oz_g, oz_yk, oz_sw, oz_swt, oz_sg, oz_syk;
+    int oz_kq = 0, oz_ndq = 0;          // digit row pitches: KB / nd rounded up to 16 bytes
+    CUtensorMap ozmap_w, ozmap_g, ozmap_wt, ozmap_yk;
+    bool oz_ready = false;
     DevBuf G;  // [nl][ncol] slit-space vector (forward G / adjoint Gt), columns in INTERNAL order
     // The ABI (and the detector) order slit-space columns as ((p*S + s)*na + a)*nb + b; internally they are
     // stored as ((p*na + a)*S + s)*nb + b, so that the 32 consecutive cube pixels a warp of the scatter owns
@@ -234,6 +241,40 @@ static CUtensorMap tensor_map_2d_f64(const void* base, int inner, int rows, size
     if (r != CUDA_SUCCESS) throw Error(SURFH_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return m;
 }
+
+// int8 digit planes [S][rows][pitch] -> boxes of box_rows x 64 bytes of one digit, 64-byte swizzle, zero fill
+static CUtensorMap tensor_map_digits(const void* base, int inner, int rows, int pitch, int digits, int box_rows) {
+    CUtensorMap m;
+    const cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)digits};
+    const cuuint64_t gstride[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * (cuuint64_t)rows};
+    const cuuint32_t box[3] = {(cuuint32_t)kOzBK, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstride, box,
+                                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(SURFH_ECUDA, "cuTensorMapEncodeTiled (digits) failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+// How the fp64 operator evaluates the spectral response (SURFH_F64_GEMM): "ozaki" (default) = int8-sliced product on
+// tcgen05 (kernels_ozaki.cuh) with SURFH_OZAKI_DIGITS = 6, 7 or 8 (default) digits; "tma" = DMMA fed by TMA
+// (kernels_gemm_tma.cuh); "mma" = round 1's offset-table DMMA kernel.
+enum { F64_GEMM_MMA = 0, F64_GEMM_TMA = 1, F64_GEMM_OZAKI = 2 };
+static int f64_gemm_mode_env() {
+    const char* e = std::getenv("SURFH_F64_GEMM");
+    if (!e || !*e || std::strcmp(e, "ozaki") == 0) return F64_GEMM_OZAKI;
+    if (std::strcmp(e, "tma") == 0 || std::strcmp(e, "dmma") == 0) return F64_GEMM_TMA;
+    if (std::strcmp(e, "mma") == 0) return F64_GEMM_MMA;
+    throw Error(SURFH_EINVAL, std::string("SURFH_F64_GEMM must be ozaki, tma or mma, not ") + e);
+}
+static int ozaki_digits_env() {
+    const char* e = std::getenv("SURFH_OZAKI_DIGITS");
+    if (!e || !*e) return 8;
+    const int d = std::atoi(e);
+    if (d < 6 || d > 8) throw Error(SURFH_EINVAL, "SURFH_OZAKI_DIGITS must be 6, 7 or 8");
+    return d;
+}
+constexpr int kOzCluster = 2;   // CTAs per cluster of the sliced contraction (A digit tiles multicast)
 
 template <typename T> struct ModelImpl : surfh_model {
     using C = cplx_t<T>;
@@ -484,6 +525,7 @@ template <typename T> struct ModelImpl : surfh_model {
             b->map_wt = tensor_map_2d_f64(b->lsf_t.p, b->nd, b->KB, (size_t)b->ndp, kTBM);
             b->map_yk = tensor_map_2d_f64(b->yk.p, b->nd, b->Nn, (size_t)b->ndp, kTBN);
             b->tma_ready = true;
+            if (f64_gemm_mode == F64_GEMM_OZAKI) prepare_ozaki(*b);
         }
         bands.push_back(std::move(b));
     }
@@ -590,8 +632,8 @@ template <typename T> struct ModelImpl : surfh_model {
             SURFH_CUDA(cudaFuncSetAttribute(sgemm_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)sgemm_smem_bytes<false, false>()));
         }
-        if (const char* e = std::getenv("SURFH_F64_GEMM")) f64_tma_gemm = std::strcmp(e, "mma") != 0;
         if (std::is_same<T, double>::value) {
+            set_ozaki_attributes();
             SURFH_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmemBytes));
             SURFH_CUDA(cudaFuncSetAttribute(dgemm_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)dgemm_smem_bytes<true, true>()));
@@ -613,6 +655,7 @@ template <typename T> struct ModelImpl : surfh_model {
                     y_internal.bytes + x_stage.bytes + y_stage.bytes + dbl_stage.bytes;
         for (auto& b : bands)
             t += b->lsf.bytes + b->lsf_t.bytes + b->yk.bytes + b->G.bytes + b->grid_base.bytes + b->grid_frac.bytes +
+                 b->oz_w.bytes + b->oz_wt.bytes + b->oz_g.bytes + b->oz_yk.bytes +
                  b->csr_col[0].bytes + b->csr_val[0].bytes + b->csr_col[1].bytes + b->csr_val[1].bytes;
         return t + precond_inv.bytes;
     }
@@ -733,8 +776,13 @@ template <typename T> struct ModelImpl : surfh_model {
     // FP32 tensor path (3xTF32 split), same grouping; SURFH_F32_GEMM=simt selects the FFMA kernel
     void gemm_grouped_f32(float* y, bool adjoint, cudaStream_t st);
     bool f32_tensor_gemm = true;
-    bool f64_tma_gemm = true;   // SURFH_F64_GEMM=mma selects the round-1 offset-table DMMA kernel (A/B runs)
+    int f64_gemm_mode = f64_gemm_mode_env();   // read once per handle, before the bands are added
+    int ozaki_digits = ozaki_digits_env();
     void gemm_grouped_f64_tma(double* y, bool adjoint, cudaStream_t st);
+    void prepare_ozaki(BandT<T>& b);
+    void set_ozaki_attributes();
+    void gemm_grouped_f64_ozaki(double* y, bool adjoint, cudaStream_t st);
+    template <int S> void ozaki_run(double* y, bool adjoint, cudaStream_t st);
 
     void beta_sum(BandT<T>& b, T* y, bool adjoint, cudaStream_t st) {
         const size_t n = (size_t)b.nl * b.Nn * (adjoint ? b.nb : 1);
@@ -1244,8 +1292,140 @@ template <> void ModelImpl<double>::gemm_grouped_f64_tma(double* y, bool adjoint
     }
 }
 
+// ---- the sliced contraction on tcgen05 (kernels_ozaki.cuh) ----------------------------------------------------
+template <typename T> void ModelImpl<T>::prepare_ozaki(BandT<T>&) {}
+template <typename T> void ModelImpl<T>::set_ozaki_attributes() {}
+template <typename T> void ModelImpl<T>::gemm_grouped_f64_ozaki(double*, bool, cudaStream_t) {
+    throw Error(SURFH_ESTATE, "internal: fp64 contraction on an fp32 model");
+}
+
+template <int S> static void ozaki_slice(const double* x, int rows, int k, size_t ld, DevBuf& digits, int pitch, DevBuf& scale,
+                                         cudaStream_t st) {
+    ozaki_slice_rows_kernel<S><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, k, ld, digits.as<int8_t>(), pitch, scale.as<double>());
+}
+static void ozaki_slice_n(int S, const double* x, int rows, int k, size_t ld, DevBuf& digits, int pitch, DevBuf& scale,
+                          cudaStream_t st) {
+    if (S == 6) ozaki_slice<6>(x, rows, k, ld, digits, pitch, scale, st);
+    else if (S == 7) ozaki_slice<7>(x, rows, k, ld, digits, pitch, scale, st);
+    else ozaki_slice<8>(x, rows, k, ld, digits, pitch, scale, st);
+    SURFH_CUDA(cudaGetLastError());
+}
+
+template <> void ModelImpl<double>::prepare_ozaki(BandT<double>& b) {
+    const int S = ozaki_digits;
+    // every level sum_{p+q=t} sum_k dA dB must fit an int32: (t + 1) K 64^2 < 2^31
+    if ((int64_t)S * std::max(b.KB, b.nd) * 4096 >= ((int64_t)1 << 31)) return;   // this band keeps the DMMA kernel
+    b.oz_kq = (b.KB + 15) / 16 * 16;
+    b.oz_ndq = (b.nd + 15) / 16 * 16;
+    b.oz_w.alloc((size_t)S * b.nd * b.oz_kq);
+    b.oz_wt.alloc((size_t)S * b.KB * b.oz_ndq);
+    b.oz_g.alloc((size_t)S * b.Nn * b.oz_kq);
+    b.oz_yk.alloc((size_t)S * b.Nn * b.oz_ndq);
+    b.oz_sw.alloc((size_t)b.nd * sizeof(double));
+    b.oz_swt.alloc((size_t)b.KB * sizeof(double));
+    b.oz_sg.alloc((size_t)b.Nn * sizeof(double));
+    b.oz_syk.alloc((size_t)b.Nn * sizeof(double));
+    // the LSF and its transpose are constant: cut them into digits once
+    ozaki_slice_n(S, b.lsf.as<double>(), b.nd, b.KB, (size_t)b.KBp, b.oz_w, b.oz_kq, b.oz_sw, 0);
+    ozaki_slice_n(S, b.lsf_t.as<double>(), b.KB, b.nd, (size_t)b.ndp, b.oz_wt, b.oz_ndq, b.oz_swt, 0);
+    SURFH_CUDA(cudaDeviceSynchronize());
+    b.ozmap_w = tensor_map_digits(b.oz_w.p, b.KB, b.nd, b.oz_kq, S, kOzBM / kOzCluster);
+    b.ozmap_g = tensor_map_digits(b.oz_g.p, b.KB, b.Nn, b.oz_kq, S, kOzBN);
+    b.ozmap_wt = tensor_map_digits(b.oz_wt.p, b.nd, b.KB, b.oz_ndq, S, kOzBM / kOzCluster);
+    b.ozmap_yk = tensor_map_digits(b.oz_yk.p, b.nd, b.Nn, b.oz_ndq, S, kOzBN);
+    b.oz_ready = true;
+}
+
+template <> void ModelImpl<double>::set_ozaki_attributes() {
+    SURFH_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<6, kOzCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ozaki_smem_bytes(6)));
+    SURFH_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<7, kOzCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ozaki_smem_bytes(7)));
+    SURFH_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<8, kOzCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ozaki_smem_bytes(8)));
+}
+
+template <> template <int S> void ModelImpl<double>::ozaki_run(double* y, bool adjoint, cudaStream_t st) {
+    std::vector<size_t> lsf_bands;
+    for (size_t i = 0; i < bands.size(); ++i)
+        if (bands[i]->mode == SURFH_SPECTRAL_LSF) lsf_bands.push_back(i);
+    std::stable_sort(lsf_bands.begin(), lsf_bands.end(), [&](size_t x, size_t y2) {
+        const int kx = adjoint ? bands[x]->nd : bands[x]->KB, ky = adjoint ? bands[y2]->nd : bands[y2]->KB;
+        return kx > ky;
+    });
+    {
+        // the per-call operand -> int8 digit planes + row scales (forward: the slit-space vector G; adjoint: the
+        // detector block, first re-laid K-fast per detector column)
+        double bytes = 0;
+        for (size_t j : lsf_bands) {
+            const BandT<double>& b = *bands[j];
+            bytes += adjoint ? (2.0 * sizeof(double) + S) * (double)b.out_size : (sizeof(double) + S) * (double)b.Nn * b.KB;
+        }
+        Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, 0, (int)lsf_bands.size() * (adjoint ? 2 : 1), true);
+        for (size_t j : lsf_bands) {
+            BandT<double>& b = *bands[j];
+            if (adjoint) {
+                const size_t n = (size_t)b.Nn * b.nd;
+                detector_to_kfast_kernel<<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.na, b.nd, b.Nn, b.ndp,
+                                                                            b.yk.as<double>());
+                ozaki_slice<S>(b.yk.as<double>(), b.Nn, b.nd, (size_t)b.ndp, b.oz_yk, b.oz_ndq, b.oz_syk, st);
+            } else {
+                ozaki_slice<S>(b.G.as<double>(), b.Nn, b.KB, (size_t)b.g_col, b.oz_g, b.oz_kq, b.oz_sg, st);
+            }
+        }
+        SURFH_CUDA(cudaGetLastError());
+    }
+    for (size_t first = 0; first < lsf_bands.size(); first += kMaxGemmGroup) {
+        OzakiBatch batch;
+        batch.count = 0;
+        batch.tile_start[0] = 0;
+        batch.dump = nullptr;
+        double bytes = 0, flops = 0;
+        for (size_t j = first; j < std::min(lsf_bands.size(), first + (size_t)kMaxGemmGroup); ++j) {
+            BandT<double>& b = *bands[lsf_bands[j]];
+            OzakiProblem& g = batch.p[batch.count];
+            if (!adjoint) {   // y = W . G
+                g.a = b.ozmap_w; g.b = b.ozmap_g; g.M = b.nd; g.N = b.Nn; g.K = b.KB;
+                g.sa = b.oz_sw.as<double>(); g.sb = b.oz_sg.as<double>();
+                g.C = y + b.out_offset; g.cM = b.t_yM.as<int32_t>(); g.cN = b.t_yN.as<int32_t>();
+            } else {          // Gt = Wt . Yk
+                g.a = b.ozmap_wt; g.b = b.ozmap_yk; g.M = b.KB; g.N = b.Nn; g.K = b.nd;
+                g.sa = b.oz_swt.as<double>(); g.sb = b.oz_syk.as<double>();
+                g.C = b.G.as<double>(); g.cM = b.t_ident.as<int32_t>(); g.cN = b.t_gN.as<int32_t>();
+            }
+            const int tiles_n = ceil_div(ceil_div(g.N, kOzBN), kOzCluster) * kOzCluster;
+            batch.tile_start[batch.count + 1] = batch.tile_start[batch.count] + ceil_div(g.M, kOzBM) * tiles_n;
+            batch.count++;
+            bytes += (double)S * ((double)b.nd * b.KB + (double)b.Nn * (adjoint ? b.nd : b.KB)) + sizeof(double) * (double)g.M * g.N;
+            flops += 2.0 * g.M * g.N * g.K;
+        }
+        Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, flops, 1, true);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)batch.tile_start[batch.count]);
+        cfg.blockDim = dim3(kOzThreads);
+        cfg.dynamicSmemBytes = ozaki_smem_bytes(S);
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kOzCluster;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        SURFH_CUDA(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<S, kOzCluster>, batch));
+    }
+}
+
+template <> void ModelImpl<double>::gemm_grouped_f64_ozaki(double* y, bool adjoint, cudaStream_t st) {
+    if (ozaki_digits == 6) ozaki_run<6>(y, adjoint, st);
+    else if (ozaki_digits == 7) ozaki_run<7>(y, adjoint, st);
+    else ozaki_run<8>(y, adjoint, st);
+}
+
 template <> void ModelImpl<double>::gemm_grouped_f64(double* y, bool adjoint, cudaStream_t st) {
-    if (f64_tma_gemm) return gemm_grouped_f64_tma(y, adjoint, st);
+    if (f64_gemm_mode == F64_GEMM_OZAKI) {
+        bool all = true;
+        for (auto& b : bands) all = all && (b->mode != SURFH_SPECTRAL_LSF || b->oz_ready);
+        if (all) return gemm_grouped_f64_ozaki(y, adjoint, st);
+    }
+    if (f64_gemm_mode != F64_GEMM_MMA) return gemm_grouped_f64_tma(y, adjoint, st);
     std::vector<size_t> lsf_bands;
     for (size_t i = 0; i < bands.size(); ++i)
         if (bands[i]->mode == SURFH_SPECTRAL_LSF) lsf_bands.push_back(i);
