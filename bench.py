@@ -94,6 +94,18 @@ def measured_fp_peak(torch, tdtype):
         return {"tflops": None, "source": f"unavailable ({exc})"}
 
 
+def measured_int8_peak():
+    """Dense int8 tensor rate (TOP/s): twice the measured dense bf16 rate of this pool's B200s (MEASURED_PEAKS.json,
+    the sustained figure: the contraction runs inside a long step); nominal 4500 when the file is absent."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        bf16 = float(p.get("bf16_tflops_sustained") or p["bf16_tflops"])
+        return 2.0 * bf16, "2 x measured sustained dense bf16 (MEASURED_PEAKS.json): int8 runs at twice the bf16 rate on B200"
+    return 4500.0, "nominal dense int8 (B200_PROFILING.md)"
+
+
 def ncu_traffic():
     """DRAM bytes per launch of each stage's kernels from the committed ncu --set full capture of this same
     command (profiles/traffic.json, written by tools/ncu_traffic.py); {} when no capture is committed."""
@@ -510,6 +522,7 @@ def run_b200(args):
     hbm_peak, peak_src = measured_peaks()
     fp_peak = measured_fp_peak(torch, tdtype)  # cuBLAS GEMM of the compute dtype, this GPU, this run
     traffic = ncu_traffic()
+    contraction = model.contraction_info()
     stage_rows = []
     tot_ms = sum(s["ms"] for s in stages) or 1.0
     for s in stages:
@@ -519,7 +532,23 @@ def run_b200(args):
         row = {"stage": name, "ms_per_step": per_step_ms, "share": s["ms"] / tot_ms, "own": own,
                "launches_per_step": s["launches"] / args.steps}
         sec = s["ms"] * 1e-3
-        if name.startswith("spectral_gemm"):
+        if name.startswith("spectral_gemm") and contraction["mode"] == "ozaki_i8":
+            # int8-sliced error-free product on tcgen05: S digits per operand = S (S + 1) / 2 int8 products of the
+            # contraction's shape; measured against the int8 tensor rate.  The stage time includes cutting the
+            # per-call operand into digits.
+            digits = contraction["digits"]
+            products = digits * (digits + 1) // 2
+            i8_peak, i8_src = measured_int8_peak()
+            eq = s["flops"] / sec / 1e12 if sec > 0 else None
+            row.update(bound="tensor", unit="TFLOP/s", achieved=None if eq is None else eq * products, peak=i8_peak,
+                       peak_source=i8_src, digits=digits, int8_products=products, fp64_equivalent_tflops=eq,
+                       note="achieved / peak are int8 tensor operations (TOP/s); fp64_equivalent_tflops = the "
+                            "contraction's own 2 M N K flops over the same time")
+            if eq is not None:
+                row["frac"] = row["achieved"] / i8_peak
+                if fp_peak["tflops"]:
+                    row["vs_cublas_gemm_of_dtype"] = eq / fp_peak["tflops"]
+        elif name.startswith("spectral_gemm"):
             # dense contraction on the FP64 tensor pipe (DMMA) / FP32 FMA: flop-bound, not HBM-bound
             row.update(bound="tensor" if esz == 8 else "fma_fp32", unit="TFLOP/s",
                        achieved=s["flops"] / sec / 1e12 if sec > 0 else None, peak=fp_peak["tflops"])
@@ -557,7 +586,7 @@ def run_b200(args):
         roofline = {"kernel": top["stage"], "bound": top["bound"] if top["bound"] in ("hbm", "tensor") else "hbm",
                     "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top.get("frac"),
                     "traffic": top.get("traffic"),
-                    "peak_source": peak_src if top["unit"] == "GB/s" else fp_peak["source"],
+                    "peak_source": top.get("peak_source") or (peak_src if top["unit"] == "GB/s" else fp_peak["source"]),
                     "share_of_step": top["share"],
                     "fp_peak": {"tflops": fp_peak["tflops"], "source": fp_peak["source"]},
                     "hbm_peak": {"gbs": hbm_peak, "source": peak_src}}
@@ -565,6 +594,7 @@ def run_b200(args):
             if k in top:
                 roofline[k] = top[k]
         # every stage in one compact list, inside the object the driver keeps
+        roofline["contraction"] = contraction
         roofline["stages"] = [{"stage": r["stage"], "ms": round(r["ms_per_step"], 4), "bound": r.get("bound"),
                                "frac": None if r.get("frac") is None else round(r["frac"], 4),
                                "frac_of_fp_peak": None if r.get("frac_of_fp_peak") is None else round(r["frac_of_fp_peak"], 4)}

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SURFH_ABI_VERSION 4
+#define SURFH_ABI_VERSION 5
 
 enum { SURFH_F32 = 0, SURFH_F64 = 1 };
 
@@ -229,6 +229,12 @@ int surfh_shepard(const float* alpha_coord, const float* lambda_coord, const flo
 /* number of kernels (own + cuFFT exec calls) this handle has launched since creation */
 int64_t surfh_launch_count(surfh_handle h);
 int64_t surfh_own_launch_count(surfh_handle h);
+/* how this handle evaluates the spectral response (wblur_subSampling / wblur_t, surfh/ToolsDir/jax_utils.py:72-91):
+ * *mode 2 = int8-sliced error-free product on tcgen05 tensor cores with *digits int8 digits per operand (default:
+ * 8 digits in fp64, 4 in fp32), 1 = FP64 DMMA fed by TMA, 0 = mma.sync kernels of round 1 (DMMA / 3xTF32), 3 = FFMA,
+ * -1 = no band has a spectral response (beta-sum bands only).
+ * Selected per process by SURFH_F64_GEMM / SURFH_F32_GEMM / SURFH_OZAKI_DIGITS when the handle is created. */
+int surfh_contraction_info(surfh_handle h, int32_t* mode, int32_t* digits);
 /* per-stage CUDA-event timing of the calls made while enabled: enable, run, then read.
  * Output arrays of capacity `cap` (any may be NULL): stage name ("chirpz_*" = hand-written FFT passes,
  * "cufft_*" = library FFT), summed milliseconds, algorithmic bytes, flops and kernel launches.

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("SURFH_B200_LIB") or os.path.join(os.path.dirname(os.p
 F32, F64 = 0, 1
 ADJ_EXACT, ADJ_REFERENCE = 0, 1
 CG_NSCALARS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 SPECTRAL_LSF, SPECTRAL_BETA_SUM = 0, 1
 FFT_BACKENDS = {"auto": 0, "cufft": 1, "own": 2}
 
@@ -29,7 +29,7 @@ SYMBOLS = [
     "surfh_last_error", "surfh_input_size", "surfh_output_size", "surfh_workspace_bytes", "surfh_forward",
     "surfh_adjoint", "surfh_fwadj", "surfh_maps_to_cube", "surfh_forward_host", "surfh_adjoint_host",
     "surfh_cg_regularise_dot", "surfh_laplacian_axpby", "surfh_cg_start", "surfh_cg_update", "surfh_cg_refresh", "surfh_criterion_terms", "surfh_cg_dot_x_b_plus_r", "surfh_axpy_device_scalar", "surfh_precond_build", "surfh_precond_apply", "surfh_pcg_update", "surfh_pcg_direction", "surfh_shepard",
-    "surfh_launch_count", "surfh_own_launch_count", "surfh_profile_enable", "surfh_profile_read", "surfh_rfft2",
+    "surfh_launch_count", "surfh_own_launch_count", "surfh_contraction_info", "surfh_profile_enable", "surfh_profile_read", "surfh_rfft2",
 ]
 
 
@@ -110,6 +110,7 @@ def load() -> C.CDLL:
         "surfh_rfft2": (C.c_int, [i32, i32, i32, i32, i32, vp, vp, vp]),
         "surfh_launch_count": (i64, [vp]),
         "surfh_own_launch_count": (i64, [vp]),
+        "surfh_contraction_info": (C.c_int, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
         "surfh_profile_enable": (C.c_int, [vp, i32]),
         "surfh_profile_read": (C.c_int, [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                          C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),

@@ -78,6 +78,7 @@ struct surfh_model {
     virtual int64_t input_size() const = 0;
     virtual int64_t output_size() const = 0;
     virtual int64_t workspace_bytes() const = 0;
+    virtual void contraction_info(int32_t* mode, int32_t* digits) const = 0;
     virtual void forward(const void* x, void* y, cudaStream_t st) = 0;
     virtual void adjoint(const void* y, void* x, int mode, cudaStream_t st) = 0;
     virtual void fwadj(const void* x, void* out, int mode, void* yscratch, cudaStream_t st) = 0;
@@ -256,18 +257,25 @@ static CUtensorMap tensor_map_digits(const void* base, int inner, int rows, int 
     return m;
 }
 
-// How the fp64 operator evaluates the spectral response (SURFH_F64_GEMM): "ozaki" (default) = int8-sliced product on
-// tcgen05 (kernels_ozaki.cuh) with SURFH_OZAKI_DIGITS = 6, 7 or 8 (default) digits; "tma" = DMMA fed by TMA
-// (kernels_gemm_tma.cuh); "mma" = round 1's offset-table DMMA kernel.
-enum { F64_GEMM_MMA = 0, F64_GEMM_TMA = 1, F64_GEMM_OZAKI = 2 };
-static int f64_gemm_mode_env() {
-    const char* e = std::getenv("SURFH_F64_GEMM");
-    if (!e || !*e || std::strcmp(e, "ozaki") == 0) return F64_GEMM_OZAKI;
-    if (std::strcmp(e, "tma") == 0 || std::strcmp(e, "dmma") == 0) return F64_GEMM_TMA;
-    if (std::strcmp(e, "mma") == 0) return F64_GEMM_MMA;
-    throw Error(SURFH_EINVAL, std::string("SURFH_F64_GEMM must be ozaki, tma or mma, not ") + e);
+// How the spectral response is evaluated.  GEMM_OZAKI (default, both dtypes): int8-sliced product on tcgen05
+// (kernels_ozaki.cuh) -- fp64: SURFH_OZAKI_DIGITS = 6, 7 or 8 (default) digits; fp32: 4 digits.
+// SURFH_F64_GEMM = ozaki | tma (DMMA fed by TMA, kernels_gemm_tma.cuh) | mma (round 1's offset-table DMMA kernel);
+// SURFH_F32_GEMM = ozaki | tf32 (3xTF32 mma.sync) | simt (FFMA).
+enum { GEMM_LEGACY = 0, GEMM_TMA = 1, GEMM_OZAKI = 2, GEMM_SIMT = 3 };
+static int gemm_mode_env(bool f64) {
+    const char* e = std::getenv(f64 ? "SURFH_F64_GEMM" : "SURFH_F32_GEMM");
+    if (!e || !*e || std::strcmp(e, "ozaki") == 0) return GEMM_OZAKI;
+    if (f64) {
+        if (std::strcmp(e, "tma") == 0 || std::strcmp(e, "dmma") == 0) return GEMM_TMA;
+        if (std::strcmp(e, "mma") == 0) return GEMM_LEGACY;
+        throw Error(SURFH_EINVAL, std::string("SURFH_F64_GEMM must be ozaki, tma or mma, not ") + e);
+    }
+    if (std::strcmp(e, "tf32") == 0 || std::strcmp(e, "mma") == 0 || std::strcmp(e, "tensor") == 0) return GEMM_LEGACY;
+    if (std::strcmp(e, "simt") == 0) return GEMM_SIMT;
+    throw Error(SURFH_EINVAL, std::string("SURFH_F32_GEMM must be ozaki, tf32 or simt, not ") + e);
 }
-static int ozaki_digits_env() {
+static int ozaki_digits_env(bool f64) {
+    if (!f64) return 4;   // 6 + 3 x 7 = 27 bits below the row maximum
     const char* e = std::getenv("SURFH_OZAKI_DIGITS");
     if (!e || !*e) return 8;
     const int d = std::atoi(e);
@@ -512,20 +520,23 @@ template <typename T> struct ModelImpl : surfh_model {
         const size_t g_elems = b->mode == SURFH_SPECTRAL_LSF ? (size_t)b->Nn * b->KBp : (size_t)b->nl * b->ncol;
         b->G.alloc(g_elems * sizeof(T));
         SURFH_CUDA(cudaMemset(b->G.p, 0, b->G.bytes));   // the pad column is never written: keep it finite (zero)
-        if (b->mode == SURFH_SPECTRAL_LSF && std::is_same<T, double>::value) {
-            // operands and tables of the TMA contraction (kernels_gemm_tma.cuh)
+        if (b->mode == SURFH_SPECTRAL_LSF) {
+            // K-fast operands of the adjoint product: the transposed LSF and the re-laid detector block
             b->ndp = (b->nd + 1) / 2 * 2;
             std::vector<double> wt((size_t)b->KB * b->ndp, 0.0);
             for (int m = 0; m < b->nd; ++m)
                 for (int k = 0; k < b->KB; ++k) wt[(size_t)k * b->ndp + m] = d->lsf[(size_t)m * b->KB + k];
-            upload_converted<double>(b->lsf_t, wt.data(), wt.size());
-            b->yk.alloc((size_t)b->Nn * b->ndp * sizeof(double));
-            b->map_w = tensor_map_2d_f64(b->lsf.p, b->KB, b->nd, (size_t)b->KBp, kTBM);
-            b->map_g = tensor_map_2d_f64(b->G.p, b->KB, b->Nn, (size_t)b->g_col, kTBN);
-            b->map_wt = tensor_map_2d_f64(b->lsf_t.p, b->nd, b->KB, (size_t)b->ndp, kTBM);
-            b->map_yk = tensor_map_2d_f64(b->yk.p, b->nd, b->Nn, (size_t)b->ndp, kTBN);
-            b->tma_ready = true;
-            if (f64_gemm_mode == F64_GEMM_OZAKI) prepare_ozaki(*b);
+            upload_converted<T>(b->lsf_t, wt.data(), wt.size());
+            b->yk.alloc((size_t)b->Nn * b->ndp * sizeof(T));
+            if (std::is_same<T, double>::value) {
+                // tensor maps of the TMA-fed DMMA contraction (kernels_gemm_tma.cuh)
+                b->map_w = tensor_map_2d_f64(b->lsf.p, b->KB, b->nd, (size_t)b->KBp, kTBM);
+                b->map_g = tensor_map_2d_f64(b->G.p, b->KB, b->Nn, (size_t)b->g_col, kTBN);
+                b->map_wt = tensor_map_2d_f64(b->lsf_t.p, b->nd, b->KB, (size_t)b->ndp, kTBM);
+                b->map_yk = tensor_map_2d_f64(b->yk.p, b->nd, b->Nn, (size_t)b->ndp, kTBN);
+                b->tma_ready = true;
+            }
+            if (gemm_mode == GEMM_OZAKI) prepare_ozaki(*b);
         }
         bands.push_back(std::move(b));
     }
@@ -625,7 +636,7 @@ template <typename T> struct ModelImpl : surfh_model {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         SURFH_CUDA(cudaFuncSetAttribute(otgemm_kernel<T, G::BM, G::BN, G::BK, G::TM, G::TN, false, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (const char* e = std::getenv("SURFH_F32_GEMM")) f32_tensor_gemm = std::strcmp(e, "simt") != 0;
+        set_ozaki_attributes();
         if (std::is_same<T, float>::value) {
             SURFH_CUDA(cudaFuncSetAttribute(sgemm_tf32x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)sgemm_smem_bytes<true, true>()));
@@ -633,7 +644,6 @@ template <typename T> struct ModelImpl : surfh_model {
                                             (int)sgemm_smem_bytes<false, false>()));
         }
         if (std::is_same<T, double>::value) {
-            set_ozaki_attributes();
             SURFH_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTSmemBytes));
             SURFH_CUDA(cudaFuncSetAttribute(dgemm_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)dgemm_smem_bytes<true, true>()));
@@ -658,6 +668,19 @@ template <typename T> struct ModelImpl : surfh_model {
                  b->oz_w.bytes + b->oz_wt.bytes + b->oz_g.bytes + b->oz_yk.bytes +
                  b->csr_col[0].bytes + b->csr_val[0].bytes + b->csr_col[1].bytes + b->csr_val[1].bytes;
         return t + precond_inv.bytes;
+    }
+
+    void contraction_info(int32_t* mode, int32_t* digits) const override {
+        bool any_lsf = false;
+        for (auto& b : bands) any_lsf = any_lsf || b->mode == SURFH_SPECTRAL_LSF;
+        if (!any_lsf) {   // beta-sum bands only (MRSBlurred): there is no contraction
+            if (mode) *mode = -1;
+            if (digits) *digits = 0;
+            return;
+        }
+        const bool oz = ozaki_usable();
+        if (mode) *mode = oz ? GEMM_OZAKI : (gemm_mode == GEMM_OZAKI ? (std::is_same<T, double>::value ? GEMM_TMA : GEMM_LEGACY) : gemm_mode);
+        if (digits) *digits = oz ? ozaki_digits : 0;
     }
 
     // ---- launch helpers ---------------------------------------------------------------------
@@ -775,14 +798,133 @@ template <typename T> struct ModelImpl : surfh_model {
     void gemm_grouped_f64(double* y, bool adjoint, cudaStream_t st);
     // FP32 tensor path (3xTF32 split), same grouping; SURFH_F32_GEMM=simt selects the FFMA kernel
     void gemm_grouped_f32(float* y, bool adjoint, cudaStream_t st);
-    bool f32_tensor_gemm = true;
-    int f64_gemm_mode = f64_gemm_mode_env();   // read once per handle, before the bands are added
-    int ozaki_digits = ozaki_digits_env();
+    int gemm_mode = gemm_mode_env(std::is_same<T, double>::value);   // read once per handle, before the bands are added
+    int ozaki_digits = ozaki_digits_env(std::is_same<T, double>::value);
     void gemm_grouped_f64_tma(double* y, bool adjoint, cudaStream_t st);
-    void prepare_ozaki(BandT<T>& b);
-    void set_ozaki_attributes();
-    void gemm_grouped_f64_ozaki(double* y, bool adjoint, cudaStream_t st);
-    template <int S> void ozaki_run(double* y, bool adjoint, cudaStream_t st);
+    // ---- the sliced contraction on tcgen05 (kernels_ozaki.cuh) -------------------------------------------
+    template <int S> static void ozaki_slice(const T* x, int rows, int k, size_t ld, DevBuf& digits, int pitch, DevBuf& scale,
+                                             cudaStream_t st) {
+        ozaki_slice_rows_kernel<S, T><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, k, ld, digits.as<int8_t>(), pitch,
+                                                                         scale.as<double>());
+    }
+    template <typename F> void with_digits(F&& f) {   // f(std::integral_constant<int, S>) for this handle's digit count
+        if (std::is_same<T, float>::value) return f(std::integral_constant<int, 4>());
+        if (ozaki_digits == 6) return f(std::integral_constant<int, 6>());
+        if (ozaki_digits == 7) return f(std::integral_constant<int, 7>());
+        return f(std::integral_constant<int, 8>());
+    }
+    void prepare_ozaki(BandT<T>& b) {
+        const int S = ozaki_digits;
+        // every level sum_{p+q=t} sum_k dA dB must fit an int32: (t + 1) K 64^2 < 2^31
+        if ((int64_t)S * std::max(b.KB, b.nd) * 4096 >= ((int64_t)1 << 31)) return;   // this band keeps the older kernels
+        b.oz_kq = (b.KB + 15) / 16 * 16;
+        b.oz_ndq = (b.nd + 15) / 16 * 16;
+        b.oz_w.alloc((size_t)S * b.nd * b.oz_kq);
+        b.oz_wt.alloc((size_t)S * b.KB * b.oz_ndq);
+        b.oz_g.alloc((size_t)S * b.Nn * b.oz_kq);
+        b.oz_yk.alloc((size_t)S * b.Nn * b.oz_ndq);
+        b.oz_sw.alloc((size_t)b.nd * sizeof(double));
+        b.oz_swt.alloc((size_t)b.KB * sizeof(double));
+        b.oz_sg.alloc((size_t)b.Nn * sizeof(double));
+        b.oz_syk.alloc((size_t)b.Nn * sizeof(double));
+        // the LSF and its transpose are constant: cut them into digits once
+        with_digits([&](auto s_) {
+            constexpr int SS = decltype(s_)::value;
+            ozaki_slice<SS>(b.lsf.template as<T>(), b.nd, b.KB, (size_t)b.KBp, b.oz_w, b.oz_kq, b.oz_sw, 0);
+            ozaki_slice<SS>(b.lsf_t.template as<T>(), b.KB, b.nd, (size_t)b.ndp, b.oz_wt, b.oz_ndq, b.oz_swt, 0);
+        });
+        SURFH_CUDA(cudaGetLastError());
+        SURFH_CUDA(cudaDeviceSynchronize());
+        b.ozmap_w = tensor_map_digits(b.oz_w.p, b.KB, b.nd, b.oz_kq, S, kOzBM / kOzCluster);
+        b.ozmap_g = tensor_map_digits(b.oz_g.p, b.KB, b.Nn, b.oz_kq, S, kOzBN);
+        b.ozmap_wt = tensor_map_digits(b.oz_wt.p, b.nd, b.KB, b.oz_ndq, S, kOzBM / kOzCluster);
+        b.ozmap_yk = tensor_map_digits(b.oz_yk.p, b.nd, b.Nn, b.oz_ndq, S, kOzBN);
+        b.oz_ready = true;
+    }
+    void set_ozaki_attributes() {
+        with_digits([&](auto s_) {
+            constexpr int SS = decltype(s_)::value;
+            SURFH_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<SS, kOzCluster, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)ozaki_smem_bytes(SS)));
+        });
+    }
+    bool ozaki_usable() const {
+        if (gemm_mode != GEMM_OZAKI) return false;
+        for (auto& b : bands)
+            if (b->mode == SURFH_SPECTRAL_LSF && !b->oz_ready) return false;
+        return true;
+    }
+    template <int S> void ozaki_run(T* y, bool adjoint, cudaStream_t st) {
+        std::vector<size_t> lsf_bands;
+        for (size_t i = 0; i < bands.size(); ++i)
+            if (bands[i]->mode == SURFH_SPECTRAL_LSF) lsf_bands.push_back(i);
+        // longest contractions first: the block scheduler hands tiles out in blockIdx order
+        std::stable_sort(lsf_bands.begin(), lsf_bands.end(), [&](size_t x, size_t y2) {
+            const int kx = adjoint ? bands[x]->nd : bands[x]->KB, ky = adjoint ? bands[y2]->nd : bands[y2]->KB;
+            return kx > ky;
+        });
+        {
+            // the per-call operand -> int8 digit planes + row scales (forward: the slit-space vector G; adjoint: the
+            // detector block, first re-laid K-fast per detector column)
+            double bytes = 0;
+            for (size_t j : lsf_bands) {
+                const BandT<T>& b = *bands[j];
+                bytes += adjoint ? (2.0 * sizeof(T) + S) * (double)b.out_size : (sizeof(T) + S) * (double)b.Nn * b.KB;
+            }
+            Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, 0, (int)lsf_bands.size() * (adjoint ? 2 : 1), true);
+            for (size_t j : lsf_bands) {
+                BandT<T>& b = *bands[j];
+                if (adjoint) {
+                    const size_t n = (size_t)b.Nn * b.nd;
+                    detector_to_kfast_kernel<T><<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.na, b.nd, b.Nn, b.ndp,
+                                                                                   b.yk.template as<T>());
+                    ozaki_slice<S>(b.yk.template as<T>(), b.Nn, b.nd, (size_t)b.ndp, b.oz_yk, b.oz_ndq, b.oz_syk, st);
+                } else {
+                    ozaki_slice<S>(b.G.template as<T>(), b.Nn, b.KB, (size_t)b.g_col, b.oz_g, b.oz_kq, b.oz_sg, st);
+                }
+            }
+            SURFH_CUDA(cudaGetLastError());
+        }
+        for (size_t first = 0; first < lsf_bands.size(); first += kMaxGemmGroup) {
+            OzakiBatch batch;
+            batch.count = 0;
+            batch.tile_start[0] = 0;
+            batch.dump = nullptr;
+            double bytes = 0, flops = 0;
+            for (size_t j = first; j < std::min(lsf_bands.size(), first + (size_t)kMaxGemmGroup); ++j) {
+                BandT<T>& b = *bands[lsf_bands[j]];
+                OzakiProblem& g = batch.p[batch.count];
+                if (!adjoint) {   // y = W . G
+                    g.a = b.ozmap_w; g.b = b.ozmap_g; g.M = b.nd; g.N = b.Nn; g.K = b.KB;
+                    g.sa = b.oz_sw.template as<double>(); g.sb = b.oz_sg.template as<double>();
+                    g.C = y + b.out_offset; g.cM = b.t_yM.template as<int32_t>(); g.cN = b.t_yN.template as<int32_t>();
+                } else {          // Gt = Wt . Yk
+                    g.a = b.ozmap_wt; g.b = b.ozmap_yk; g.M = b.KB; g.N = b.Nn; g.K = b.nd;
+                    g.sa = b.oz_swt.template as<double>(); g.sb = b.oz_syk.template as<double>();
+                    g.C = b.G.p; g.cM = b.t_ident.template as<int32_t>(); g.cN = b.t_gN.template as<int32_t>();
+                }
+                const int tiles_n = ceil_div(ceil_div(g.N, kOzBN), kOzCluster) * kOzCluster;
+                batch.tile_start[batch.count + 1] = batch.tile_start[batch.count] + ceil_div(g.M, kOzBM) * tiles_n;
+                batch.count++;
+                bytes += (double)S * ((double)b.nd * b.KB + (double)b.Nn * (adjoint ? b.nd : b.KB)) + sizeof(T) * (double)g.M * g.N;
+                flops += 2.0 * g.M * g.N * g.K;
+            }
+            Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, flops, 1, true);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)batch.tile_start[batch.count]);
+            cfg.blockDim = dim3(kOzThreads);
+            cfg.dynamicSmemBytes = ozaki_smem_bytes(S);
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = kOzCluster;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            SURFH_CUDA(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<S, kOzCluster, T>, batch));
+        }
+    }
 
     void beta_sum(BandT<T>& b, T* y, bool adjoint, cudaStream_t st) {
         const size_t n = (size_t)b.nl * b.Nn * (adjoint ? b.nb : 1);
@@ -804,9 +946,11 @@ template <typename T> struct ModelImpl : surfh_model {
             else any_lsf = true;
         }
         if (!any_lsf) return;
-        if (std::is_same<T, double>::value) {
+        if (ozaki_usable()) {
+            with_digits([&](auto s_) { ozaki_run<decltype(s_)::value>(y, adjoint, st); });
+        } else if (std::is_same<T, double>::value) {
             gemm_grouped_f64(reinterpret_cast<double*>(y), adjoint, st);
-        } else if (f32_tensor_gemm) {
+        } else if (gemm_mode != GEMM_SIMT) {
             gemm_grouped_f32(reinterpret_cast<float*>(y), adjoint, st);
         } else {
             for (auto& bp : bands)
@@ -1261,8 +1405,8 @@ template <> void ModelImpl<double>::gemm_grouped_f64_tma(double* y, bool adjoint
         for (size_t j : lsf_bands) {
             BandT<double>& b = *bands[j];
             const size_t n = (size_t)b.Nn * b.nd;
-            detector_to_kfast_kernel<<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.na, b.nd, b.Nn, b.ndp,
-                                                                        b.yk.as<double>());
+            detector_to_kfast_kernel<double><<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.na, b.nd, b.Nn, b.ndp,
+                                                                                b.yk.as<double>());
         }
         SURFH_CUDA(cudaGetLastError());
     }
@@ -1292,140 +1436,8 @@ template <> void ModelImpl<double>::gemm_grouped_f64_tma(double* y, bool adjoint
     }
 }
 
-// ---- the sliced contraction on tcgen05 (kernels_ozaki.cuh) ----------------------------------------------------
-template <typename T> void ModelImpl<T>::prepare_ozaki(BandT<T>&) {}
-template <typename T> void ModelImpl<T>::set_ozaki_attributes() {}
-template <typename T> void ModelImpl<T>::gemm_grouped_f64_ozaki(double*, bool, cudaStream_t) {
-    throw Error(SURFH_ESTATE, "internal: fp64 contraction on an fp32 model");
-}
-
-template <int S> static void ozaki_slice(const double* x, int rows, int k, size_t ld, DevBuf& digits, int pitch, DevBuf& scale,
-                                         cudaStream_t st) {
-    ozaki_slice_rows_kernel<S><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, k, ld, digits.as<int8_t>(), pitch, scale.as<double>());
-}
-static void ozaki_slice_n(int S, const double* x, int rows, int k, size_t ld, DevBuf& digits, int pitch, DevBuf& scale,
-                          cudaStream_t st) {
-    if (S == 6) ozaki_slice<6>(x, rows, k, ld, digits, pitch, scale, st);
-    else if (S == 7) ozaki_slice<7>(x, rows, k, ld, digits, pitch, scale, st);
-    else ozaki_slice<8>(x, rows, k, ld, digits, pitch, scale, st);
-    SURFH_CUDA(cudaGetLastError());
-}
-
-template <> void ModelImpl<double>::prepare_ozaki(BandT<double>& b) {
-    const int S = ozaki_digits;
-    // every level sum_{p+q=t} sum_k dA dB must fit an int32: (t + 1) K 64^2 < 2^31
-    if ((int64_t)S * std::max(b.KB, b.nd) * 4096 >= ((int64_t)1 << 31)) return;   // this band keeps the DMMA kernel
-    b.oz_kq = (b.KB + 15) / 16 * 16;
-    b.oz_ndq = (b.nd + 15) / 16 * 16;
-    b.oz_w.alloc((size_t)S * b.nd * b.oz_kq);
-    b.oz_wt.alloc((size_t)S * b.KB * b.oz_ndq);
-    b.oz_g.alloc((size_t)S * b.Nn * b.oz_kq);
-    b.oz_yk.alloc((size_t)S * b.Nn * b.oz_ndq);
-    b.oz_sw.alloc((size_t)b.nd * sizeof(double));
-    b.oz_swt.alloc((size_t)b.KB * sizeof(double));
-    b.oz_sg.alloc((size_t)b.Nn * sizeof(double));
-    b.oz_syk.alloc((size_t)b.Nn * sizeof(double));
-    // the LSF and its transpose are constant: cut them into digits once
-    ozaki_slice_n(S, b.lsf.as<double>(), b.nd, b.KB, (size_t)b.KBp, b.oz_w, b.oz_kq, b.oz_sw, 0);
-    ozaki_slice_n(S, b.lsf_t.as<double>(), b.KB, b.nd, (size_t)b.ndp, b.oz_wt, b.oz_ndq, b.oz_swt, 0);
-    SURFH_CUDA(cudaDeviceSynchronize());
-    b.ozmap_w = tensor_map_digits(b.oz_w.p, b.KB, b.nd, b.oz_kq, S, kOzBM / kOzCluster);
-    b.ozmap_g = tensor_map_digits(b.oz_g.p, b.KB, b.Nn, b.oz_kq, S, kOzBN);
-    b.ozmap_wt = tensor_map_digits(b.oz_wt.p, b.nd, b.KB, b.oz_ndq, S, kOzBM / kOzCluster);
-    b.ozmap_yk = tensor_map_digits(b.oz_yk.p, b.nd, b.Nn, b.oz_ndq, S, kOzBN);
-    b.oz_ready = true;
-}
-
-template <> void ModelImpl<double>::set_ozaki_attributes() {
-    SURFH_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<6, kOzCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ozaki_smem_bytes(6)));
-    SURFH_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<7, kOzCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ozaki_smem_bytes(7)));
-    SURFH_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<8, kOzCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ozaki_smem_bytes(8)));
-}
-
-template <> template <int S> void ModelImpl<double>::ozaki_run(double* y, bool adjoint, cudaStream_t st) {
-    std::vector<size_t> lsf_bands;
-    for (size_t i = 0; i < bands.size(); ++i)
-        if (bands[i]->mode == SURFH_SPECTRAL_LSF) lsf_bands.push_back(i);
-    std::stable_sort(lsf_bands.begin(), lsf_bands.end(), [&](size_t x, size_t y2) {
-        const int kx = adjoint ? bands[x]->nd : bands[x]->KB, ky = adjoint ? bands[y2]->nd : bands[y2]->KB;
-        return kx > ky;
-    });
-    {
-        // the per-call operand -> int8 digit planes + row scales (forward: the slit-space vector G; adjoint: the
-        // detector block, first re-laid K-fast per detector column)
-        double bytes = 0;
-        for (size_t j : lsf_bands) {
-            const BandT<double>& b = *bands[j];
-            bytes += adjoint ? (2.0 * sizeof(double) + S) * (double)b.out_size : (sizeof(double) + S) * (double)b.Nn * b.KB;
-        }
-        Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, 0, (int)lsf_bands.size() * (adjoint ? 2 : 1), true);
-        for (size_t j : lsf_bands) {
-            BandT<double>& b = *bands[j];
-            if (adjoint) {
-                const size_t n = (size_t)b.Nn * b.nd;
-                detector_to_kfast_kernel<<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.na, b.nd, b.Nn, b.ndp,
-                                                                            b.yk.as<double>());
-                ozaki_slice<S>(b.yk.as<double>(), b.Nn, b.nd, (size_t)b.ndp, b.oz_yk, b.oz_ndq, b.oz_syk, st);
-            } else {
-                ozaki_slice<S>(b.G.as<double>(), b.Nn, b.KB, (size_t)b.g_col, b.oz_g, b.oz_kq, b.oz_sg, st);
-            }
-        }
-        SURFH_CUDA(cudaGetLastError());
-    }
-    for (size_t first = 0; first < lsf_bands.size(); first += kMaxGemmGroup) {
-        OzakiBatch batch;
-        batch.count = 0;
-        batch.tile_start[0] = 0;
-        batch.dump = nullptr;
-        double bytes = 0, flops = 0;
-        for (size_t j = first; j < std::min(lsf_bands.size(), first + (size_t)kMaxGemmGroup); ++j) {
-            BandT<double>& b = *bands[lsf_bands[j]];
-            OzakiProblem& g = batch.p[batch.count];
-            if (!adjoint) {   // y = W . G
-                g.a = b.ozmap_w; g.b = b.ozmap_g; g.M = b.nd; g.N = b.Nn; g.K = b.KB;
-                g.sa = b.oz_sw.as<double>(); g.sb = b.oz_sg.as<double>();
-                g.C = y + b.out_offset; g.cM = b.t_yM.as<int32_t>(); g.cN = b.t_yN.as<int32_t>();
-            } else {          // Gt = Wt . Yk
-                g.a = b.ozmap_wt; g.b = b.ozmap_yk; g.M = b.KB; g.N = b.Nn; g.K = b.nd;
-                g.sa = b.oz_swt.as<double>(); g.sb = b.oz_syk.as<double>();
-                g.C = b.G.as<double>(); g.cM = b.t_ident.as<int32_t>(); g.cN = b.t_gN.as<int32_t>();
-            }
-            const int tiles_n = ceil_div(ceil_div(g.N, kOzBN), kOzCluster) * kOzCluster;
-            batch.tile_start[batch.count + 1] = batch.tile_start[batch.count] + ceil_div(g.M, kOzBM) * tiles_n;
-            batch.count++;
-            bytes += (double)S * ((double)b.nd * b.KB + (double)b.Nn * (adjoint ? b.nd : b.KB)) + sizeof(double) * (double)g.M * g.N;
-            flops += 2.0 * g.M * g.N * g.K;
-        }
-        Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, flops, 1, true);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)batch.tile_start[batch.count]);
-        cfg.blockDim = dim3(kOzThreads);
-        cfg.dynamicSmemBytes = ozaki_smem_bytes(S);
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = kOzCluster;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        SURFH_CUDA(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<S, kOzCluster>, batch));
-    }
-}
-
-template <> void ModelImpl<double>::gemm_grouped_f64_ozaki(double* y, bool adjoint, cudaStream_t st) {
-    if (ozaki_digits == 6) ozaki_run<6>(y, adjoint, st);
-    else if (ozaki_digits == 7) ozaki_run<7>(y, adjoint, st);
-    else ozaki_run<8>(y, adjoint, st);
-}
-
 template <> void ModelImpl<double>::gemm_grouped_f64(double* y, bool adjoint, cudaStream_t st) {
-    if (f64_gemm_mode == F64_GEMM_OZAKI) {
-        bool all = true;
-        for (auto& b : bands) all = all && (b->mode != SURFH_SPECTRAL_LSF || b->oz_ready);
-        if (all) return gemm_grouped_f64_ozaki(y, adjoint, st);
-    }
-    if (f64_gemm_mode != F64_GEMM_MMA) return gemm_grouped_f64_tma(y, adjoint, st);
+    if (gemm_mode != GEMM_LEGACY) return gemm_grouped_f64_tma(y, adjoint, st);
     std::vector<size_t> lsf_bands;
     for (size_t i = 0; i < bands.size(); ++i)
         if (bands[i]->mode == SURFH_SPECTRAL_LSF) lsf_bands.push_back(i);
@@ -1709,6 +1721,12 @@ int surfh_shepard(const float* alpha_coord, const float* lambda_coord, const flo
 
 int64_t surfh_launch_count(surfh_handle h) { return h ? h->launches : -1; }
 int64_t surfh_own_launch_count(surfh_handle h) { return h ? h->own_launches : -1; }
+
+int surfh_contraction_info(surfh_handle h, int32_t* mode, int32_t* digits) {
+    if (!h) return SURFH_EINVAL;
+    h->contraction_info(mode, digits);
+    return SURFH_OK;
+}
 
 int surfh_profile_enable(surfh_handle h, int32_t on) {
     if (!h) return SURFH_EINVAL;

@@ -165,8 +165,9 @@ dgemm_tma_kernel(const __grid_constant__ GemmTmaBatch batch) {
 
 // Yk[n][m] = y[(ps*nd + m)*na + a],  n = ps*na + a  (row pitch ldk >= nd): the detector block of a band re-laid
 // K-fast per detector column, the B operand of the adjoint product (per (p, s): an [nd][na] -> [na][nd] transpose).
+template <typename T>
 __global__ void __launch_bounds__(256)
-detector_to_kfast_kernel(const double* __restrict__ y, int na, int nd, int Nn, int ldk, double* __restrict__ yk) {
+detector_to_kfast_kernel(const T* __restrict__ y, int na, int nd, int Nn, int ldk, T* __restrict__ yk) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)Nn * nd) return;
     const int m = (int)(idx % nd), n = (int)(idx / nd);

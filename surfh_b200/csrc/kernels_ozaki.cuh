@@ -15,8 +15,9 @@
 // The product of a row of A and a row of B is then
 //     2^(eA-6) 2^(eB-6) * sum_t 2^(-7t) L_t,    L_t = sum_{p+q=t} sum_k dA_p[k] dB_q[k]
 // and every L_t is an exact integer: |L_t| <= (t+1) K 64^2 < 2^31 for K < 65536 / (t+1).  Levels t >= S are
-// dropped (they sit below the digits' own truncation).  S = 7 (28 int8 products) reproduces the fp64 product to
-// ~1e-14 of max|A_row| max|B_row| sqrt(K); the accumulation itself has no rounding at all.
+// dropped (they sit below the digits' own truncation).  S = 8 (36 int8 products) keeps 55 bits below every row's
+// maximum: the fp64 product to ~1e-14 (7 digits: ~1e-12); the accumulation itself has no rounding at all, which is why
+// the result is closer to the exact product than an fp64 FMA chain.  The fp32 operator uses S = 4 (27 bits, 10 products).
 //
 // Kernel (one CTA = one 128 x 64 tile of C, 6 warps, one CTA per SM):
 //   warp 0 (one lane)  TMA producer: per 64-deep k-block, S + S `cp.async.bulk.tensor.3d` boxes (A digit p:
@@ -58,7 +59,7 @@ struct OzakiProblem {
     int M, N, K;
     const double* sa;        // [M] 2^(eA - 6)
     const double* sb;        // [N] 2^(eB - 6)
-    double* C;               // C(m, n) at C[cM[m] + cN[n]]
+    void* C;                 // C(m, n) at C[cM[m] + cN[n]], elements of the kernel's output type
     const int32_t* cM;
     const int32_t* cN;
 };
@@ -73,15 +74,15 @@ struct OzakiBatch {
 // ---- digit extraction ---------------------------------------------------------------------------------------
 // One warp per row: row maximum -> exponent e -> S int8 digit planes + the scale 2^(e-6).
 // X: rows at pitch ld (elements); digits: [S][rows][Kp] (Kp multiple of 16, >= K; the pad is written as zero).
-template <int S>
+template <int S, typename TIn>
 __global__ void __launch_bounds__(256)
-ozaki_slice_rows_kernel(const double* __restrict__ X, int rows, int K, size_t ld, int8_t* __restrict__ digits, int Kp,
+ozaki_slice_rows_kernel(const TIn* __restrict__ X, int rows, int K, size_t ld, int8_t* __restrict__ digits, int Kp,
                         double* __restrict__ scale) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const double* x = X + (size_t)row * ld;
+    const TIn* x = X + (size_t)row * ld;
     double amax = 0.0;
-    for (int k = lane; k < K; k += 32) amax = fmax(amax, fabs(x[k]));
+    for (int k = lane; k < K; k += 32) amax = fmax(amax, fabs((double)x[k]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     // |x| < 2^e (ilogb(amax) + 1); an all-zero row keeps e = 0
@@ -96,7 +97,7 @@ ozaki_slice_rows_kernel(const double* __restrict__ X, int rows, int K, size_t ld
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = k0 + j;
-            double r = k < K ? scalbn(x[k], 6 - e) : 0.0;     // |r| < 64
+            double r = k < K ? scalbn((double)x[k], 6 - e) : 0.0;     // |r| < 64
 #pragma unroll
             for (int p = 0; p < S; ++p) {
                 const double d = rint(r);
@@ -204,7 +205,7 @@ __device__ __forceinline__ void oz_wait(void* bar, unsigned parity, int) { mbar_
 // CL: CTAs per cluster.  The CL CTAs of a cluster own CL neighbouring column tiles of ONE row tile: each loads 1/CL
 // of every A digit tile and multicasts it to the whole cluster (the L2 -> SM traffic, which bounds the kernel,
 // drops from 12 KB to (8 / CL + 4) KB per digit and k-block); tile_start counts CTAs (CL per cluster).
-template <int S, int CL>
+template <int S, int CL, typename TOut>
 __global__ void __launch_bounds__(kOzThreads, 1)
 ozaki_gemm_kernel(const __grid_constant__ OzakiBatch batch) {
     static_assert(S >= 1 && S <= kOzMaxDigits, "digit count");
@@ -332,7 +333,7 @@ ozaki_gemm_kernel(const __grid_constant__ OzakiBatch batch) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int n = n0 + c * 16 + j;
-                if (m_ok && n < g.N) g.C[(size_t)cm + __ldg(g.cN + n)] = acc[j] * sa * __ldg(g.sb + n);
+                if (m_ok && n < g.N) static_cast<TOut*>(g.C)[(size_t)cm + __ldg(g.cN + n)] = (TOut)(acc[j] * sa * __ldg(g.sb + n));
             }
         }
         tc_fence_before();

@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(_capi.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported"
-    assert lib.surfh_abi_version() == _capi.ABI_VERSION == 4
+    assert lib.surfh_abi_version() == _capi.ABI_VERSION == 5
 
 
 def test_struct_layouts_match_header():

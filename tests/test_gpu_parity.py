@@ -92,11 +92,12 @@ def test_c3_vs_reference_golden(built, golden_dir):
     assert abs(np.linalg.norm(x) - float(gold["adj_norm"])) <= 1e-10 * float(gold["adj_norm"])
 
 
-@pytest.mark.parametrize("gemm", ["tensor", "simt"])
+@pytest.mark.parametrize("gemm", ["ozaki", "tf32", "simt"])
 def test_fp32_full_size_vs_reference_golden(built, golden_dir, gemm, monkeypatch):
     """fp32 mode at full size (contraction length 3144) against the reference's golden vectors, 1e-5 budget,
-    for both spectral-response kernels: 3xTF32 on the tensor cores (slab-wise accumulation, without which
-    the truncating tensor-core adds bias the sum by 2e-5) and the FFMA kernel."""
+    for the three spectral-response kernels: the int8-sliced product on tcgen05 (4 digits, the default), 3xTF32
+    mma.sync (slab-wise accumulation, without which the truncating tensor-core adds bias the sum by 2e-5) and the
+    FFMA kernel."""
     monkeypatch.setenv("SURFH_F32_GEMM", gemm)
     cfg = CASES["c1_band1a"]()
     gold = np.load(os.path.join(golden_dir, "c1_band1a.npz"))
@@ -178,3 +179,41 @@ def test_partial_handle_host_forward_after_adjoint_has_zero_foreign_blocks(built
     cut = int(full._idx[1])
     assert np.all(y[cut:] == 0.0)
     assert rel(y[:cut], full.forward(cfg.maps)[:cut]) <= 1e-13
+
+
+def test_contraction_backends_agree(built, monkeypatch):
+    """The spectral response runs as an int8-sliced product on the tcgen05 tensor cores by default (8 digits in
+    fp64, 4 in fp32: csrc/kernels_ozaki.cuh).  It has to agree with the FP64 DMMA kernels it replaces -- to the
+    rounding of those kernels with 8 digits, to 2^-(7 digits) with fewer -- and with the oracle (reference:
+    jax_utils.wblur_subSampling / wblur_t, surfh/ToolsDir/jax_utils.py:72-91)."""
+    from surfh_oracle import model as om
+    cfg = CASES["band2a_4p"]()
+    args = cfg.model_args()
+    v = np.random.default_rng(7).standard_normal(int(om.SpectroLMM(**args).osize))
+    monkeypatch.delenv("SURFH_F64_GEMM", raising=False)
+    monkeypatch.delenv("SURFH_OZAKI_DIGITS", raising=False)
+    oz = built(**args, dtype="float64", adjoint_mode="exact")
+    assert oz.contraction_info() == {"mode": "ozaki_i8", "digits": 8}
+    y_oz, x_oz = oz.forward(cfg.maps), oz.adjoint(v)
+    monkeypatch.setenv("SURFH_F64_GEMM", "tma")
+    dm = built(**args, dtype="float64", adjoint_mode="exact")
+    assert dm.contraction_info()["mode"] == "dmma_tma"
+    y_dm, x_dm = dm.forward(cfg.maps), dm.adjoint(v)
+    monkeypatch.setenv("SURFH_F64_GEMM", "mma")
+    assert built(**args, dtype="float64").contraction_info()["mode"] == "mma_sync"
+    assert rel(y_oz, y_dm) <= 1e-13 and rel(x_oz, x_dm) <= 1e-13
+    monkeypatch.setenv("SURFH_F64_GEMM", "ozaki")
+    for digits, tol in ((7, 1e-11), (6, 1e-9)):
+        monkeypatch.setenv("SURFH_OZAKI_DIGITS", str(digits))
+        m = built(**args, dtype="float64", adjoint_mode="exact")
+        assert m.contraction_info() == {"mode": "ozaki_i8", "digits": digits}
+        assert rel(m.forward(cfg.maps), y_dm) <= tol and rel(m.adjoint(v), x_dm) <= tol
+    monkeypatch.delenv("SURFH_OZAKI_DIGITS")
+    monkeypatch.delenv("SURFH_F64_GEMM")
+    f32 = built(**args, dtype="float32", adjoint_mode="exact")
+    assert f32.contraction_info() == {"mode": "ozaki_i8", "digits": 4}
+    assert rel(f32.forward(cfg.maps), y_dm) <= 1e-5 and rel(f32.adjoint(v), x_dm) <= 1e-5
+    monkeypatch.setenv("SURFH_F32_GEMM", "tf32")
+    t32 = built(**args, dtype="float32", adjoint_mode="exact")
+    assert t32.contraction_info()["mode"] == "mma_sync"
+    assert rel(t32.forward(cfg.maps), y_dm) <= 1e-5

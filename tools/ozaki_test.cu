@@ -90,9 +90,9 @@ static void run(int M, int N, int K, int reps) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    ozaki_slice_rows_kernel<S><<<(M + 7) / 8, 256>>>(dA, M, K, (size_t)K, dAd, Kp, dsa);
+    ozaki_slice_rows_kernel<S, double><<<(M + 7) / 8, 256>>>(dA, M, K, (size_t)K, dAd, Kp, dsa);
     CK(cudaEventRecord(e0));
-    for (int r = 0; r < reps; ++r) ozaki_slice_rows_kernel<S><<<(N + 7) / 8, 256>>>(dB, N, K, (size_t)K, dBd, Kp, dsb);
+    for (int r = 0; r < reps; ++r) ozaki_slice_rows_kernel<S, double><<<(N + 7) / 8, 256>>>(dB, N, K, (size_t)K, dBd, Kp, dsb);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms_slice;
@@ -126,7 +126,7 @@ static void run(int M, int N, int K, int reps) {
     g.b = digits_map(dBd, K, N, Kp, S, kOzBN);
     g.M = M; g.N = N; g.K = K; g.sa = dsa; g.sb = dsb; g.C = dC; g.cM = dcM; g.cN = dcN;
     batch.dump = ddump;
-    CK(cudaFuncSetAttribute(ozaki_gemm_kernel<S, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ozaki_smem_bytes(S)));
+    CK(cudaFuncSetAttribute(ozaki_gemm_kernel<S, CL, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ozaki_smem_bytes(S)));
     auto launch = [&]() {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(batch.tile_start[1]);
@@ -136,7 +136,7 @@ static void run(int M, int N, int K, int reps) {
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<S, CL>, batch));
+        CK(cudaLaunchKernelEx(&cfg, ozaki_gemm_kernel<S, CL, double>, batch));
     };
     launch();
     CK(cudaGetLastError());
