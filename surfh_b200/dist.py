@@ -70,12 +70,13 @@ def lambda_costs(n_lambda: int, bands: Sequence[dict], n_pix: int, bytes_per_rea
       * the two column passes of its 2-D FFT pair, the two template x OTF streams and the memset,
       * the two row passes, proportional to the row pairs in the hull of the bands covering it,
     plus, per band covering it, its share of the gather / scatter index streams (2.2 TB/s effective)
-    and of the spectral contraction (27.6 TFLOP/s on the FP64 tensor pipe)."""
+    and of the spectral contraction (56 TFLOP/s fp64-equivalent as an int8-sliced product on tcgen05, digit cutting
+    included; 130 in fp32)."""
     scale = (n_pix / 501.0) ** 2 * (bytes_per_real / 8.0) ** 0.8
     # round 2 kernels (warp-per-transform chirp-z): 7.9 ns per 1-D transform -> 2 x 251 column transforms per
     # plane = 4.0 us, 7.9 ns per row pair and direction = 15.8 ns per pair; k1 + k1^T + hull zeroing = 1.5 us
     col_passes, streams, per_pair = 4.0e-6 * scale, 1.5e-6 * scale, 15.8e-9 * (n_pix / 501.0) * (bytes_per_real / 8.0) ** 0.8
-    gemm_rate = 2.76e13 if bytes_per_real == 8 else 1.7e13
+    gemm_rate = 5.6e13 if bytes_per_real == 8 else 1.3e14
     cost = np.zeros(n_lambda)
     hull = np.zeros(n_lambda)
     for b in bands:
