@@ -802,11 +802,23 @@ template <typename T> struct ModelImpl : surfh_model {
     int ozaki_digits = ozaki_digits_env(std::is_same<T, double>::value);
     void gemm_grouped_f64_tma(double* y, bool adjoint, cudaStream_t st);
     // ---- the sliced contraction on tcgen05 (kernels_ozaki.cuh) -------------------------------------------
-    template <int S> static void ozaki_slice(const T* x, int rows, int k, size_t ld, DevBuf& digits, int pitch, DevBuf& scale,
-                                             cudaStream_t st) {
-        ozaki_slice_rows_kernel<S, T><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, k, ld, digits.as<int8_t>(), pitch,
-                                                                         scale.as<double>());
-    }
+    // cuts the rows of up to kMaxGemmGroup matrices into int8 digit planes + row scales: one launch, one CTA per row
+    struct SliceJobs {
+        OzSliceBatch batch;
+        SliceJobs() { batch.count = 0; batch.row_start[0] = 0; }
+        void add(const T* x, int rows, int k, size_t ld, DevBuf& digits, int pitch, DevBuf& scale) {
+            OzSliceJob& j = batch.j[batch.count];
+            j.x = x; j.digits = digits.as<int8_t>(); j.scale = scale.as<double>(); j.ld = ld; j.rows = rows; j.K = k; j.Kp = pitch;
+            batch.row_start[batch.count + 1] = batch.row_start[batch.count] + rows;
+            batch.count++;
+        }
+        bool full() const { return batch.count == kMaxGemmGroup; }
+        template <int S> void launch(cudaStream_t st) {
+            if (batch.count == 0) return;
+            ozaki_slice_rows_kernel<S, T><<<batch.row_start[batch.count], 256, 0, st>>>(batch);
+            batch.count = 0;
+        }
+    };
     template <typename F> void with_digits(F&& f) {   // f(std::integral_constant<int, S>) for this handle's digit count
         if (std::is_same<T, float>::value) return f(std::integral_constant<int, 4>());
         if (ozaki_digits == 6) return f(std::integral_constant<int, 6>());
@@ -829,9 +841,10 @@ template <typename T> struct ModelImpl : surfh_model {
         b.oz_syk.alloc((size_t)b.Nn * sizeof(double));
         // the LSF and its transpose are constant: cut them into digits once
         with_digits([&](auto s_) {
-            constexpr int SS = decltype(s_)::value;
-            ozaki_slice<SS>(b.lsf.template as<T>(), b.nd, b.KB, (size_t)b.KBp, b.oz_w, b.oz_kq, b.oz_sw, 0);
-            ozaki_slice<SS>(b.lsf_t.template as<T>(), b.KB, b.nd, (size_t)b.ndp, b.oz_wt, b.oz_ndq, b.oz_swt, 0);
+            SliceJobs jobs;
+            jobs.add(b.lsf.template as<T>(), b.nd, b.KB, (size_t)b.KBp, b.oz_w, b.oz_kq, b.oz_sw);
+            jobs.add(b.lsf_t.template as<T>(), b.KB, b.nd, (size_t)b.ndp, b.oz_wt, b.oz_ndq, b.oz_swt);
+            jobs.template launch<decltype(s_)::value>(0);
         });
         SURFH_CUDA(cudaGetLastError());
         SURFH_CUDA(cudaDeviceSynchronize());
@@ -871,18 +884,22 @@ template <typename T> struct ModelImpl : surfh_model {
                 const BandT<T>& b = *bands[j];
                 bytes += adjoint ? (2.0 * sizeof(T) + S) * (double)b.out_size : (sizeof(T) + S) * (double)b.Nn * b.KB;
             }
-            Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, 0, (int)lsf_bands.size() * (adjoint ? 2 : 1), true);
+            Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, 0,
+                     (adjoint ? (int)lsf_bands.size() : 0) + ceil_div(lsf_bands.size(), kMaxGemmGroup), true);
+            SliceJobs jobs;
             for (size_t j : lsf_bands) {
                 BandT<T>& b = *bands[j];
                 if (adjoint) {
                     const size_t n = (size_t)b.Nn * b.nd;
                     detector_to_kfast_kernel<T><<<ceil_div(n, 256), 256, 0, st>>>(y + b.out_offset, b.na, b.nd, b.Nn, b.ndp,
                                                                                    b.yk.template as<T>());
-                    ozaki_slice<S>(b.yk.template as<T>(), b.Nn, b.nd, (size_t)b.ndp, b.oz_yk, b.oz_ndq, b.oz_syk, st);
+                    jobs.add(b.yk.template as<T>(), b.Nn, b.nd, (size_t)b.ndp, b.oz_yk, b.oz_ndq, b.oz_syk);
                 } else {
-                    ozaki_slice<S>(b.G.template as<T>(), b.Nn, b.KB, (size_t)b.g_col, b.oz_g, b.oz_kq, b.oz_sg, st);
+                    jobs.add(b.G.template as<T>(), b.Nn, b.KB, (size_t)b.g_col, b.oz_g, b.oz_kq, b.oz_sg);
                 }
+                if (jobs.full()) jobs.template launch<S>(st);
             }
+            jobs.template launch<S>(st);
             SURFH_CUDA(cudaGetLastError());
         }
         for (size_t first = 0; first < lsf_bands.size(); first += kMaxGemmGroup) {

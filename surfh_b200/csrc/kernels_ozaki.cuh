@@ -72,37 +72,86 @@ struct OzakiBatch {
 };
 
 // ---- digit extraction ---------------------------------------------------------------------------------------
-// One warp per row: row maximum -> exponent e -> S int8 digit planes + the scale 2^(e-6).
-// X: rows at pitch ld (elements); digits: [S][rows][Kp] (Kp multiple of 16, >= K; the pad is written as zero).
+// One CTA per row, all rows of up to kMaxGemmGroup matrices in one launch: row maximum (block reduction) -> exponent
+// e -> S int8 digit planes + the scale 2^(e-6).  A thread owns 4 consecutive elements per sweep: two 16-byte loads
+// (8-byte for fp32), one 4-byte store per digit plane, both coalesced across the warp.  Rounding to the nearest
+// integer is the add-and-subtract of 1.5 * 2^52, whose sum also carries the integer in its low word.
+struct OzSliceJob {
+    const void* x;        // rows at pitch ld (elements, even)
+    int8_t* digits;       // [S][rows][Kp], Kp multiple of 16 and >= K; the pad is written as zero
+    double* scale;        // [rows]
+    size_t ld;
+    int rows, K, Kp;
+};
+struct OzSliceBatch {
+    int count;
+    int row_start[kMaxGemmGroup + 1];
+    OzSliceJob j[kMaxGemmGroup];
+};
+
+template <typename TIn> __device__ __forceinline__ void oz_load4(const TIn* x, int k0, int K, double* v);
+template <> __device__ __forceinline__ void oz_load4<double>(const double* x, int k0, int K, double* v) {
+    if (k0 + 3 < K) {
+        const double2 a = *reinterpret_cast<const double2*>(x + k0), b = *reinterpret_cast<const double2*>(x + k0 + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = k0 + j < K ? x[k0 + j] : 0.0;
+    }
+}
+template <> __device__ __forceinline__ void oz_load4<float>(const float* x, int k0, int K, double* v) {
+    if (k0 + 3 < K) {
+        const float2 a = *reinterpret_cast<const float2*>(x + k0), b = *reinterpret_cast<const float2*>(x + k0 + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = k0 + j < K ? (double)x[k0 + j] : 0.0;
+    }
+}
+
 template <int S, typename TIn>
 __global__ void __launch_bounds__(256)
-ozaki_slice_rows_kernel(const TIn* __restrict__ X, int rows, int K, size_t ld, int8_t* __restrict__ digits, int Kp,
-                        double* __restrict__ scale) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const TIn* x = X + (size_t)row * ld;
+ozaki_slice_rows_kernel(const __grid_constant__ OzSliceBatch batch) {
+    __shared__ double red[8];
+    int ji = 0;
+    while (ji + 1 < batch.count && (int)blockIdx.x >= batch.row_start[ji + 1]) ++ji;
+    const OzSliceJob& job = batch.j[ji];
+    const int row = blockIdx.x - batch.row_start[ji], K = job.K, Kp = job.Kp;
+    const TIn* x = static_cast<const TIn*>(job.x) + (size_t)row * job.ld;
     double amax = 0.0;
-    for (int k = lane; k < K; k += 32) amax = fmax(amax, fabs((double)x[k]));
+    for (int k0 = 4 * threadIdx.x; k0 < K; k0 += 4 * 256) {
+        double v[4];
+        oz_load4<TIn>(x, k0, K, v);
+        amax = fmax(fmax(amax, fmax(fabs(v[0]), fabs(v[1]))), fmax(fabs(v[2]), fabs(v[3])));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) amax = fmax(amax, red[w]);
     // |x| < 2^e (ilogb(amax) + 1); an all-zero row keeps e = 0
     const int e = amax > 0.0 ? ilogb(amax) + 1 : 0;
-    if (lane == 0) scale[row] = scalbn(1.0, e - 6);
-    const size_t plane = (size_t)rows * Kp;
-    int8_t* drow = digits + (size_t)row * Kp;
-    for (int k0 = 4 * lane; k0 < Kp; k0 += 128) {
+    if (threadIdx.x == 0) job.scale[row] = scalbn(1.0, e - 6);
+    const double up = scalbn(1.0, 6 - e);             // exact power of two
+    constexpr double kMagic = 6755399441055744.0;     // 1.5 * 2^52
+    const size_t plane = (size_t)job.rows * Kp;
+    int8_t* drow = job.digits + (size_t)row * Kp;
+    for (int k0 = 4 * threadIdx.x; k0 < Kp; k0 += 4 * 256) {
+        double v[4];
+        oz_load4<TIn>(x, k0, K, v);
         uint32_t word[S];
 #pragma unroll
         for (int p = 0; p < S; ++p) word[p] = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int k = k0 + j;
-            double r = k < K ? scalbn((double)x[k], 6 - e) : 0.0;     // |r| < 64
+            double r = v[j] * up;                          // |r| < 64
 #pragma unroll
             for (int p = 0; p < S; ++p) {
-                const double d = rint(r);
-                word[p] |= ((uint32_t)(int)d & 0xffu) << (8 * j);
-                r = (r - d) * 128.0;                           // |r - d| <= 0.5 -> |next| <= 64
+                const double t = r + kMagic;               // round to nearest; the integer sits in the low word
+                word[p] |= ((uint32_t)__double2loint(t) & 0xffu) << (8 * j);
+                const double d = t - kMagic;
+                r = (r - d) * 128.0;                       // |r - d| <= 0.5 -> |next| <= 64, exact
             }
         }
 #pragma unroll

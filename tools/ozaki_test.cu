@@ -90,9 +90,14 @@ static void run(int M, int N, int K, int reps) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    ozaki_slice_rows_kernel<S, double><<<(M + 7) / 8, 256>>>(dA, M, K, (size_t)K, dAd, Kp, dsa);
+    OzSliceBatch sa_job, sb_job;
+    std::memset(&sa_job, 0, sizeof(sa_job));
+    std::memset(&sb_job, 0, sizeof(sb_job));
+    sa_job.count = 1; sa_job.row_start[1] = M; sa_job.j[0] = OzSliceJob{dA, dAd, dsa, (size_t)K, M, K, Kp};
+    sb_job.count = 1; sb_job.row_start[1] = N; sb_job.j[0] = OzSliceJob{dB, dBd, dsb, (size_t)K, N, K, Kp};
+    ozaki_slice_rows_kernel<S, double><<<M, 256>>>(sa_job);
     CK(cudaEventRecord(e0));
-    for (int r = 0; r < reps; ++r) ozaki_slice_rows_kernel<S, double><<<(N + 7) / 8, 256>>>(dB, N, K, (size_t)K, dBd, Kp, dsb);
+    for (int r = 0; r < reps; ++r) ozaki_slice_rows_kernel<S, double><<<N, 256>>>(sb_job);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms_slice;
