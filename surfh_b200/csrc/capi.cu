@@ -295,6 +295,11 @@ template <typename T> struct ModelImpl : surfh_model {
     size_t cplane = 0;  // elements between planes of the working cube: `plane` rounded up to even with the hand-written
                         // FFT, so that every row pair starts 16-byte aligned (one TMA bulk copy stages it)
     DevBuf fft_work;
+    // second lane of the chunk pipeline (two chunks in flight on two streams, see forward / adjoint)
+    DevBuf spec2, cubebuf2, zbuf2;
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_acc[2] = {nullptr, nullptr};
+    bool two_lanes = false;
     DevBuf zbuf;      // [max(chunk, K)][z_plane] complex: intermediate of the hand-written FFT passes
     OwnFft2d<T> ownfft;
     DevBuf plane_pairs;                   // [Nl] int2 (first row pair, count) each plane's FFT must cover
@@ -312,6 +317,9 @@ template <typename T> struct ModelImpl : surfh_model {
 
     ~ModelImpl() override {
         for (auto& kv : plans) cufftDestroy(kv.second);
+        if (aux_stream) cudaStreamDestroy(aux_stream);
+        for (cudaEvent_t e : {ev_fork, ev_join, ev_acc[0], ev_acc[1]})
+            if (e) cudaEventDestroy(e);
     }
 
     void init(const surfh_model_desc* d) {
@@ -604,6 +612,26 @@ template <typename T> struct ModelImpl : surfh_model {
         if (use_own_fft) {
             ownfft.init(Na, Nb);
             zbuf.alloc((size_t)std::max(chunk, K) * ownfft.z_plane() * sizeof(C));
+            // Optional (SURFH_STREAMS=2, off by default): two chunks in flight, chunk i on lane i % 2 (own stream, own
+            // spectrum / cube / intermediate buffers), so that the HBM-bound template x OTF stream of one chunk could
+            // share the SMs with the LSU-bound slit gather / scatter of its neighbour.  Measured on C4: 33.7 ms per
+            // application against 33.1 ms on one stream -- the persistent FFT kernels need whole SMs (225 KB of shared
+            // memory, every register), so the other lane's small CTAs only delay their start.  Kept for A/B runs.
+            int n_chunks = 0;
+            for (auto& r : ranges) n_chunks += ceil_div(r.second - r.first, chunk);
+            const char* e_streams = std::getenv("SURFH_STREAMS");
+            two_lanes = n_chunks > 1 && e_streams && std::atoi(e_streams) == 2;
+            if (two_lanes) {
+                spec2.alloc(spec.bytes);
+                SURFH_CUDA(cudaMemset(spec2.p, 0, spec2.bytes));
+                cubebuf2.alloc(cubebuf.bytes);
+                zbuf2.alloc((size_t)chunk * ownfft.z_plane() * sizeof(C));
+                SURFH_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
+                SURFH_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+                SURFH_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+                SURFH_CUDA(cudaEventCreateWithFlags(&ev_acc[0], cudaEventDisableTiming));
+                SURFH_CUDA(cudaEventCreateWithFlags(&ev_acc[1], cudaEventDisableTiming));
+            }
             std::vector<int2> pr(Nl, make_int2(0, 0));
             plane_pair_cnt.assign(Nl, 0);
             for (int l = 0; l < Nl; ++l) {
@@ -661,7 +689,7 @@ template <typename T> struct ModelImpl : surfh_model {
         return m;
     }
     int64_t workspace_bytes() const override {
-        int64_t t = otf.bytes + tpl.bytes + tpl_raw.bytes + xhat.bytes + spec.bytes + cubebuf.bytes + fft_work.bytes + zbuf.bytes +
+        int64_t t = otf.bytes + tpl.bytes + tpl_raw.bytes + xhat.bytes + spec.bytes + cubebuf.bytes + fft_work.bytes + zbuf.bytes + spec2.bytes + cubebuf2.bytes + zbuf2.bytes +
                     y_internal.bytes + x_stage.bytes + y_stage.bytes + dbl_stage.bytes;
         for (auto& b : bands)
             t += b->lsf.bytes + b->lsf_t.bytes + b->yk.bytes + b->G.bytes + b->grid_base.bytes + b->grid_frac.bytes +
@@ -684,15 +712,18 @@ template <typename T> struct ModelImpl : surfh_model {
     }
 
     // ---- launch helpers ---------------------------------------------------------------------
-    template <int KK> void launch_lmm_fwd(int c0, int nl, cudaStream_t st) {
+    DevBuf& spec_of(int lane) { return lane ? spec2 : spec; }
+    DevBuf& cube_of(int lane) { return lane ? cubebuf2 : cubebuf; }
+    DevBuf& zbuf_of(int lane) { return lane ? zbuf2 : zbuf; }
+    template <int KK> void launch_lmm_fwd(int c0, int nl, cudaStream_t st, int lane) {
         dim3 grid(ceil_div(nfp, 256), ceil_div(nl, kLmmLsub));
         lmm_otf_fwd_kernel<T, KK><<<grid, 256, 0, st>>>(xhat.as<C>(), otf.as<C>() + (size_t)c0 * nfp, tpl.as<T>(), Nl,
-                                                        c0, nl, nfp, spec.as<C>());
+                                                        c0, nl, nfp, spec_of(lane).template as<C>());
     }
-    template <int KK> void launch_lmm_adj(int c0, int nl, bool accumulate, cudaStream_t st) {
+    template <int KK> void launch_lmm_adj(int c0, int nl, bool accumulate, cudaStream_t st, int lane) {
         dim3 grid(ceil_div(nfp, 32)), block(32, kAdjLanes);
-        lmm_otf_adj_kernel<T, KK><<<grid, block, 0, st>>>(spec.as<C>(), otf.as<C>() + (size_t)c0 * nfp, tpl.as<T>(),
-                                                          Nl, c0, nl, nfp, xhat.as<C>(), accumulate ? 1 : 0);
+        lmm_otf_adj_kernel<T, KK><<<grid, block, 0, st>>>(spec_of(lane).template as<C>(), otf.as<C>() + (size_t)c0 * nfp,
+                                                          tpl.as<T>(), Nl, c0, nl, nfp, xhat.as<C>(), accumulate ? 1 : 0);
     }
     template <int KK> void launch_maps_to_cube(const T* maps, float* cube, cudaStream_t st) {
         dim3 grid(ceil_div(plane, 256), ceil_div(Nl, 32));
@@ -737,7 +768,8 @@ template <typename T> struct ModelImpl : surfh_model {
     // prune_c0 >= 0: the real side is the working cube of planes [prune_c0, prune_c0 + batch), of which only
     // the rows some band touches matter (C2R: produced; R2C: non-zero)
     // real_stride: elements between the real planes (0 = `plane`: caller-owned contiguous maps / cubes)
-    void fft_exec(int kind, int batch, void* in, void* out, cudaStream_t st, int prune_c0 = -1, size_t real_stride = 0) {
+    void fft_exec(int kind, int batch, void* in, void* out, cudaStream_t st, int prune_c0 = -1, size_t real_stride = 0,
+                  int lane = 0) {
         if (real_stride == 0) real_stride = plane;
         if (use_own_fft) {
             const int2* pr = nullptr;
@@ -747,11 +779,12 @@ template <typename T> struct ModelImpl : surfh_model {
                 for (int l = prune_c0; l < prune_c0 + batch; ++l) n_pairs += plane_pair_cnt[l];
             }
             if (kind == 0)
-                ownfft.r2c(reinterpret_cast<const T*>(in), real_stride, reinterpret_cast<C*>(out), nfp, zbuf.as<C>(), batch, st,
-                           true, pr, n_pairs, /*row_slack=*/in == cubebuf.p);
+                ownfft.r2c(reinterpret_cast<const T*>(in), real_stride, reinterpret_cast<C*>(out), nfp,
+                           zbuf_of(lane).template as<C>(), batch, st, true, pr, n_pairs,
+                           /*row_slack=*/in == cubebuf.p || in == cubebuf2.p);
             else
-                ownfft.c2r(reinterpret_cast<const C*>(in), nfp, reinterpret_cast<T*>(out), real_stride, zbuf.as<C>(), batch, st,
-                           true, pr, n_pairs);
+                ownfft.c2r(reinterpret_cast<const C*>(in), nfp, reinterpret_cast<T*>(out), real_stride,
+                           zbuf_of(lane).template as<C>(), batch, st, true, pr, n_pairs);
             return;
         }
         cufftHandle p = plan(kind, batch);
@@ -984,7 +1017,7 @@ template <typename T> struct ModelImpl : surfh_model {
     static constexpr int kLB = SURFH_GATHER_LB;    // wavelengths per thread in the gather ...
     static constexpr int kLBs = SURFH_SCATTER_LB;  // ... and in the scatter
 
-    void gather_chunk(int c0, int c1, cudaStream_t st) {
+    void gather_chunk(int c0, int c1, cudaStream_t st, int lane = 0) {
         for (auto& bp : bands) {
             BandT<T>& b = *bp;
             const int lo = std::max(c0, b.l0), hi = std::min(c1, b.l0 + b.nl);
@@ -995,24 +1028,24 @@ template <typename T> struct ModelImpl : surfh_model {
             Scope sc(this, ST_SLIT_GATHER, st, bytes, 8.0 * nl * b.ncol * b.srf, 1, true);
             const int pp = std::min(b.P, 4), chunks = 4 / pp;  // see the kernel: 4 warps = pp pointings x chunks
             dim3 grid(ceil_div(b.S * b.na * b.nb, 32 * chunks), ceil_div(nl, kLB));
-            slit_gather_kernel<T, kLB><<<grid, 128, 0, st>>>(cubebuf.as<T>() + (size_t)(lo - c0) * cplane, cplane, Nb, nl,
+            slit_gather_kernel<T, kLB><<<grid, 128, 0, st>>>(cube_of(lane).template as<T>() + (size_t)(lo - c0) * cplane, cplane, Nb, nl,
                                                              b.slit_tables(),
                                                              b.G.template as<T>() + (size_t)(lo - b.l0) * b.g_l);
             SURFH_CUDA(cudaGetLastError());
         }
     }
 
-    void scatter_chunk(int c0, int c1, int mode, cudaStream_t st) {
+    void scatter_chunk(int c0, int c1, int mode, cudaStream_t st, int lane = 0) {
         if (use_own_fft && prune_rows) {
             double rows = 0;
             for (int l = c0; l < c1; ++l) rows += 2.0 * plane_pair_cnt[l];
             Scope sc(this, ST_MEMSET, st, rows * Nb * sizeof(T), 0, 1, true);
             dim3 grid(32, c1 - c0);
-            zero_row_hull_kernel<T><<<grid, 256, 0, st>>>(cubebuf.as<T>(), cplane, Na, Nb, plane_pairs.as<int2>() + c0);
+            zero_row_hull_kernel<T><<<grid, 256, 0, st>>>(cube_of(lane).template as<T>(), cplane, Na, Nb, plane_pairs.as<int2>() + c0);
             SURFH_CUDA(cudaGetLastError());
         } else {
             Scope sc(this, ST_MEMSET, st, (double)(c1 - c0) * plane * sizeof(T), 0, 1, false);
-            SURFH_CUDA(cudaMemsetAsync(cubebuf.p, 0, (size_t)(c1 - c0) * cplane * sizeof(T), st));
+            SURFH_CUDA(cudaMemsetAsync(cube_of(lane).p, 0, (size_t)(c1 - c0) * cplane * sizeof(T), st));
         }
         for (auto& bp : bands) {
             BandT<T>& b = *bp;
@@ -1024,13 +1057,27 @@ template <typename T> struct ModelImpl : surfh_model {
             Scope sc(this, ST_SLIT_SCATTER, st, bytes, 2.0 * nl * (double)b.csr_nnz[mode], 1, true);
             slit_scatter_kernel<T, kLBs><<<grid, 128, 0, st>>>(b.G.template as<T>() + (size_t)(lo - b.l0) * b.g_l, b.g_l,
                                                               nl, b.csr(mode),
-                                                              cubebuf.as<T>() + (size_t)(lo - c0) * cplane, cplane);
+                                                              cube_of(lane).template as<T>() + (size_t)(lo - c0) * cplane, cplane);
             SURFH_CUDA(cudaGetLastError());
         }
     }
 
     void require_ready() const {
         if (!finalized) throw Error(SURFH_ESTATE, "surfh_finalize has not been called");
+    }
+
+    // Chunk i of the pipeline runs on lane i % 2: the caller's stream or the handle's auxiliary stream, each with its
+    // own spectrum / cube / FFT-intermediate buffers.  fork: the auxiliary stream waits for everything queued so far
+    // on the caller's stream; join: the caller's stream waits for the auxiliary one.
+    void lanes_fork(cudaStream_t st) {
+        if (!two_lanes) return;
+        SURFH_CUDA(cudaEventRecord(ev_fork, st));
+        SURFH_CUDA(cudaStreamWaitEvent(aux_stream, ev_fork, 0));
+    }
+    void lanes_join(cudaStream_t st) {
+        if (!two_lanes) return;
+        SURFH_CUDA(cudaEventRecord(ev_join, aux_stream));
+        SURFH_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     }
 
     void forward(const void* xv, void* yv, cudaStream_t st) override {
@@ -1042,32 +1089,37 @@ template <typename T> struct ModelImpl : surfh_model {
             Scope sc(this, ST_RFFT_MAPS, st, fft_bytes(K, -1), fft_flops(K, -1), fft_launches(), use_own_fft);
             fft_exec(0, K, const_cast<T*>(x), xhat.p, st);
         }
+        lanes_fork(st);
+        int i = 0;
         for (auto& r : ranges) {
-            for (int c0 = r.first; c0 < r.second; c0 += chunk) {
+            for (int c0 = r.first; c0 < r.second; c0 += chunk, ++i) {
                 const int c1 = std::min(r.second, c0 + chunk), nl = c1 - c0;
+                const int lane = two_lanes ? (i & 1) : 0;
+                cudaStream_t ls = lane ? aux_stream : st;
                 if (K > 0) {
-                    Scope sc(this, ST_LMM_OTF_FWD, st, (double)nl * nf * sizeof(C) * 2 + (double)K * nf * sizeof(C),
+                    Scope sc(this, ST_LMM_OTF_FWD, ls, (double)nl * nf * sizeof(C) * 2 + (double)K * nf * sizeof(C),
                              (4.0 * K + 6.0) * nl * nf, 1, true);
-                    SURFH_DISPATCH_K(launch_lmm_fwd, c0, nl, st);
+                    SURFH_DISPATCH_K(launch_lmm_fwd, c0, nl, ls, lane);
                     SURFH_CUDA(cudaGetLastError());
                 } else {
                     {
-                        Scope sc(this, ST_RFFT_CUBE, st, fft_bytes(nl, -1), fft_flops(nl, -1), fft_launches(), use_own_fft);
-                        fft_exec(0, nl, const_cast<T*>(x) + (size_t)c0 * plane, spec.p, st);
+                        Scope sc(this, ST_RFFT_CUBE, ls, fft_bytes(nl, -1), fft_flops(nl, -1), fft_launches(), use_own_fft);
+                        fft_exec(0, nl, const_cast<T*>(x) + (size_t)c0 * plane, spec_of(lane).p, ls, -1, 0, lane);
                     }
-                    Scope sc(this, ST_LMM_OTF_FWD, st, (double)nl * nf * sizeof(C) * 3, 6.0 * nl * nf, 1, true);
+                    Scope sc(this, ST_LMM_OTF_FWD, ls, (double)nl * nf * sizeof(C) * 3, 6.0 * nl * nf, 1, true);
                     const size_t n = (size_t)nl * nfp;
-                    otf_mul_kernel<T, false><<<ceil_div(n, 256), 256, 0, st>>>(
-                        spec.as<C>(), otf.as<C>() + (size_t)c0 * nfp, n, (T)(1.0 / ((double)Na * Nb)));
+                    otf_mul_kernel<T, false><<<ceil_div(n, 256), 256, 0, ls>>>(
+                        spec_of(lane).template as<C>(), otf.as<C>() + (size_t)c0 * nfp, n, (T)(1.0 / ((double)Na * Nb)));
                     SURFH_CUDA(cudaGetLastError());
                 }
                 {
-                    Scope sc(this, ST_IRFFT_CUBE, st, fft_bytes(nl, c0), fft_flops(nl, c0), fft_launches(), use_own_fft);
-                    fft_exec(1, nl, spec.p, cubebuf.p, st, c0, cplane);
+                    Scope sc(this, ST_IRFFT_CUBE, ls, fft_bytes(nl, c0), fft_flops(nl, c0), fft_launches(), use_own_fft);
+                    fft_exec(1, nl, spec_of(lane).p, cube_of(lane).p, ls, c0, cplane, lane);
                 }
-                gather_chunk(c0, c1, st);
+                gather_chunk(c0, c1, ls, lane);
             }
         }
+        lanes_join(st);
         gemm_all(y, false, st);
     }
 
@@ -1082,34 +1134,45 @@ template <typename T> struct ModelImpl : surfh_model {
             Scope sc(this, ST_MEMSET, st, (double)Nl * plane * sizeof(T), 0, 1, false);
             SURFH_CUDA(cudaMemsetAsync(x, 0, (size_t)Nl * plane * sizeof(T), st));
         }
+        lanes_fork(st);
         bool first = true;
+        int i = 0;
         for (auto& r : ranges) {
-            for (int c0 = r.first; c0 < r.second; c0 += chunk) {
+            for (int c0 = r.first; c0 < r.second; c0 += chunk, ++i) {
                 const int c1 = std::min(r.second, c0 + chunk), nl = c1 - c0;
-                scatter_chunk(c0, c1, mode, st);
+                const int lane = two_lanes ? (i & 1) : 0;
+                cudaStream_t ls = lane ? aux_stream : st;
+                scatter_chunk(c0, c1, mode, ls, lane);
                 {
-                    Scope sc(this, ST_RFFT_CUBE, st, fft_bytes(nl, c0), fft_flops(nl, c0), fft_launches(), use_own_fft);
-                    fft_exec(0, nl, cubebuf.p, spec.p, st, c0, cplane);
+                    Scope sc(this, ST_RFFT_CUBE, ls, fft_bytes(nl, c0), fft_flops(nl, c0), fft_launches(), use_own_fft);
+                    fft_exec(0, nl, cube_of(lane).p, spec_of(lane).p, ls, c0, cplane, lane);
                 }
                 if (K > 0) {
-                    Scope sc(this, ST_LMM_OTF_ADJ, st, (double)nl * nf * sizeof(C) * 2 + (double)K * nf * sizeof(C),
-                             (4.0 * K + 6.0) * nl * nf, 1, true);
-                    SURFH_DISPATCH_K(launch_lmm_adj, c0, nl, !first, st);
-                    SURFH_CUDA(cudaGetLastError());
-                } else {
+                    // the reduction over wavelengths accumulates chunk after chunk into the K map spectra: chunk i's
+                    // stream waits for chunk i - 1's accumulation (fixed summation order: bitwise reproducible)
+                    if (two_lanes && !first) SURFH_CUDA(cudaStreamWaitEvent(ls, ev_acc[lane ^ 1], 0));
                     {
-                        Scope sc(this, ST_LMM_OTF_ADJ, st, (double)nl * nf * sizeof(C) * 3, 6.0 * nl * nf, 1, true);
-                        const size_t n = (size_t)nl * nfp;
-                        otf_mul_kernel<T, true><<<ceil_div(n, 256), 256, 0, st>>>(
-                            spec.as<C>(), otf.as<C>() + (size_t)c0 * nfp, n, (T)(1.0 / ((double)Na * Nb)));
+                        Scope sc(this, ST_LMM_OTF_ADJ, ls, (double)nl * nf * sizeof(C) * 2 + (double)K * nf * sizeof(C),
+                                 (4.0 * K + 6.0) * nl * nf, 1, true);
+                        SURFH_DISPATCH_K(launch_lmm_adj, c0, nl, !first, ls, lane);
                         SURFH_CUDA(cudaGetLastError());
                     }
-                    Scope sc(this, ST_IRFFT_CUBE, st, fft_bytes(nl, -1), fft_flops(nl, -1), fft_launches(), use_own_fft);
-                    fft_exec(1, nl, spec.p, x + (size_t)c0 * plane, st);
+                    if (two_lanes) SURFH_CUDA(cudaEventRecord(ev_acc[lane], ls));
+                } else {
+                    {
+                        Scope sc(this, ST_LMM_OTF_ADJ, ls, (double)nl * nf * sizeof(C) * 3, 6.0 * nl * nf, 1, true);
+                        const size_t n = (size_t)nl * nfp;
+                        otf_mul_kernel<T, true><<<ceil_div(n, 256), 256, 0, ls>>>(
+                            spec_of(lane).template as<C>(), otf.as<C>() + (size_t)c0 * nfp, n, (T)(1.0 / ((double)Na * Nb)));
+                        SURFH_CUDA(cudaGetLastError());
+                    }
+                    Scope sc(this, ST_IRFFT_CUBE, ls, fft_bytes(nl, -1), fft_flops(nl, -1), fft_launches(), use_own_fft);
+                    fft_exec(1, nl, spec_of(lane).p, x + (size_t)c0 * plane, ls, -1, 0, lane);
                 }
                 first = false;
             }
         }
+        lanes_join(st);
         if (K > 0) {
             Scope sc(this, ST_IRFFT_MAPS, st, fft_bytes(K, -1), fft_flops(K, -1), fft_launches(), use_own_fft);
             fft_exec(1, K, xhat.p, x, st);
