@@ -1,9 +1,12 @@
-# the round's standard check: GPU parity suite, smoke, default bench line, reference arm; then the ncu passes of profiles/
+# the round's standard check: GPU parity suite, smoke, default bench line, reference arm, the other configurations,
+# one ncu --set full capture of the tcgen05 contraction (every step under its own timeout)
 set -x
-python -m pytest tests -m gpu -q -s --durations=5 > gpurun_out/pytest_gpu.log 2>&1; tail -12 gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
-python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -2 gpurun_out/bench_default.err
-M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,lts__t_sector_hit_rate.pct,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active
-ncu --metrics $M --clock-control none -s 601 -c 114 --csv --log-file gpurun_out/r02_app_metrics_c4.csv python bench.py --config c4 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --solve-iters 0 > gpurun_out/ncu_app.log 2>&1
-tail -2 gpurun_out/ncu_app.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --solve-iters 0 > gpurun_out/ncu_l.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q -s --durations=5 > gpurun_out/pytest_gpu.log 2>&1; tail -12 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
+timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -2 gpurun_out/bench_default.err
+timeout 600 python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; tail -2 gpurun_out/bench_reference.err
+timeout 300 python bench.py --dtype float32 --no-cpu-baseline > gpurun_out/bench_c4_f32.json 2> gpurun_out/bench_c4_f32.err; tail -1 gpurun_out/bench_c4_f32.err
+for c in c2 c3 c5; do
+timeout 300 python bench.py --config $c --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; tail -1 gpurun_out/bench_$c.err
+done
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:ozaki_gemm -s 2 -c 2 -o gpurun_out/r02_ozaki_gemm python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --solve-iters 0 > gpurun_out/ncu_oz.log 2>&1; tail -2 gpurun_out/ncu_oz.log

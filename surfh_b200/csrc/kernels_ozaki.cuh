@@ -119,20 +119,25 @@ ozaki_slice_rows_kernel(const __grid_constant__ OzSliceBatch batch) {
     const int row = blockIdx.x - batch.row_start[ji], K = job.K, Kp = job.Kp;
     const TIn* x = static_cast<const TIn*>(job.x) + (size_t)row * job.ld;
     double amax = 0.0;
+    int bad = 0;   // a NaN or an infinity in the row: fmax would drop the NaN and the digits of either are meaningless
     for (int k0 = 4 * threadIdx.x; k0 < K; k0 += 4 * 256) {
         double v[4];
         oz_load4<TIn>(x, k0, K, v);
-        amax = fmax(fmax(amax, fmax(fabs(v[0]), fabs(v[1]))), fmax(fabs(v[2]), fabs(v[3])));
+        const double m = fmax(fmax(fabs(v[0]), fabs(v[1])), fmax(fabs(v[2]), fabs(v[3])));
+        bad |= !(fabs(v[0]) + fabs(v[1]) + fabs(v[2]) + fabs(v[3]) <= 1.7976931348623157e308);
+        amax = fmax(amax, m);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
-    __syncthreads();
+    bad = __syncthreads_or(bad);
 #pragma unroll
     for (int w = 0; w < 8; ++w) amax = fmax(amax, red[w]);
-    // |x| < 2^e (ilogb(amax) + 1); an all-zero row keeps e = 0
-    const int e = amax > 0.0 ? ilogb(amax) + 1 : 0;
-    if (threadIdx.x == 0) job.scale[row] = scalbn(1.0, e - 6);
+    // |x| < 2^e (ilogb(amax) + 1); an all-zero row keeps e = 0; rows below 2^-1000 are cut relative to 2^-1000 (the
+    // scales 2^(e-6) and 2^(6-e) stay normal numbers)
+    const int e = amax > 0.0 ? max(ilogb(amax) + 1, -1000) : 0;
+    // a row holding a NaN / infinity poisons its whole row (or column) of the product, like the fp64 product would
+    if (threadIdx.x == 0) job.scale[row] = bad ? __longlong_as_double(0x7ff8000000000000ll) : scalbn(1.0, e - 6);
     const double up = scalbn(1.0, 6 - e);             // exact power of two
     constexpr double kMagic = 6755399441055744.0;     // 1.5 * 2^52
     const size_t plane = (size_t)job.rows * Kp;

@@ -217,3 +217,21 @@ def test_contraction_backends_agree(built, monkeypatch):
     t32 = built(**args, dtype="float32", adjoint_mode="exact")
     assert t32.contraction_info()["mode"] == "mma_sync"
     assert rel(t32.forward(cfg.maps), y_dm) <= 1e-5
+
+
+def test_contraction_nonfinite_and_tiny_inputs(built):
+    """The sliced contraction scales every row by its own power of two: a NaN in the input must still poison the
+    output (the row maximum alone would drop it), and inputs of any magnitude keep their relative accuracy."""
+    cfg = CASES["mini_2band_4p"]()
+    gpu = built(**cfg.model_args(), dtype="float64", adjoint_mode="exact")
+    y = gpu.forward(cfg.maps)
+    tiny = gpu.forward(1e-290 * cfg.maps)
+    assert rel(tiny * 1e290, y) <= 1e-13
+    huge = gpu.forward(1e250 * cfg.maps)
+    assert rel(huge * 1e-250, y) <= 1e-13
+    x = cfg.maps.copy()
+    x[0, x.shape[1] // 2, x.shape[2] // 2] = np.nan
+    assert np.isnan(gpu.forward(x)).any()
+    v = np.random.default_rng(3).standard_normal(gpu.osize)
+    v[17] = np.inf
+    assert not np.isfinite(gpu.adjoint(v)).all()
