@@ -95,15 +95,11 @@ def measured_fp_peak(torch, tdtype):
 
 
 def measured_int8_peak():
-    """Dense int8 tensor rate (TOP/s): twice the measured dense bf16 rate of this pool's B200s (MEASURED_PEAKS.json,
-    the sustained figure: the contraction runs inside a long step); nominal 4500 when the file is absent."""
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            p = json.load(f)
-        bf16 = float(p.get("bf16_tflops_sustained") or p["bf16_tflops"])
-        return 2.0 * bf16, "2 x measured sustained dense bf16 (MEASURED_PEAKS.json): int8 runs at twice the bf16 rate on B200"
-    return 4500.0, "nominal dense int8 (B200_PROFILING.md)"
+    """Dense int8 tensor rate (TOP/s).  MEASURED_PEAKS.json holds no int8 figure (its dense bf16 GEMM runs power-capped
+    at 1312 MHz; the int8 contraction holds 1965 MHz and exceeds twice that bf16 rate), so the denominator is the
+    recipe's nominal dense 8-bit rate: 4.5 POP/s (B200_PROFILING.md; 16384 ops per clock and SM x 148 SMs x 1.965 GHz
+    = 4.76 is what ncu's sm__ops_path_tensor_op_utcimma peak uses)."""
+    return 4500.0, "nominal dense 8-bit tensor rate, 4.5 POP/s (B200_PROFILING.md: MEASURED_PEAKS.json has no int8 figure)"
 
 
 def ncu_traffic():
