@@ -887,11 +887,13 @@ template <typename T> struct ModelImpl : surfh_model {
         b.ozmap_yk = tensor_map_digits(b.oz_yk.p, b.nd, b.Nn, b.oz_ndq, S, kOzBN);
         b.oz_ready = true;
     }
+    int oz_resident_ctas = 0;   // one wave of co-resident clusters: the persistent contraction's grid
     void set_ozaki_attributes() {
         with_digits([&](auto s_) {
             constexpr int SS = decltype(s_)::value;
             SURFH_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<SS, kOzCluster, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)ozaki_smem_bytes(SS)));
+            oz_resident_ctas = ozaki_max_resident_ctas(ozaki_gemm_kernel<SS, kOzCluster, T>, kOzCluster, ozaki_smem_bytes(SS));
         });
     }
     bool ozaki_usable() const {
@@ -961,7 +963,8 @@ template <typename T> struct ModelImpl : surfh_model {
             }
             Scope sc(this, adjoint ? ST_GEMM_ADJ : ST_GEMM_FWD, st, bytes, flops, 1, true);
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)batch.tile_start[batch.count]);
+            const int n_tiles = batch.tile_start[batch.count];
+            cfg.gridDim = dim3((unsigned)(oz_resident_ctas > 0 ? std::min(n_tiles, oz_resident_ctas) : n_tiles));
             cfg.blockDim = dim3(kOzThreads);
             cfg.dynamicSmemBytes = ozaki_smem_bytes(S);
             cfg.stream = st;

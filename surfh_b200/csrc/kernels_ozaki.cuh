@@ -71,6 +71,27 @@ struct OzakiBatch {
     int32_t* dump;   // debugging: when non-null, CTA 0 also writes its raw level accumulators [S][128][64]
 };
 
+// Host side: one wave of co-resident clusters for the persistent kernel (0 when the query fails).
+template <typename Kernel> inline int ozaki_max_resident_ctas(Kernel kernel, int cluster, size_t smem_bytes) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cluster * 64));
+    cfg.blockDim = dim3(kOzThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n * cluster;
+}
+
 // ---- digit extraction ---------------------------------------------------------------------------------------
 // One CTA per row, all rows of up to kMaxGemmGroup matrices in one launch: row maximum (block reduction) -> exponent
 // e -> S int8 digit planes + the scale 2^(e-6).  A thread owns 4 consecutive elements per sweep: two 16-byte loads
@@ -256,9 +277,54 @@ __device__ __forceinline__ void oz_wait(void* bar, unsigned parity, int what) {
 __device__ __forceinline__ void oz_wait(void* bar, unsigned parity, int) { mbar_wait(bar, parity); }
 #endif
 
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+
+// One tile of the grouped launch: which problem, which 128 x 64 block of its C.
+struct OzTile {
+    int pi, m0, n0, n_kb;
+};
+template <int CL> __device__ __forceinline__ OzTile oz_decode_tile(const OzakiBatch& batch, int tile) {
+    OzTile t;
+    t.pi = 0;
+    while (t.pi + 1 < batch.count && tile >= batch.tile_start[t.pi + 1]) ++t.pi;
+    const OzakiProblem& g = batch.p[t.pi];
+    const int local_tile = tile - batch.tile_start[t.pi];
+    const int tiles_n = ((g.N + kOzBN - 1) / kOzBN + CL - 1) / CL * CL;   // column tiles, padded to whole clusters
+    t.m0 = (local_tile / tiles_n) * kOzBM;
+    t.n0 = (local_tile % tiles_n) * kOzBN;
+    t.n_kb = (g.K + kOzBK - 1) / kOzBK;
+    return t;
+}
+
+// Static schedule of the persistent kernel: in round r cluster c takes tile group r * n_clusters + c (even rounds) or
+// r * n_clusters + n_clusters - 1 - c (odd rounds).  The tiles are sorted by contraction length, longest first, so the
+// boustrophedon evens out the load of the clusters; every role of every CTA of a cluster walks the same sequence.
+template <int CL> struct OzSchedule {
+    int n_groups, n_clusters, c, rank, round;
+    __device__ OzSchedule(int n_tiles, int cta_rank)
+        : n_groups(n_tiles / CL), n_clusters((int)gridDim.x / CL), c((int)blockIdx.x / CL), rank(cta_rank), round(0) {}
+    // next tile of this CTA, or -1
+    __device__ int next() {
+        while (round * n_clusters < n_groups) {
+            const int g = round * n_clusters + ((round & 1) ? n_clusters - 1 - c : c);
+            ++round;
+            if (g < n_groups) return g * CL + rank;
+        }
+        return -1;
+    }
+};
+
 // CL: CTAs per cluster.  The CL CTAs of a cluster own CL neighbouring column tiles of ONE row tile: each loads 1/CL
 // of every A digit tile and multicasts it to the whole cluster (the L2 -> SM traffic, which bounds the kernel,
 // drops from 12 KB to (8 / CL + 4) KB per digit and k-block); tile_start counts CTAs (CL per cluster).
+// PERSISTENT: the grid is one wave of co-resident clusters (cudaOccupancyMaxActiveClusters); every cluster walks its
+// share of the tile groups (OzSchedule).  Tensor memory, barriers and the stage ring live for the whole
+// kernel; the producer runs ahead into the next tile while the epilogue drains the accumulators (`tmem_empty` tells the
+// MMA issuer when it may overwrite them), so only the tensor-memory read of the epilogue is not hidden.
 template <int S, int CL, typename TOut>
 __global__ void __launch_bounds__(kOzThreads, 1)
 ozaki_gemm_kernel(const __grid_constant__ OzakiBatch batch) {
@@ -273,17 +339,12 @@ ozaki_gemm_kernel(const __grid_constant__ OzakiBatch batch) {
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + kOzStages * kStage);
     unsigned long long* empty = full + kOzStages;
     unsigned long long* tmem_full = empty + kOzStages;
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(tmem_full + 1);
+    unsigned long long* tmem_empty = tmem_full + 1;
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(tmem_empty + 1);
 
-    int pi = 0;
-    while (pi + 1 < batch.count && (int)blockIdx.x >= batch.tile_start[pi + 1]) ++pi;
-    const OzakiProblem& g = batch.p[pi];
-    const int local_tile = blockIdx.x - batch.tile_start[pi];
-    const int tiles_n = ((g.N + kOzBN - 1) / kOzBN + CL - 1) / CL * CL;   // column tiles, padded to whole clusters
-    const int m0 = (local_tile / tiles_n) * kOzBM, n0 = (local_tile % tiles_n) * kOzBN;
-    const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;             // = (local_tile % tiles_n) % CL
+    const int n_tiles = batch.tile_start[batch.count];
+    const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;   // = tile % CL for every tile of this CTA
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_kb = (g.K + kOzBK - 1) / kOzBK;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -292,9 +353,8 @@ ozaki_gemm_kernel(const __grid_constant__ OzakiBatch batch) {
             mbar_init(&empty[s], CL);   // every CTA of the cluster writes into this stage
         }
         mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);       // one arrival per epilogue warp
         mbar_init_fence();
-        tma_prefetch_desc(&g.a);
-        tma_prefetch_desc(&g.b);
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
@@ -305,93 +365,122 @@ ozaki_gemm_kernel(const __grid_constant__ OzakiBatch batch) {
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int s = kb % kOzStages;
-                oz_wait(&empty[s], (((unsigned)(kb / kOzStages)) & 1u) ^ 1u, 0);   // first round: passes at once
-                unsigned char* a_tiles = smem + s * kStage;
-                unsigned char* b_tiles = a_tiles + S * kOzATile;
-                mbar_expect_tx(&full[s], (unsigned)kStage);
+            unsigned kbg = 0;   // k-blocks issued so far by this CTA: ring position and phase
+            OzSchedule<CL> sched(n_tiles, cta_rank);
+            for (int tile = sched.next(); tile >= 0; tile = sched.next()) {
+                const OzTile t = oz_decode_tile<CL>(batch, tile);
+                const OzakiProblem& g = batch.p[t.pi];
+                for (int kb = 0; kb < t.n_kb; ++kb, ++kbg) {
+                    const unsigned s = kbg % kOzStages;
+                    oz_wait(&empty[s], ((kbg / kOzStages) & 1u) ^ 1u, 0);   // first round: passes at once
+                    unsigned char* a_tiles = smem + s * kStage;
+                    unsigned char* b_tiles = a_tiles + S * kOzATile;
+                    mbar_expect_tx(&full[s], (unsigned)kStage);
 #pragma unroll
-                for (int p = 0; p < S; ++p) {
-                    if (CL == 1)
-                        tma_load_3d(a_tiles + p * kOzATile, &g.a, kb * kOzBK, m0, p, &full[s]);
-                    else
-                        tma_load_3d_mc(a_tiles + p * kOzATile + cta_rank * kARows * kOzBK, &g.a, kb * kOzBK,
-                                       m0 + cta_rank * kARows, p, &full[s], kClMask);
-                    tma_load_3d(b_tiles + p * kOzBTile, &g.b, kb * kOzBK, n0, p, &full[s]);
+                    for (int p = 0; p < S; ++p) {
+                        if (CL == 1)
+                            tma_load_3d(a_tiles + p * kOzATile, &g.a, kb * kOzBK, t.m0, p, &full[s]);
+                        else
+                            tma_load_3d_mc(a_tiles + p * kOzATile + cta_rank * kARows * kOzBK, &g.a, kb * kOzBK,
+                                           t.m0 + cta_rank * kARows, p, &full[s], kClMask);
+                        tma_load_3d(b_tiles + p * kOzBTile, &g.b, kb * kOzBK, t.n0, p, &full[s]);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int s = kb % kOzStages;
-                oz_wait(&full[s], ((unsigned)(kb / kOzStages)) & 1u, 1);
+            unsigned kbg = 0, done = 0;
+            OzSchedule<CL> sched(n_tiles, cta_rank);
+            for (int tile = sched.next(); tile >= 0; tile = sched.next(), ++done) {
+                const OzTile t = oz_decode_tile<CL>(batch, tile);
+                oz_wait(tmem_empty, (done & 1u) ^ 1u, 3);   // the epilogue has drained the previous tile's accumulators
                 tc_fence_after();
-                const unsigned char* a_tiles = smem + s * kStage;
-                const unsigned char* b_tiles = a_tiles + S * kOzATile;
-                const uint64_t a0 = umma_desc_k_sw64(a_tiles), b0 = umma_desc_k_sw64(b_tiles);
+                for (int kb = 0; kb < t.n_kb; ++kb, ++kbg) {
+                    const unsigned s = kbg % kOzStages;
+                    oz_wait(&full[s], (kbg / kOzStages) & 1u, 1);
+                    tc_fence_after();
+                    const unsigned char* a_tiles = smem + s * kStage;
+                    const unsigned char* b_tiles = a_tiles + S * kOzATile;
+                    const uint64_t a0 = umma_desc_k_sw64(a_tiles), b0 = umma_desc_k_sw64(b_tiles);
 #ifndef SURFH_OZ_TEST_NO_MMA
 #pragma unroll
-                for (int ks = 0; ks < kOzBK / 32; ++ks) {
+                    for (int ks = 0; ks < kOzBK / 32; ++ks) {
 #pragma unroll
-                    for (int p = 0; p < S; ++p) {
-                        // A digit p meets the B digits q = 0 .. S-1-p, whose products belong to the levels p .. S-1:
-                        // CONSECUTIVE 64-column accumulators.  The digit tiles of B are consecutive in shared memory
-                        // (64 rows x 64 bytes each, i.e. one tall K-major matrix), so up to four of them are ONE
-                        // instruction of N = 256: the A tile is read from shared memory once per four products
-                        // (an N = 64 instruction is bound by the 128 B/clk shared-memory port, not by the tensor pipe)
-                        const uint64_t ad = a0 + (uint64_t)((p * kOzATile + ks * 32) >> 4);
+                        for (int p = 0; p < S; ++p) {
+                            // A digit p meets the B digits q = 0 .. S-1-p, whose products belong to the levels p .. S-1:
+                            // CONSECUTIVE 64-column accumulators.  The digit tiles of B are consecutive in shared memory
+                            // (64 rows x 64 bytes each, i.e. one tall K-major matrix), so up to four of them are ONE
+                            // instruction of N = 256: the A tile is read from shared memory once per four products
+                            // (an N = 64 instruction is bound by the 128 B/clk shared-memory port, not by the tensor pipe)
+                            const uint64_t ad = a0 + (uint64_t)((p * kOzATile + ks * 32) >> 4);
 #pragma unroll
-                        for (int q0 = 0; q0 < S - p; q0 += 4) {
-                            const int cnt = (S - p - q0) < 4 ? (S - p - q0) : 4;
-                            const uint64_t bd = b0 + (uint64_t)((q0 * kOzBTile + ks * 32) >> 4);
-                            const unsigned acc = (kb > 0 || ks > 0 || p > 0) ? 1u : 0u;   // the p = 0 products open every level
-                            tc_mma_i8(tmem_base + (unsigned)((p + q0) * kOzBN), ad, bd, oz_idesc(cnt * kOzBN), acc);
+                            for (int q0 = 0; q0 < S - p; q0 += 4) {
+                                const int cnt = (S - p - q0) < 4 ? (S - p - q0) : 4;
+                                const uint64_t bd = b0 + (uint64_t)((q0 * kOzBTile + ks * 32) >> 4);
+                                const unsigned acc = (kb > 0 || ks > 0 || p > 0) ? 1u : 0u;   // the p = 0 products open every level
+                                tc_mma_i8(tmem_base + (unsigned)((p + q0) * kOzBN), ad, bd, oz_idesc(cnt * kOzBN), acc);
+                            }
                         }
                     }
-                }
 #endif
-                // the stage is free once these MMAs have read it -- in every CTA of the cluster
-                if (CL == 1) tc_commit(&empty[s]); else tc_commit_mc(&empty[s], kClMask);
-                if (kb == n_kb - 1) tc_commit(tmem_full);   // ... and the accumulators are final
+                    // the stage is free once these MMAs have read it -- in every CTA of the cluster
+                    if (CL == 1) tc_commit(&empty[s]); else tc_commit_mc(&empty[s], kClMask);
+                    if (kb == t.n_kb - 1) tc_commit(tmem_full);   // ... and the accumulators are final
+                }
             }
         }
     } else {
         // ---- epilogue: warp w owns tensor-memory lanes 32 (w % 4) .. + 31 = rows of the tile ---------------
         const int quad = warp & 3;
-        oz_wait(tmem_full, 0u, 2);
-        tc_fence_after();
-        const int m = m0 + quad * 32 + lane;
-        const bool m_ok = m < g.M;
-        const double sa = m_ok ? __ldg(g.sa + m) : 0.0;
-        const int32_t cm = m_ok ? __ldg(g.cM + m) : 0;
         const unsigned lane_base = tmem_base + ((unsigned)(quad * 32) << 16);
+        unsigned done = 0;
+        OzSchedule<CL> sched(n_tiles, cta_rank);
+        for (int tile = sched.next(); tile >= 0; tile = sched.next(), ++done) {
+            const OzTile t = oz_decode_tile<CL>(batch, tile);
+            const OzakiProblem& g = batch.p[t.pi];
+            const int m = t.m0 + quad * 32 + lane;
+            const bool m_ok = m < g.M;
+            const double sa = m_ok ? __ldg(g.sa + m) : 0.0;
+            const int32_t cm = m_ok ? __ldg(g.cM + m) : 0;
+            const bool dump = batch.dump != nullptr && tile == 0;
+            oz_wait(tmem_full, done & 1u, 2);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < kOzBN / 16; ++c) {
-            double acc[16];
+            for (int c = 0; c < kOzBN / 8; ++c) {
+                // all S levels of 8 columns in flight, one wait
+                uint32_t v[S][8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = 0.0;
-#pragma unroll
-            for (int t = S - 1; t >= 0; --t) {
-                uint32_t v[16];
-                tmem_ld16(lane_base + (unsigned)(t * kOzBN + c * 16), v);
+                for (int lv = 0; lv < S; ++lv) tmem_ld8(lane_base + (unsigned)(lv * kOzBN + c * 8), v[lv]);
                 tmem_ld_wait();
-                if (batch.dump != nullptr && blockIdx.x == 0) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) batch.dump[((size_t)t * kOzBM + quad * 32 + lane) * kOzBN + c * 16 + j] = (int32_t)v[j];
+                if (c == kOzBN / 8 - 1) {   // the accumulators are in registers: the next tile's products may start
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
                 }
+                if (dump) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.0078125, (double)(int32_t)v[j]);   // Horner in 2^-7
-            }
+                    for (int lv = 0; lv < S; ++lv)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = n0 + c * 16 + j;
-                if (m_ok && n < g.N) static_cast<TOut*>(g.C)[(size_t)cm + __ldg(g.cN + n)] = (TOut)(acc[j] * sa * __ldg(g.sb + n));
+                        for (int j = 0; j < 8; ++j)
+                            batch.dump[((size_t)lv * kOzBM + quad * 32 + lane) * kOzBN + c * 8 + j] = (int32_t)v[lv][j];
+                }
+                double acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = (double)(int32_t)v[S - 1][j];
+#pragma unroll
+                for (int lv = S - 2; lv >= 0; --lv)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fma(acc[j], 0.0078125, (double)(int32_t)v[lv][j]);   // Horner in 2^-7
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = t.n0 + c * 8 + j;
+                    if (m_ok && n < g.N) static_cast<TOut*>(g.C)[(size_t)cm + __ldg(g.cN + n)] = (TOut)(acc[j] * sa * __ldg(g.sb + n));
+                }
             }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still signal its barriers
     if (warp == 1) {

@@ -132,9 +132,11 @@ static void run(int M, int N, int K, int reps) {
     g.M = M; g.N = N; g.K = K; g.sa = dsa; g.sb = dsb; g.C = dC; g.cM = dcM; g.cN = dcN;
     batch.dump = ddump;
     CK(cudaFuncSetAttribute(ozaki_gemm_kernel<S, CL, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ozaki_smem_bytes(S)));
+    const int resident = ozaki_max_resident_ctas(ozaki_gemm_kernel<S, CL, double>, CL, ozaki_smem_bytes(S));
+    std::printf("persistent grid: %d co-resident CTAs for %d tiles\n", resident, batch.tile_start[1]);
     auto launch = [&]() {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(batch.tile_start[1]);
+        cfg.gridDim = dim3(resident > 0 && resident < batch.tile_start[1] ? resident : batch.tile_start[1]);
         cfg.blockDim = dim3(kOzThreads);
         cfg.dynamicSmemBytes = ozaki_smem_bytes(S);
         cudaLaunchAttribute at[1];
