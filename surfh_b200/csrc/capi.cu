@@ -146,6 +146,7 @@ template <typename T> struct BandT {
     // int8-sliced tcgen05 contraction (kernels_ozaki.cuh): digit planes [S][rows][pitch] + per-row scales of the LSF
     // and its transpose (cut once), of the slit-space vector G and of the K-fast detector block (cut per call)
     DevBuf oz_w, oz_wt, oz_g, oz_yk, oz_sw, oz_swt, oz_sg, oz_syk;
+    DevBuf oz_mask_w, oz_mask_wt;       // per 128 x 64 tile of the LSF / its transpose: which digits are not all zero
     int oz_kq = 0, oz_ndq = 0;          // digit row pitches: KB / nd rounded up to 16 bytes
     CUtensorMap ozmap_w, ozmap_g, ozmap_wt, ozmap_yk;
     bool oz_ready = false;
@@ -693,7 +694,7 @@ template <typename T> struct ModelImpl : surfh_model {
                     y_internal.bytes + x_stage.bytes + y_stage.bytes + dbl_stage.bytes;
         for (auto& b : bands)
             t += b->lsf.bytes + b->lsf_t.bytes + b->yk.bytes + b->G.bytes + b->grid_base.bytes + b->grid_frac.bytes +
-                 b->oz_w.bytes + b->oz_wt.bytes + b->oz_g.bytes + b->oz_yk.bytes +
+                 b->oz_w.bytes + b->oz_wt.bytes + b->oz_g.bytes + b->oz_yk.bytes + b->oz_mask_w.bytes + b->oz_mask_wt.bytes +
                  b->csr_col[0].bytes + b->csr_val[0].bytes + b->csr_col[1].bytes + b->csr_val[1].bytes;
         return t + precond_inv.bytes;
     }
@@ -879,6 +880,16 @@ template <typename T> struct ModelImpl : surfh_model {
             jobs.add(b.lsf_t.template as<T>(), b.KB, b.nd, (size_t)b.ndp, b.oz_wt, b.oz_ndq, b.oz_swt);
             jobs.template launch<decltype(s_)::value>(0);
         });
+        // the response decays away from its peak: its leading digits vanish outside a band, those tiles are skipped
+        b.oz_mask_w.alloc((size_t)ceil_div(b.nd, kOzBM) * ceil_div(b.KB, kOzBK));
+        b.oz_mask_wt.alloc((size_t)ceil_div(b.KB, kOzBM) * ceil_div(b.nd, kOzBK));
+        with_digits([&](auto s_) {
+            constexpr int SS = decltype(s_)::value;
+            ozaki_tile_mask_kernel<SS><<<dim3(ceil_div(b.KB, kOzBK), ceil_div(b.nd, kOzBM)), 128>>>(
+                b.oz_w.template as<int8_t>(), b.nd, b.KB, b.oz_kq, b.oz_mask_w.template as<uint8_t>());
+            ozaki_tile_mask_kernel<SS><<<dim3(ceil_div(b.nd, kOzBK), ceil_div(b.KB, kOzBM)), 128>>>(
+                b.oz_wt.template as<int8_t>(), b.KB, b.nd, b.oz_ndq, b.oz_mask_wt.template as<uint8_t>());
+        });
         SURFH_CUDA(cudaGetLastError());
         SURFH_CUDA(cudaDeviceSynchronize());
         b.ozmap_w = tensor_map_digits(b.oz_w.p, b.KB, b.nd, b.oz_kq, S, kOzBM / kOzCluster);
@@ -888,6 +899,7 @@ template <typename T> struct ModelImpl : surfh_model {
         b.oz_ready = true;
     }
     int oz_resident_ctas = 0;   // one wave of co-resident clusters: the persistent contraction's grid
+    bool oz_skip_zero_tiles = !(std::getenv("SURFH_OZAKI_DENSE") && std::atoi(std::getenv("SURFH_OZAKI_DENSE")) == 1);   // A/B switch
     void set_ozaki_attributes() {
         with_digits([&](auto s_) {
             constexpr int SS = decltype(s_)::value;
@@ -949,10 +961,12 @@ template <typename T> struct ModelImpl : surfh_model {
                 if (!adjoint) {   // y = W . G
                     g.a = b.ozmap_w; g.b = b.ozmap_g; g.M = b.nd; g.N = b.Nn; g.K = b.KB;
                     g.sa = b.oz_sw.template as<double>(); g.sb = b.oz_sg.template as<double>();
+                    g.amask = oz_skip_zero_tiles ? b.oz_mask_w.template as<uint8_t>() : nullptr;
                     g.C = y + b.out_offset; g.cM = b.t_yM.template as<int32_t>(); g.cN = b.t_yN.template as<int32_t>();
                 } else {          // Gt = Wt . Yk
                     g.a = b.ozmap_wt; g.b = b.ozmap_yk; g.M = b.KB; g.N = b.Nn; g.K = b.nd;
                     g.sa = b.oz_swt.template as<double>(); g.sb = b.oz_syk.template as<double>();
+                    g.amask = oz_skip_zero_tiles ? b.oz_mask_wt.template as<uint8_t>() : nullptr;
                     g.C = b.G.p; g.cM = b.t_ident.template as<int32_t>(); g.cN = b.t_gN.template as<int32_t>();
                 }
                 const int tiles_n = ceil_div(ceil_div(g.N, kOzBN), kOzCluster) * kOzCluster;

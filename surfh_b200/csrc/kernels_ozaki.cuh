@@ -59,6 +59,7 @@ struct OzakiProblem {
     int M, N, K;
     const double* sa;        // [M] 2^(eA - 6)
     const double* sb;        // [N] 2^(eB - 6)
+    const uint8_t* amask;    // [ceil(M / 128)][ceil(K / 64)] or NULL: bit p set = digit p of that A tile is not all zero
     void* C;                 // C(m, n) at C[cM[m] + cN[n]], elements of the kernel's output type
     const int32_t* cM;
     const int32_t* cN;
@@ -183,6 +184,32 @@ ozaki_slice_rows_kernel(const __grid_constant__ OzSliceBatch batch) {
 #pragma unroll
         for (int p = 0; p < S; ++p) *reinterpret_cast<uint32_t*>(drow + (size_t)p * plane + k0) = word[p];
     }
+}
+
+// Which digit tiles of a constant operand are entirely zero?  The line-spread function decays away from its peak, so its
+// leading digits vanish outside a band around the diagonal: digit 0 is non-zero in 12-28 % of the 128 x 64 tiles of the
+// MRS responses, digit 1 in 40-55 %.  The product skips the loads and the instructions of those tiles.  One CTA per
+// tile (grid: k-blocks x row tiles, 128 threads = rows); k-block 0 is always marked dense (its products open the
+// accumulators).
+template <int S>
+__global__ void __launch_bounds__(128)
+ozaki_tile_mask_kernel(const int8_t* __restrict__ digits, int rows, int K, int Kp, uint8_t* __restrict__ mask) {
+    const int kb = blockIdx.x, mt = blockIdx.y, row = mt * kOzBM + threadIdx.x;
+    unsigned bits = 0;
+    if (row < rows) {
+        const int k0 = kb * kOzBK, k1 = min(K, k0 + kOzBK);
+#pragma unroll
+        for (int p = 0; p < S; ++p) {
+            const int8_t* d = digits + ((size_t)p * rows + row) * Kp;
+            bool any = false;
+            for (int k = k0; k < k1; k += 4) any = any || *reinterpret_cast<const uint32_t*>(d + k) != 0u;   // Kp % 16 == 0, pad = 0
+            bits |= any ? (1u << p) : 0u;
+        }
+    }
+    unsigned all = 0;
+#pragma unroll
+    for (int p = 0; p < S; ++p) all |= __syncthreads_or((bits >> p) & 1u) ? (1u << p) : 0u;
+    if (threadIdx.x == 0) mask[(size_t)mt * gridDim.x + kb] = (uint8_t)(kb == 0 ? (1u << S) - 1u : all);
 }
 
 // ---- tcgen05 / TMEM / TMA wrappers --------------------------------------------------------------------------
@@ -375,14 +402,19 @@ ozaki_gemm_kernel(const __grid_constant__ OzakiBatch batch) {
                     oz_wait(&empty[s], ((kbg / kOzStages) & 1u) ^ 1u, 0);   // first round: passes at once
                     unsigned char* a_tiles = smem + s * kStage;
                     unsigned char* b_tiles = a_tiles + S * kOzATile;
-                    mbar_expect_tx(&full[s], (unsigned)kStage);
+                    // digit tiles of A that are all zero are neither loaded nor multiplied (same mask in every CTA
+                    // of the cluster: they share the row tile)
+                    const unsigned present = g.amask ? __ldg(g.amask + (size_t)(t.m0 / kOzBM) * t.n_kb + kb) : 0xffu;
+                    mbar_expect_tx(&full[s], (unsigned)(S * kOzBTile + __popc(present & ((1u << S) - 1u)) * kOzATile));
 #pragma unroll
                     for (int p = 0; p < S; ++p) {
-                        if (CL == 1)
-                            tma_load_3d(a_tiles + p * kOzATile, &g.a, kb * kOzBK, t.m0, p, &full[s]);
-                        else
-                            tma_load_3d_mc(a_tiles + p * kOzATile + cta_rank * kARows * kOzBK, &g.a, kb * kOzBK,
-                                           t.m0 + cta_rank * kARows, p, &full[s], kClMask);
+                        if (present & (1u << p)) {
+                            if (CL == 1)
+                                tma_load_3d(a_tiles + p * kOzATile, &g.a, kb * kOzBK, t.m0, p, &full[s]);
+                            else
+                                tma_load_3d_mc(a_tiles + p * kOzATile + cta_rank * kARows * kOzBK, &g.a, kb * kOzBK,
+                                               t.m0 + cta_rank * kARows, p, &full[s], kClMask);
+                        }
                         tma_load_3d(b_tiles + p * kOzBTile, &g.b, kb * kOzBK, t.n0, p, &full[s]);
                     }
                 }
@@ -394,6 +426,8 @@ ozaki_gemm_kernel(const __grid_constant__ OzakiBatch batch) {
             OzSchedule<CL> sched(n_tiles, cta_rank);
             for (int tile = sched.next(); tile >= 0; tile = sched.next(), ++done) {
                 const OzTile t = oz_decode_tile<CL>(batch, tile);
+                const uint8_t* amask = batch.p[t.pi].amask;
+                if (amask) amask += (size_t)(t.m0 / kOzBM) * t.n_kb;
                 oz_wait(tmem_empty, (done & 1u) ^ 1u, 3);   // the epilogue has drained the previous tile's accumulators
                 tc_fence_after();
                 for (int kb = 0; kb < t.n_kb; ++kb, ++kbg) {
@@ -403,11 +437,13 @@ ozaki_gemm_kernel(const __grid_constant__ OzakiBatch batch) {
                     const unsigned char* a_tiles = smem + s * kStage;
                     const unsigned char* b_tiles = a_tiles + S * kOzATile;
                     const uint64_t a0 = umma_desc_k_sw64(a_tiles), b0 = umma_desc_k_sw64(b_tiles);
+                    const unsigned present = amask ? __ldg(amask + kb) : 0xffu;   // k-block 0 is always dense
 #ifndef SURFH_OZ_TEST_NO_MMA
 #pragma unroll
                     for (int ks = 0; ks < kOzBK / 32; ++ks) {
 #pragma unroll
                         for (int p = 0; p < S; ++p) {
+                            if (!(present & (1u << p))) continue;
                             // A digit p meets the B digits q = 0 .. S-1-p, whose products belong to the levels p .. S-1:
                             // CONSECUTIVE 64-column accumulators.  The digit tiles of B are consecutive in shared memory
                             // (64 rows x 64 bytes each, i.e. one tall K-major matrix), so up to four of them are ONE

@@ -129,6 +129,19 @@ static void run(int M, int N, int K, int reps) {
     OzakiProblem& g = batch.p[0];
     g.a = digits_map(dAd, K, M, Kp, S, kOzBM / CL);
     g.b = digits_map(dBd, K, N, Kp, S, kOzBN);
+    uint8_t* dmask = nullptr;
+    const int m_tiles = (M + kOzBM - 1) / kOzBM, n_kb = (K + kOzBK - 1) / kOzBK;
+    if (!std::getenv("OZ_NOMASK")) {
+        CK(cudaMalloc(&dmask, (size_t)m_tiles * n_kb));
+        ozaki_tile_mask_kernel<S><<<dim3(n_kb, m_tiles), 128>>>(dAd, M, K, Kp, dmask);
+        CK(cudaDeviceSynchronize());
+        std::vector<uint8_t> hm((size_t)m_tiles * n_kb);
+        CK(cudaMemcpy(hm.data(), dmask, hm.size(), cudaMemcpyDeviceToHost));
+        long long present = 0;
+        for (uint8_t b : hm) present += __builtin_popcount(b);
+        std::printf("A digit tiles present: %.1f %% of %lld\n", 100.0 * present / ((double)hm.size() * S), (long long)hm.size() * S);
+    }
+    g.amask = dmask;
     g.M = M; g.N = N; g.K = K; g.sa = dsa; g.sb = dsb; g.C = dC; g.cM = dcM; g.cN = dcN;
     batch.dump = ddump;
     CK(cudaFuncSetAttribute(ozaki_gemm_kernel<S, CL, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ozaki_smem_bytes(S)));
