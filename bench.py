@@ -536,10 +536,13 @@ def run_b200(args):
             products = digits * (digits + 1) // 2
             i8_peak, i8_src = measured_int8_peak()
             eq = s["flops"] / sec / 1e12 if sec > 0 else None
-            row.update(bound="tensor", unit="TFLOP/s", achieved=None if eq is None else eq * products, peak=i8_peak,
-                       peak_source=i8_src, digits=digits, int8_products=products, fp64_equivalent_tflops=eq,
-                       note="achieved / peak are int8 tensor operations (TOP/s); fp64_equivalent_tflops = the "
-                            "contraction's own 2 M N K flops over the same time")
+            executed = contraction.get("executed_fraction", 1.0)
+            row.update(bound="tensor", unit="TFLOP/s", achieved=None if eq is None else eq * products * executed, peak=i8_peak,
+                       peak_source=i8_src, digits=digits, int8_products=products, executed_fraction=executed,
+                       fp64_equivalent_tflops=eq,
+                       note="achieved / peak are int8 tensor operations actually executed (TOP/s; the all-zero digit "
+                            "tiles of the line-spread function are skipped: executed_fraction); fp64_equivalent_tflops = "
+                            "the contraction's own 2 M N K flops over the same time")
             if eq is not None:
                 row["frac"] = row["achieved"] / i8_peak
                 if fp_peak["tflops"]:

@@ -233,8 +233,11 @@ int64_t surfh_own_launch_count(surfh_handle h);
  * *mode 2 = int8-sliced error-free product on tcgen05 tensor cores with *digits int8 digits per operand (default:
  * 8 digits in fp64, 4 in fp32), 1 = FP64 DMMA fed by TMA, 0 = mma.sync kernels of round 1 (DMMA / 3xTF32), 3 = FFMA,
  * -1 = no band has a spectral response (beta-sum bands only).
+ * *executed_fraction (may be NULL): share of the S (S + 1) / 2 digit products per tile and k-block that is actually run --
+ * the leading digits of the line-spread function vanish outside a band around its peak and those all-zero tiles are
+ * skipped (SURFH_OZAKI_DENSE=1 runs them all); 1 for the other modes.
  * Selected per process by SURFH_F64_GEMM / SURFH_F32_GEMM / SURFH_OZAKI_DIGITS when the handle is created. */
-int surfh_contraction_info(surfh_handle h, int32_t* mode, int32_t* digits);
+int surfh_contraction_info(surfh_handle h, int32_t* mode, int32_t* digits, double* executed_fraction);
 /* per-stage CUDA-event timing of the calls made while enabled: enable, run, then read.
  * Output arrays of capacity `cap` (any may be NULL): stage name ("chirpz_*" = hand-written FFT passes,
  * "cufft_*" = library FFT), summed milliseconds, algorithmic bytes, flops and kernel launches.

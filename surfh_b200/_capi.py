@@ -110,7 +110,7 @@ def load() -> C.CDLL:
         "surfh_rfft2": (C.c_int, [i32, i32, i32, i32, i32, vp, vp, vp]),
         "surfh_launch_count": (i64, [vp]),
         "surfh_own_launch_count": (i64, [vp]),
-        "surfh_contraction_info": (C.c_int, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+        "surfh_contraction_info": (C.c_int, [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
         "surfh_profile_enable": (C.c_int, [vp, i32]),
         "surfh_profile_read": (C.c_int, [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
                                          C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),

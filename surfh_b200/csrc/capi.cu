@@ -78,7 +78,7 @@ struct surfh_model {
     virtual int64_t input_size() const = 0;
     virtual int64_t output_size() const = 0;
     virtual int64_t workspace_bytes() const = 0;
-    virtual void contraction_info(int32_t* mode, int32_t* digits) const = 0;
+    virtual void contraction_info(int32_t* mode, int32_t* digits, double* executed_fraction) const = 0;
     virtual void forward(const void* x, void* y, cudaStream_t st) = 0;
     virtual void adjoint(const void* y, void* x, int mode, cudaStream_t st) = 0;
     virtual void fwadj(const void* x, void* out, int mode, void* yscratch, cudaStream_t st) = 0;
@@ -699,7 +699,8 @@ template <typename T> struct ModelImpl : surfh_model {
         return t + precond_inv.bytes;
     }
 
-    void contraction_info(int32_t* mode, int32_t* digits) const override {
+    void contraction_info(int32_t* mode, int32_t* digits, double* executed_fraction) const override {
+        if (executed_fraction) *executed_fraction = 1.0;
         bool any_lsf = false;
         for (auto& b : bands) any_lsf = any_lsf || b->mode == SURFH_SPECTRAL_LSF;
         if (!any_lsf) {   // beta-sum bands only (MRSBlurred): there is no contraction
@@ -710,6 +711,8 @@ template <typename T> struct ModelImpl : surfh_model {
         const bool oz = ozaki_usable();
         if (mode) *mode = oz ? GEMM_OZAKI : (gemm_mode == GEMM_OZAKI ? (std::is_same<T, double>::value ? GEMM_TMA : GEMM_LEGACY) : gemm_mode);
         if (digits) *digits = oz ? ozaki_digits : 0;
+        if (executed_fraction && oz && oz_skip_zero_tiles && oz_products_dense > 0)
+            *executed_fraction = oz_products_executed / oz_products_dense;
     }
 
     // ---- launch helpers ---------------------------------------------------------------------
@@ -892,12 +895,25 @@ template <typename T> struct ModelImpl : surfh_model {
         });
         SURFH_CUDA(cudaGetLastError());
         SURFH_CUDA(cudaDeviceSynchronize());
+        {   // bookkeeping for surfh_contraction_info: digit products executed / of the dense scheme, both directions
+            const double tiles_n = ceil_div(ceil_div(b.Nn, kOzBN), kOzCluster) * kOzCluster;
+            for (DevBuf* mk : {&b.oz_mask_w, &b.oz_mask_wt}) {
+                std::vector<uint8_t> hm(mk->bytes);
+                SURFH_CUDA(cudaMemcpy(hm.data(), mk->p, mk->bytes, cudaMemcpyDeviceToHost));
+                for (uint8_t bits : hm) {
+                    for (int p = 0; p < S; ++p)
+                        if (bits & (1u << p)) oz_products_executed += tiles_n * (S - p);
+                    oz_products_dense += tiles_n * (S * (S + 1) / 2);
+                }
+            }
+        }
         b.ozmap_w = tensor_map_digits(b.oz_w.p, b.KB, b.nd, b.oz_kq, S, kOzBM / kOzCluster);
         b.ozmap_g = tensor_map_digits(b.oz_g.p, b.KB, b.Nn, b.oz_kq, S, kOzBN);
         b.ozmap_wt = tensor_map_digits(b.oz_wt.p, b.nd, b.KB, b.oz_ndq, S, kOzBM / kOzCluster);
         b.ozmap_yk = tensor_map_digits(b.oz_yk.p, b.nd, b.Nn, b.oz_ndq, S, kOzBN);
         b.oz_ready = true;
     }
+    double oz_products_executed = 0, oz_products_dense = 0;   // digit-tile products: with zero tiles skipped / dense
     int oz_resident_ctas = 0;   // one wave of co-resident clusters: the persistent contraction's grid
     bool oz_skip_zero_tiles = !(std::getenv("SURFH_OZAKI_DENSE") && std::atoi(std::getenv("SURFH_OZAKI_DENSE")) == 1);   // A/B switch
     void set_ozaki_attributes() {
@@ -1819,9 +1835,9 @@ int surfh_shepard(const float* alpha_coord, const float* lambda_coord, const flo
 int64_t surfh_launch_count(surfh_handle h) { return h ? h->launches : -1; }
 int64_t surfh_own_launch_count(surfh_handle h) { return h ? h->own_launches : -1; }
 
-int surfh_contraction_info(surfh_handle h, int32_t* mode, int32_t* digits) {
+int surfh_contraction_info(surfh_handle h, int32_t* mode, int32_t* digits, double* executed_fraction) {
     if (!h) return SURFH_EINVAL;
-    h->contraction_info(mode, digits);
+    h->contraction_info(mode, digits, executed_fraction);
     return SURFH_OK;
 }
 

@@ -16,8 +16,8 @@
 //     2^(eA-6) 2^(eB-6) * sum_t 2^(-7t) L_t,    L_t = sum_{p+q=t} sum_k dA_p[k] dB_q[k]
 // and every L_t is an exact integer: |L_t| <= (t+1) K 64^2 < 2^31 for K < 65536 / (t+1).  Levels t >= S are
 // dropped (they sit below the digits' own truncation).  S = 8 (36 int8 products) keeps 55 bits below every row's
-// maximum: the fp64 product to ~1e-14 (7 digits: ~1e-12); the accumulation itself has no rounding at all, which is why
-// the result is closer to the exact product than an fp64 FMA chain.  The fp32 operator uses S = 4 (27 bits, 10 products).
+// maximum: the fp64 product to 1e-15 ... 1e-14 depending on the rows' dynamic range (7 digits: ~1e-12); the accumulation
+// itself has no rounding at all (on the C4 operator the forward is closer to the oracle than the DMMA kernel's FMA chains).  The fp32 operator uses S = 4 (27 bits, 10 products).
 //
 // Kernel (one CTA = one 128 x 64 tile of C, 6 warps, one CTA per SM):
 //   warp 0 (one lane)  TMA producer: per 64-deep k-block, S + S `cp.async.bulk.tensor.3d` boxes (A digit p:

@@ -447,11 +447,14 @@ class spectroSigRLSCT(LinOp):
         return int(self._lib.surfh_own_launch_count(self._h))
 
     def contraction_info(self) -> dict:
-        """How the spectral response is evaluated: {'mode': 'ozaki_i8' | 'dmma_tma' | 'mma_sync' | 'simt' | 'none', 'digits': n}."""
+        """How the spectral response is evaluated: {'mode': 'ozaki_i8' | 'dmma_tma' | 'mma_sync' | 'simt' | 'none', 'digits': n,
+        'executed_fraction': share of the digit products that is run (all-zero digit tiles of the LSF are skipped)}."""
         import ctypes
-        mode, digits = ctypes.c_int32(0), ctypes.c_int32(0)
-        _capi.check(self._h, self._lib.surfh_contraction_info(self._h, ctypes.byref(mode), ctypes.byref(digits)))
-        return {"mode": {-1: "none", 0: "mma_sync", 1: "dmma_tma", 2: "ozaki_i8", 3: "simt"}[mode.value], "digits": int(digits.value)}
+        mode, digits, frac = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_double(1.0)
+        _capi.check(self._h, self._lib.surfh_contraction_info(self._h, ctypes.byref(mode), ctypes.byref(digits),
+                                                              ctypes.byref(frac)))
+        return {"mode": {-1: "none", 0: "mma_sync", 1: "dmma_tma", 2: "ozaki_i8", 3: "simt"}[mode.value],
+                "digits": int(digits.value), "executed_fraction": float(frac.value)}
 
     def workspace_bytes(self) -> int:
         return int(self._lib.surfh_workspace_bytes(self._h))

@@ -193,7 +193,8 @@ def test_contraction_backends_agree(built, monkeypatch):
     monkeypatch.delenv("SURFH_F64_GEMM", raising=False)
     monkeypatch.delenv("SURFH_OZAKI_DIGITS", raising=False)
     oz = built(**args, dtype="float64", adjoint_mode="exact")
-    assert oz.contraction_info() == {"mode": "ozaki_i8", "digits": 8}
+    info = oz.contraction_info()
+    assert (info["mode"], info["digits"]) == ("ozaki_i8", 8) and 0.3 < info["executed_fraction"] <= 1.0
     y_oz, x_oz = oz.forward(cfg.maps), oz.adjoint(v)
     monkeypatch.setenv("SURFH_F64_GEMM", "tma")
     dm = built(**args, dtype="float64", adjoint_mode="exact")
@@ -206,12 +207,12 @@ def test_contraction_backends_agree(built, monkeypatch):
     for digits, tol in ((7, 1e-11), (6, 1e-9)):
         monkeypatch.setenv("SURFH_OZAKI_DIGITS", str(digits))
         m = built(**args, dtype="float64", adjoint_mode="exact")
-        assert m.contraction_info() == {"mode": "ozaki_i8", "digits": digits}
+        assert m.contraction_info()["digits"] == digits
         assert rel(m.forward(cfg.maps), y_dm) <= tol and rel(m.adjoint(v), x_dm) <= tol
     monkeypatch.delenv("SURFH_OZAKI_DIGITS")
     monkeypatch.delenv("SURFH_F64_GEMM")
     f32 = built(**args, dtype="float32", adjoint_mode="exact")
-    assert f32.contraction_info() == {"mode": "ozaki_i8", "digits": 4}
+    assert (f32.contraction_info()["mode"], f32.contraction_info()["digits"]) == ("ozaki_i8", 4)
     assert rel(f32.forward(cfg.maps), y_dm) <= 1e-5 and rel(f32.adjoint(v), x_dm) <= 1e-5
     monkeypatch.setenv("SURFH_F32_GEMM", "tf32")
     t32 = built(**args, dtype="float32", adjoint_mode="exact")
