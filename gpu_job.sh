@@ -9,4 +9,3 @@ timeout 300 python bench.py --dtype float32 --no-cpu-baseline > gpurun_out/bench
 for c in c2 c3 c5; do
 timeout 300 python bench.py --config $c --no-cpu-baseline > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; tail -1 gpurun_out/bench_$c.err
 done
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:ozaki_gemm -s 2 -c 2 -o gpurun_out/r02_ozaki_gemm python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --solve-iters 0 > gpurun_out/ncu_oz.log 2>&1; tail -2 gpurun_out/ncu_oz.log
