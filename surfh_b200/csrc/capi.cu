@@ -914,6 +914,7 @@ template <typename T> struct ModelImpl : surfh_model {
         b.oz_ready = true;
     }
     double oz_products_executed = 0, oz_products_dense = 0;   // digit-tile products: with zero tiles skipped / dense
+    int oz_n_major_fwd = std::getenv("SURFH_OZAKI_MMAJOR") ? 0 : 1;   // A/B switch of the forward product's tile order
     int oz_resident_ctas = 0;   // one wave of co-resident clusters: the persistent contraction's grid
     bool oz_skip_zero_tiles = !(std::getenv("SURFH_OZAKI_DENSE") && std::atoi(std::getenv("SURFH_OZAKI_DENSE")) == 1);   // A/B switch
     void set_ozaki_attributes() {
@@ -976,11 +977,13 @@ template <typename T> struct ModelImpl : surfh_model {
                 OzakiProblem& g = batch.p[batch.count];
                 if (!adjoint) {   // y = W . G
                     g.a = b.ozmap_w; g.b = b.ozmap_g; g.M = b.nd; g.N = b.Nn; g.K = b.KB;
+                    g.n_major = oz_n_major_fwd;   // the LSF digits are the smaller operand: they are the ones re-read
                     g.sa = b.oz_sw.template as<double>(); g.sb = b.oz_sg.template as<double>();
                     g.amask = oz_skip_zero_tiles ? b.oz_mask_w.template as<uint8_t>() : nullptr;
                     g.C = y + b.out_offset; g.cM = b.t_yM.template as<int32_t>(); g.cN = b.t_yN.template as<int32_t>();
                 } else {          // Gt = Wt . Yk
                     g.a = b.ozmap_wt; g.b = b.ozmap_yk; g.M = b.KB; g.N = b.Nn; g.K = b.nd;
+                    g.n_major = 0;                // the detector block's digits are small: re-read per row tile
                     g.sa = b.oz_swt.template as<double>(); g.sb = b.oz_syk.template as<double>();
                     g.amask = oz_skip_zero_tiles ? b.oz_mask_wt.template as<uint8_t>() : nullptr;
                     g.C = b.G.p; g.cM = b.t_ident.template as<int32_t>(); g.cN = b.t_gN.template as<int32_t>();

@@ -57,6 +57,8 @@ struct OzakiProblem {
     CUtensorMap a;   // int8 digits of A: [S][M][Kp], dims {K, M, S}, box {64, 128 / CL, 1}, 64-byte swizzle
     CUtensorMap b;   // int8 digits of B: [S][N][Kp], box {64, 64, 1}
     int M, N, K;
+    int n_major;             // tile order: 0 = row tile outer (B re-traversed per row tile), 1 = column-tile cluster outer
+                             // (A re-traversed): pick the one that re-reads the SMALLER operand, it stays in L2
     const double* sa;        // [M] 2^(eA - 6)
     const double* sb;        // [N] 2^(eB - 6)
     const uint8_t* amask;    // [ceil(M / 128)][ceil(K / 64)] or NULL: bit p set = digit p of that A tile is not all zero
@@ -321,8 +323,14 @@ template <int CL> __device__ __forceinline__ OzTile oz_decode_tile(const OzakiBa
     const OzakiProblem& g = batch.p[t.pi];
     const int local_tile = tile - batch.tile_start[t.pi];
     const int tiles_n = ((g.N + kOzBN - 1) / kOzBN + CL - 1) / CL * CL;   // column tiles, padded to whole clusters
-    t.m0 = (local_tile / tiles_n) * kOzBM;
-    t.n0 = (local_tile % tiles_n) * kOzBN;
+    if (g.n_major) {
+        const int tiles_m = (g.M + kOzBM - 1) / kOzBM, group = local_tile / CL;       // group = (column cluster, row tile)
+        t.m0 = (group % tiles_m) * kOzBM;
+        t.n0 = ((group / tiles_m) * CL + local_tile % CL) * kOzBN;
+    } else {
+        t.m0 = (local_tile / tiles_n) * kOzBM;
+        t.n0 = (local_tile % tiles_n) * kOzBN;
+    }
     t.n_kb = (g.K + kOzBK - 1) / kOzBK;
     return t;
 }
