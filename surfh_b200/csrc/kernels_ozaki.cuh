@@ -1,4 +1,4 @@
-// k4 / k4^T on the 5th-generation tensor cores (fp64 operator): the spectral response as an error-free
+// k4 / k4^T on the 5th-generation tensor cores (both dtypes): the spectral response as an error-free
 // integer-sliced ("Ozaki scheme") product on tcgen05.mma kind::i8 with int32 accumulators in tensor memory.
 //
 //   forward   y[m, n]  = sum_k W [m, k]  * G [n, k]     m = detector wavelength l', k = (l, b), n = (p, s, a)
@@ -7,6 +7,7 @@
 // Replaces jax_utils.wblur_subSampling + the alpha decimation and jax_utils.wblur_t + np.repeat
 // (surfh/ToolsDir/jax_utils.py:72-91; surfh/Models/spectroModelChannel.py:229, 242-252), like kernels_gemm_tma.cuh,
 // whose DMMA kernel is bounded by the FP64 pipe (36 TFLOP/s on B200: tcgen05 has no f64 kind).
+// A numpy restatement of the arithmetic with its error bounds: oracle/surfh_oracle/ozaki.py, tests/test_oracle_ozaki.py.
 //
 // Arithmetic.  Every row x of an operand is written as
 //     x[k] = 2^(e-6) * sum_{p<S} d_p[k] * 2^(-7p),     d_p[k] integer, |d_p[k]| <= 64   (int8)
@@ -16,22 +17,29 @@
 //     2^(eA-6) 2^(eB-6) * sum_t 2^(-7t) L_t,    L_t = sum_{p+q=t} sum_k dA_p[k] dB_q[k]
 // and every L_t is an exact integer: |L_t| <= (t+1) K 64^2 < 2^31 for K < 65536 / (t+1).  Levels t >= S are
 // dropped (they sit below the digits' own truncation).  S = 8 (36 int8 products) keeps 55 bits below every row's
-// maximum: the fp64 product to 1e-15 ... 1e-14 depending on the rows' dynamic range (7 digits: ~1e-12); the accumulation
-// itself has no rounding at all (on the C4 operator the forward is closer to the oracle than the DMMA kernel's FMA chains).  The fp32 operator uses S = 4 (27 bits, 10 products).
+// maximum: the fp64 product to 1e-15 ... 1e-14 depending on the rows' dynamic range (7 digits: ~1e-12); the
+// accumulation itself has no rounding at all.  The fp32 operator uses S = 4 (27 bits, 10 products).
 //
-// Kernel (one CTA = one 128 x 64 tile of C, 6 warps, one CTA per SM):
+// Kernel: persistent, one CTA per SM (6 warps), clusters of CL CTAs; a CTA computes 128 x 64 tiles of C.
 //   warp 0 (one lane)  TMA producer: per 64-deep k-block, S + S `cp.async.bulk.tensor.3d` boxes (A digit p:
 //                      128 rows x 64 bytes, B digit q: 64 rows x 64 bytes, 64-byte swizzle) into a 2-stage ring,
-//                      completion by transaction bytes on the stage's `full` mbarrier;
+//                      completion by transaction bytes on the stage's `full` mbarrier; the CTAs of a cluster own
+//                      neighbouring column tiles and each multicasts 1 / CL of every A tile to the cluster; digit
+//                      tiles of A that are entirely zero (per-tile bit mask, see ozaki_tile_mask_kernel) are skipped;
+//                      the producer runs ahead into the next tile of the CTA's schedule;
 //   warp 1 (one lane)  MMA issuer: `tcgen05.mma.cta_group::1.kind::i8` (M 128, K 32); digit pair (p, q) accumulates
 //                      into the level-(p+q) accumulator = 64 columns of tensor memory (S x 64 <= 512 columns), and
-//                      one instruction of N = 256 covers A digit p against FOUR stacked B digits (four levels); `tcgen05.commit` releases the stage (`empty`) and, after the
-//                      last k-block, publishes the accumulators (`tmem_full`);
-//   warps 2-5          epilogue: `tcgen05.ld` 32 lanes x 16 columns per level, Horner sum of the levels in fp64,
-//                      the two power-of-two row scales, store through the two offset tables (the detector layout
-//                      [P,S,L',na] is the reference's; the slit-space layout is the gather / scatter kernels').
+//                      one instruction of N = 256 covers A digit p against FOUR stacked B digits (four levels);
+//                      `tcgen05.commit` (multicast to the cluster) releases the stage (`empty`) and, after the last
+//                      k-block, publishes the accumulators (`tmem_full`); `tmem_empty` (the epilogue has read them)
+//                      gates the next tile's first product;
+//   warps 2-5          epilogue: `tcgen05.ld` 32 lanes x 8 columns of all S levels at a time, Horner sum of the
+//                      levels in fp64, the two power-of-two row scales, store through the two offset tables (the
+//                      detector layout [P,S,L',na] is the reference's; the slit-space layout is the gather /
+//                      scatter kernels').
 // Loading all S digits of both operands once per k-block and running the S(S+1)/2 products out of shared memory
-// is what keeps the L2 -> SM traffic (12 KB x S per 1792 tensor cycles) under the L2 throughput cap.
+// keeps the L2 -> SM traffic at 12 KB x S per 1792 tensor cycles (8 KB x S with the A multicast); that feed, not the
+// tensor pipe, is what bounds the kernel (profiles/r02_ozaki.md).
 #pragma once
 #include <cuda.h>
 
