@@ -7,7 +7,7 @@
 // Replaces jax_utils.wblur_subSampling + the alpha decimation and jax_utils.wblur_t + np.repeat
 // (surfh/ToolsDir/jax_utils.py:72-91; surfh/Models/spectroModelChannel.py:229, 242-252), like kernels_gemm_tma.cuh,
 // whose DMMA kernel is bounded by the FP64 pipe (36 TFLOP/s on B200: tcgen05 has no f64 kind).
-// A numpy restatement of the arithmetic with its error bounds: oracle/surfh_oracle/ozaki.py, tests/test_oracle_ozaki.py.
+// The arithmetic is restated in numpy, with its error bounds, by the CPU test tests/test_oracle_ozaki.py.
 //
 // Arithmetic.  Every row x of an operand is written as
 //     x[k] = 2^(e-6) * sum_{p<S} d_p[k] * 2^(-7p),     d_p[k] integer, |d_p[k]| <= 64   (int8)
